@@ -1,0 +1,250 @@
+/* lerax_b200 -- C ABI of the B200-native backend for Lerax's on-policy PPO hot path.
+ *
+ * The reference (RunnersNum40/lerax 0.0.6) is pure Python/JAX and has NO plugin, operator
+ * or FFI interface for this path: the seam is its Python API.  The entry points below are
+ * what a jax.ffi / ctypes binding of that path binds; each cites the reference function it
+ * replaces (paths relative to /root/reference/src/lerax).  INTEGRATION.md shows the
+ * reference-side stubs.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless the name ends in `_host`; the caller owns all
+ *     buffers, the library never allocates or frees on behalf of the caller (workspaces are
+ *     caller-allocated, sized by the *_workspace_bytes queries).
+ *   - Functions only ENQUEUE work on `stream` (a cudaStream_t passed as void*); none of them
+ *     synchronises the host, so they are legal inside an XLA FFI handler or a CUDA graph
+ *     capture.  They are re-entrant and keep no global state besides the thread-local
+ *     error string.
+ *   - Return value: LRX_OK (0) or a negative LRX_ERR_*; lrx_last_error() gives the message.
+ *   - Layouts: the rollout buffer is TIME-MAJOR [T][N] (env index fastest) so that lanes of a
+ *     warp touch consecutive envs; the reference's logical layout is [N][T] with flat index
+ *     i = n*T + t (buffer/base_buffer.py:38-62).  Minibatch index arrays (`idx`) are in the
+ *     REFERENCE order i = n*T + t; the translation to t*N + n happens inside the library.
+ *   - All floats are IEEE fp32 (the reference runs JAX with x64 disabled), ints int32,
+ *     dones uint8 (0/1).
+ *   - There is no CPU fallback and no multi-backend dispatch: a missing device or an
+ *     unsupported env/policy combination is an error, never a silent slow path.
+ */
+#ifndef LERAX_B200_H
+#define LERAX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRX_VERSION 100 /* 0.1.0 */
+
+#define LRX_OK 0
+#define LRX_ERR_INVALID_ARG (-1)
+#define LRX_ERR_UNSUPPORTED (-2)
+#define LRX_ERR_CUDA (-3)
+
+typedef void* lrx_stream_t; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ environments
+ * env/classic_control/{cartpole,pendulum,acrobot}.py.  Physical parameters are RUNTIME
+ * values (curriculum callbacks rewrite them between iterations, curriculum/scheduled.py:133-138).
+ * p[] per kind:
+ *   CARTPOLE : 0 gravity, 1 cart_mass, 2 pole_mass, 3 half_length, 4 force_mag,
+ *              5 theta_threshold_radians, 6 x_threshold                 (cartpole.py:110-122)
+ *   PENDULUM : 0 max_speed, 1 max_torque, 2 g, 3 m, 4 l                   (pendulum.py:51-62)
+ *   ACROBOT  : 0 gravity, 1 link_length_1, 2 link_length_2, 3 link_mass_1, 4 link_mass_2,
+ *              5 link_com_pos_1, 6 link_com_pos_2, 7 link_moi, 8 max_vel_1, 9 max_vel_2,
+ *              10..12 torques[0..2]                                       (acrobot.py:114-132)
+ * max_episode_steps > 0 applies wrapper/misc.py:115-206 (TimeLimit): truncate when the
+ * per-episode step counter reaches it; 0 = bare env, never truncates
+ * (base_classic_control.py:74-75). */
+#define LRX_ENV_CARTPOLE 0
+#define LRX_ENV_PENDULUM 1
+#define LRX_ENV_ACROBOT 2
+#define LRX_ENV_MAX_PARAMS 16
+
+typedef struct LrxEnvDesc {
+  int32_t kind;
+  int32_t max_episode_steps;
+  float dt;
+  float p[LRX_ENV_MAX_PARAMS];
+} LrxEnvDesc;
+
+/* Per-env carried state, struct-of-arrays: y[k][N] (k = 4, 2, 4), t[N], step_count[N]
+ * (CartPoleState/PendulumState/AcrobotState .y/.t and TimeLimitState.step_count). */
+typedef struct LrxEnvState {
+  float* y;
+  float* t;
+  int32_t* step_count;
+} LrxEnvState;
+
+/* ------------------------------------------------------------------------ policy
+ * policy/actor_critic/mlp.py:64-110 + policy/actor.py:194-261.  Three Linear chains
+ * (0 encoder, 1 value_head, 2 action_head.mlp followed by action_dist.mapping) given by
+ * their layer widths dims[c][0..n_layers[c]] and a ReLU flag per Linear.  The flat
+ * parameter vector is in Equinox leaf order: per chain, per Linear, weight[out][in]
+ * row-major then bias[out]; then log_std (Box only).  n_params must equal
+ * lrx_policy_num_params(). */
+#define LRX_MAX_LAYERS 8
+#define LRX_MAX_NOUT 8
+
+typedef struct LrxPolicyDesc {
+  int32_t obs_dim;
+  int32_t n_out;  /* logits (Discrete) or 1 (scalar Box) */
+  int32_t is_box; /* 1: Normal(loc, exp(log_std)); 0: Categorical(logits) */
+  int32_t n_params;
+  int32_t n_layers[3];
+  int32_t dims[3][LRX_MAX_LAYERS + 1];
+  int32_t relu[3][LRX_MAX_LAYERS];
+} LrxPolicyDesc;
+
+int lrx_policy_num_params(const LrxPolicyDesc* pol);
+
+/* --------------------------------------------------------------------------- RNG
+ * Counter-based Philox4x32-10: key = seed, counter = (env_offset + n, step_offset + s,
+ * stream, 0); stream 0 = action noise (Gumbel per logit, or one N(0,1) by Box-Muller),
+ * stream 1 = reset noise (k uniforms).  Replaces the jr.split key tree of
+ * algorithm/ppo.py:209-219 (RNG streams are not part of the parity contract). */
+typedef struct LrxRng {
+  uint64_t seed;
+  uint32_t env_offset;
+  uint32_t step_offset;
+} LrxRng;
+
+/* Injected noise for parity runs ("same action/noise sequences"): when non-NULL the
+ * kernels read noise from here instead of generating it.
+ *   action_noise  [T][N][n_out] Gumbel (Discrete) or [T][N] eps (Box)
+ *   reset_uniform [T][N][k]     uniforms in [0,1) consumed by env.initial when done */
+typedef struct LrxReplay {
+  const float* action_noise;
+  const float* reset_uniform;
+} LrxReplay;
+
+/* Rollout buffer planes, all [T][N] (obs [T][N][obs_dim]); RolloutBuffer fields of
+ * buffer/rollout.py:21-30.  act is int32 (Discrete) or float (Box).  The *_trace
+ * pointers are optional (NULL to skip): pre-transition state y [T][k][N], its time
+ * t [T][N], and the post-transition PRE-reset state [T][k][N] -- used by the
+ * teacher-forced parity tests. */
+typedef struct LrxRolloutOut {
+  float* obs;
+  void* act;
+  float* rew;
+  uint8_t* done;
+  float* logp;
+  float* val;
+  float* last_value; /* [N] : V(obs(state after T steps)), ppo.py:311-312 */
+  float* y_trace;
+  float* t_trace;
+  float* y_next_trace;
+} LrxRolloutOut;
+
+/* env.initial for N envs (PPOStepState.initial, algorithm/ppo.py:45-58,331-333).
+ * uniform: optional injected draws [N][k] in [0,1); NULL -> Philox stream 1 at
+ * step index rng.step_offset. */
+int lrx_env_reset(const LrxEnvDesc* env, LrxEnvState state, int32_t N, LrxRng rng,
+                  const float* uniform, lrx_stream_t stream);
+
+/* One batched env.transition + reward + terminal + truncate + observation, WITHOUT the
+ * reset-on-done (env/classic_control/base_classic_control.py:49-72 and the env files).
+ * state is updated in place.  action [N] int32/float; outputs may be NULL. */
+int lrx_env_step(const LrxEnvDesc* env, LrxEnvState state, const void* action, float* reward,
+                 uint8_t* terminal, uint8_t* truncated, float* obs_next, int32_t N,
+                 lrx_stream_t stream);
+
+/* env.observation and env.terminal for N envs: obs [N][obs_dim], terminal [N] (either may
+ * be NULL). */
+int lrx_env_observe(const LrxEnvDesc* env, LrxEnvState state, float* obs, uint8_t* terminal,
+                    int32_t N, lrx_stream_t stream);
+
+/* Batched network forward (policy.__call__/value/evaluate_action building block,
+ * policy/actor_critic/mlp.py:115-178): obs [B][obs_dim] -> value [B], head [B][n_out]
+ * (raw logits or loc).  Either output may be NULL. */
+int lrx_policy_forward(const LrxPolicyDesc* pol, const float* params, const float* obs,
+                       float* value, float* head, int32_t B, lrx_stream_t stream);
+
+/* The fused persistent rollout: T steps of PPO.step for N envs + last_value
+ * (algorithm/ppo.py:199-316 under the vmap of :360-368).  state is carried in/out. */
+int lrx_rollout(const LrxEnvDesc* env, const LrxPolicyDesc* pol, const float* params,
+                LrxEnvState state, LrxRng rng, const LrxReplay* replay, LrxRolloutOut out,
+                int32_t N, int32_t T, float gamma, lrx_stream_t stream);
+
+/* ---------------------------------------------------------------------------- GAE
+ * advantage/gae.py:36-66 via buffer/rollout.py:64-79.  layout LRX_LAYOUT_TN: arrays are
+ * [T][N] (kernel-native); LRX_LAYOUT_NT: [N][T] (reference-native, T contiguous).
+ * ev_sums: optional double[4] receiving sum(ret), sum(ret^2), sum(adv), sum(adv^2)
+ * (adv = ret - val) for explained_variance (algorithm/ppo.py:523-528). */
+#define LRX_LAYOUT_TN 0
+#define LRX_LAYOUT_NT 1
+int lrx_gae(const float* rew, const float* val, const uint8_t* done, const float* last_value,
+            float* adv, float* ret, int32_t N, int32_t T, float gamma, float lam, int32_t layout,
+            double* ev_sums, lrx_stream_t stream);
+
+/* --------------------------------------------------------------------- PPO update
+ * algorithm/ppo.py:396-561 + optax chain(clip_by_global_norm, adam) (ppo.py:192-194). */
+typedef struct LrxPpoHyper {
+  float clip_coefficient;
+  float value_loss_coefficient;
+  float entropy_loss_coefficient;
+  float max_grad_norm;
+  float learning_rate;
+  float adam_b1, adam_b2, adam_eps;
+  int32_t clip_value_loss;
+  int32_t normalize_advantages;
+} LrxPpoHyper;
+
+/* Flat view of the rollout buffer the update gathers from; planes are [T][N]. */
+typedef struct LrxBatchView {
+  const float* obs;  /* [T][N][obs_dim] */
+  const void* act;   /* [T][N] */
+  const float* logp; /* [T][N] */
+  const float* val;  /* [T][N] */
+  const float* ret;  /* [T][N] */
+  const float* adv;  /* [T][N] */
+  int32_t N, T;
+} LrxBatchView;
+
+#define LRX_PPO_NSTATS 8 /* approx_kl, loss, policy_loss, value_loss, entropy_loss, grad_norm, nonfinite, 0 */
+
+/* Bytes of caller-allocated workspace for minibatches of up to B rows. */
+size_t lrx_ppo_workspace_bytes(const LrxPolicyDesc* pol, int64_t B);
+
+/* Per-minibatch advantage sums for the normalisation of ppo.py:424-427:
+ * sums[b] = (sum A, sum A^2) over idx[b][0..B) in double.  One launch for a whole epoch
+ * so that a multi-GPU caller can all-reduce all of them in ONE collective. */
+int lrx_ppo_adv_sums(const float* adv, int32_t N, int32_t T, const int32_t* idx,
+                     int32_t num_batches, int64_t B, double* sums, lrx_stream_t stream);
+
+/* Loss forward + backward for ONE minibatch share of B rows (ppo_loss + grad,
+ * ppo.py:396-469).  B_global is the size of the whole minibatch across ranks and adv_sums
+ * its (all-reduced) advantage sums.  gradbuf[n_params + LRX_PPO_NSTATS] receives this
+ * share's contribution to the gradient of the MEAN loss and to the stat sums, so that a
+ * plain SUM all-reduce over ranks yields the global quantities. */
+int lrx_ppo_grad(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf,
+                 const int32_t* idx, int64_t B, int64_t B_global, const double* adv_sums,
+                 const LrxPpoHyper* h, float* gradbuf, void* workspace, size_t workspace_bytes,
+                 lrx_stream_t stream);
+
+/* clip_by_global_norm + Adam on the (all-reduced) gradbuf (train_batch, ppo.py:471-492);
+ * writes this minibatch's LRX_PPO_NSTATS stats and ORs the non-finite flag of
+ * ppo.py:413-417 into *nonfinite_flag. */
+int lrx_ppo_apply(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
+                  int32_t* adam_count, const float* gradbuf, const LrxPpoHyper* h,
+                  float* stats_out, int32_t* nonfinite_flag, lrx_stream_t stream);
+
+/* One epoch on one GPU: for each of num_batches rows of idx: adv sums, grad, apply
+ * (train_epoch, ppo.py:494-521).  stats_out [num_batches][LRX_PPO_NSTATS]. */
+int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
+                   int32_t* adam_count, const LrxBatchView* buf, const int32_t* idx,
+                   int32_t num_batches, int64_t B, const LrxPpoHyper* h, float* stats_out,
+                   int32_t* nonfinite_flag, void* workspace, size_t workspace_bytes,
+                   lrx_stream_t stream);
+
+/* ------------------------------------------------------------------------- misc */
+const char* lrx_last_error(void);
+int lrx_version(void);
+/* Number of kernel launches issued by this library on the calling thread since the last
+ * call with reset != 0 (bench.py's "gpu_launches"). */
+int64_t lrx_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LERAX_B200_H */

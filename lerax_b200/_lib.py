@@ -1,0 +1,139 @@
+"""ctypes binding of include/lerax_b200.h (the C-ABI drop-in boundary).
+
+There is deliberately no fallback: if the shared library is missing this module raises, and
+every compute entry point raises if no CUDA device is present.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_C", "liblerax_b200.so")
+
+LRX_OK = 0
+LRX_ENV_CARTPOLE, LRX_ENV_PENDULUM, LRX_ENV_ACROBOT = 0, 1, 2
+LRX_ENV_MAX_PARAMS = 16
+LRX_MAX_LAYERS = 8
+LRX_MAX_NOUT = 8
+LRX_LAYOUT_TN, LRX_LAYOUT_NT = 0, 1
+LRX_PPO_NSTATS = 8
+
+
+class LrxEnvDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("max_episode_steps", C.c_int32), ("dt", C.c_float),
+                ("p", C.c_float * LRX_ENV_MAX_PARAMS)]
+
+
+class LrxEnvState(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("t", C.c_void_p), ("step_count", C.c_void_p)]
+
+
+class LrxPolicyDesc(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("n_out", C.c_int32), ("is_box", C.c_int32), ("n_params", C.c_int32),
+                ("n_layers", C.c_int32 * 3),
+                ("dims", (C.c_int32 * (LRX_MAX_LAYERS + 1)) * 3),
+                ("relu", (C.c_int32 * LRX_MAX_LAYERS) * 3)]
+
+
+class LrxRng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("env_offset", C.c_uint32), ("step_offset", C.c_uint32)]
+
+
+class LrxReplay(C.Structure):
+    _fields_ = [("action_noise", C.c_void_p), ("reset_uniform", C.c_void_p)]
+
+
+class LrxRolloutOut(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("act", C.c_void_p), ("rew", C.c_void_p), ("done", C.c_void_p),
+                ("logp", C.c_void_p), ("val", C.c_void_p), ("last_value", C.c_void_p),
+                ("y_trace", C.c_void_p), ("t_trace", C.c_void_p), ("y_next_trace", C.c_void_p)]
+
+
+class LrxPpoHyper(C.Structure):
+    _fields_ = [("clip_coefficient", C.c_float), ("value_loss_coefficient", C.c_float),
+                ("entropy_loss_coefficient", C.c_float), ("max_grad_norm", C.c_float),
+                ("learning_rate", C.c_float), ("adam_b1", C.c_float), ("adam_b2", C.c_float),
+                ("adam_eps", C.c_float), ("clip_value_loss", C.c_int32), ("normalize_advantages", C.c_int32)]
+
+
+class LrxBatchView(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("act", C.c_void_p), ("logp", C.c_void_p), ("val", C.c_void_p),
+                ("ret", C.c_void_p), ("adv", C.c_void_p), ("N", C.c_int32), ("T", C.c_int32)]
+
+
+_P = C.POINTER
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); must list every function declared in include/lerax_b200.h
+PROTOTYPES = {
+    "lrx_policy_num_params": (C.c_int, [_P(LrxPolicyDesc)]),
+    "lrx_env_reset": (C.c_int, [_P(LrxEnvDesc), LrxEnvState, C.c_int32, LrxRng, _vp, _vp]),
+    "lrx_env_step": (C.c_int, [_P(LrxEnvDesc), LrxEnvState, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp]),
+    "lrx_env_observe": (C.c_int, [_P(LrxEnvDesc), LrxEnvState, _vp, _vp, C.c_int32, _vp]),
+    "lrx_policy_forward": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, C.c_int32, _vp]),
+    "lrx_rollout": (C.c_int, [_P(LrxEnvDesc), _P(LrxPolicyDesc), _vp, LrxEnvState, LrxRng, _P(LrxReplay),
+                              LrxRolloutOut, C.c_int32, C.c_int32, C.c_float, _vp]),
+    "lrx_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                          _vp, _vp]),
+    "lrx_ppo_workspace_bytes": (C.c_size_t, [_P(LrxPolicyDesc), C.c_int64]),
+    "lrx_ppo_adv_sums": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int64, _vp, _vp]),
+    "lrx_ppo_grad": (C.c_int, [_P(LrxPolicyDesc), _vp, _P(LrxBatchView), _vp, C.c_int64, C.c_int64, _vp,
+                               _P(LrxPpoHyper), _vp, _vp, C.c_size_t, _vp]),
+    "lrx_ppo_apply": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _vp, _P(LrxPpoHyper), _vp, _vp, _vp]),
+    "lrx_ppo_update": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _P(LrxBatchView), _vp, C.c_int32,
+                                 C.c_int64, _P(LrxPpoHyper), _vp, _vp, _vp, C.c_size_t, _vp]),
+    "lrx_last_error": (C.c_char_p, []),
+    "lrx_version": (C.c_int, []),
+    "lrx_launch_count": (C.c_int64, [C.c_int]),
+}
+
+
+class LeraxB200Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"lerax_b200: CUDA library not built ({LIB_PATH} missing). Run `python -m lerax_b200.build` "
+            "(needs nvcc). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != LRX_OK:
+        msg = lib.lrx_last_error().decode("utf-8", "replace")
+        raise LeraxB200Error(f"{what or 'lerax_b200'} failed (code {rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise LeraxB200Error("lerax_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    return torch
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "lerax_b200 expects contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,175 @@
+// Generalised Advantage Estimation: one HBM pass, reverse affine scan.
+//
+// Reference: advantage/gae.py:36-66 (via buffer/rollout.py:64-79, algorithm/ppo.py:311-315)
+//     delta_t = r_t + gamma * v_{t+1} * (1-d_t) - v_t ; A_t = delta_t + gamma*lam*(1-d_t) * A_{t+1}
+// The recurrence A_t = a_t + b_t * A_{t+1} is a composition of affine maps, so a strip of T
+// steps is split into chunks that are scanned independently and stitched with the chunk
+// summaries (a, b) -- every element is read once and written once (17 B/element).
+//
+//  * TN layout ([T][N], kernel-native): a warp owns a strip of 32 adjacent envs (lanes = envs,
+//    128 B coalesced rows); the C warps of a block own C consecutive time chunks of L steps
+//    held in registers, summaries are exchanged through shared memory.
+//  * NT layout ([N][T], reference-native): a warp owns one env, lanes = 32 consecutive steps,
+//    Kogge-Stone scan of the affine pairs with __shfl_down_sync.
+#include "lrx_common.cuh"
+
+template <int L>
+__global__ void __launch_bounds__(512)
+gae_tn_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+              const uint8_t* __restrict__ done, const float* __restrict__ last_val,
+              float* __restrict__ adv, float* __restrict__ ret, int N, int T, float gamma,
+              float lam, double* ev_sums) {
+  __shared__ float sA[16][32], sP[16][32];
+  __shared__ double sEv[16][4];
+  const int lane = threadIdx.x, c = threadIdx.y, C = blockDim.y;
+  const int n = blockIdx.x * 32 + lane;
+  const bool live = n < N;
+  const int nl = live ? n : N - 1;
+  const float gl = gamma * lam;
+  const int seg_len = C * L;
+  const int num_seg = (T + seg_len - 1) / seg_len;
+  const float lv = last_val[nl];
+  float seg_carry = 0.f;
+  double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+
+  for (int seg = num_seg - 1; seg >= 0; --seg) {
+    const int t0 = seg * seg_len + c * L;
+    float r[L], v[L + 1], nd[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int t = t0 + i;
+      const bool ok = t < T;
+      const size_t off = (size_t)(ok ? t : T - 1) * N + nl;
+      r[i] = ok ? rew[off] : 0.f;
+      v[i] = ok ? val[off] : lv;
+      nd[i] = ok ? 1.0f - (float)done[off] : 1.0f;
+    }
+    v[L] = (t0 + L < T) ? val[(size_t)(t0 + L) * N + nl] : lv;
+
+    float a = 0.f, p = 1.f;
+    float A[L], P[L];
+#pragma unroll
+    for (int i = L - 1; i >= 0; --i) {
+      const bool ok = t0 + i < T;
+      const float delta = ok ? r[i] + gamma * v[i + 1] * nd[i] - v[i] : 0.f;
+      const float disc = ok ? gl * nd[i] : 1.f;
+      a = delta + disc * a;
+      p = disc * p;
+      A[i] = a;
+      P[i] = p;
+    }
+    sA[c][lane] = a;
+    sP[c][lane] = p;
+    __syncthreads();
+    float carry = seg_carry;
+    for (int cc = C - 1; cc > c; --cc) carry = sA[cc][lane] + sP[cc][lane] * carry;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int t = t0 + i;
+      if (t < T && live) {
+        const float Ai = A[i] + P[i] * carry;
+        const float Ri = Ai + v[i];
+        const size_t off = (size_t)t * N + n;
+        adv[off] = Ai;
+        ret[off] = Ri;
+        e0 += Ri; e1 += (double)Ri * Ri; e2 += Ai; e3 += (double)Ai * Ai;
+      }
+    }
+    float cr = carry;
+    for (int cc = c; cc >= 0; --cc) cr = sA[cc][lane] + sP[cc][lane] * cr;
+    seg_carry = cr;
+    __syncthreads();
+  }
+
+  if (ev_sums) {
+    e0 = warp_sum(e0); e1 = warp_sum(e1); e2 = warp_sum(e2); e3 = warp_sum(e3);
+    if (lane == 0) { sEv[c][0] = e0; sEv[c][1] = e1; sEv[c][2] = e2; sEv[c][3] = e3; }
+    __syncthreads();
+    if (c == 0 && lane < 4) {
+      double s = 0;
+      for (int cc = 0; cc < C; ++cc) s += sEv[cc][lane];
+      atomicAdd(ev_sums + lane, s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gae_nt_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+              const uint8_t* __restrict__ done, const float* __restrict__ last_val,
+              float* __restrict__ adv, float* __restrict__ ret, int N, int T, float gamma,
+              float lam, double* ev_sums) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= N) return;  // whole warp exits together
+  const float gl = gamma * lam;
+  const size_t base_off = (size_t)env * T;
+  const float lv = last_val[env];
+  float carry = 0.f;
+  double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+  for (int base = ((T - 1) / 32) * 32; base >= 0; base -= 32) {
+    const int t = base + lane;
+    const bool ok = t < T;
+    float v = 0.f, a = 0.f, b = 1.f;
+    if (ok) {
+      v = val[base_off + t];
+      const float vn = (t + 1 < T) ? val[base_off + t + 1] : lv;
+      const float nd = 1.0f - (float)done[base_off + t];
+      a = rew[base_off + t] + gamma * vn * nd - v;
+      b = gl * nd;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float a2 = __shfl_down_sync(0xffffffffu, a, o);
+      const float b2 = __shfl_down_sync(0xffffffffu, b, o);
+      if (lane + o < 32) {
+        a = a + b * a2;
+        b = b * b2;
+      }
+    }
+    const float Ai = a + b * carry;
+    if (ok) {
+      const float Ri = Ai + v;
+      adv[base_off + t] = Ai;
+      ret[base_off + t] = Ri;
+      e0 += Ri; e1 += (double)Ri * Ri; e2 += Ai; e3 += (double)Ai * Ai;
+    }
+    carry = __shfl_sync(0xffffffffu, Ai, 0);
+  }
+  if (ev_sums) {
+    e0 = warp_sum(e0); e1 = warp_sum(e1); e2 = warp_sum(e2); e3 = warp_sum(e3);
+    if (lane == 0) {
+      atomicAdd(ev_sums + 0, e0); atomicAdd(ev_sums + 1, e1);
+      atomicAdd(ev_sums + 2, e2); atomicAdd(ev_sums + 3, e3);
+    }
+  }
+}
+
+extern "C" int lrx_gae(const float* rew, const float* val, const uint8_t* done,
+                       const float* last_value, float* adv, float* ret, int32_t N, int32_t T,
+                       float gamma, float lam, int32_t layout, double* ev_sums,
+                       lrx_stream_t stream) {
+  LRX_REQUIRE(N >= 0 && T >= 0, LRX_ERR_INVALID_ARG, "lrx_gae: negative N or T");
+  LRX_REQUIRE(layout == LRX_LAYOUT_TN || layout == LRX_LAYOUT_NT, LRX_ERR_INVALID_ARG,
+              "lrx_gae: unknown layout %d", layout);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (ev_sums) LRX_CUDA_CHECK(cudaMemsetAsync(ev_sums, 0, 4 * sizeof(double), s));
+  if (N == 0 || T == 0) return LRX_OK;
+  LRX_REQUIRE(rew && val && done && last_value && adv && ret, LRX_ERR_INVALID_ARG, "lrx_gae: NULL pointer");
+  if (layout == LRX_LAYOUT_TN) {
+    const int blocks = (N + 31) / 32;
+    if (T >= 64) {
+      int C = (T + 15) / 16;
+      if (C > 16) C = 16;
+      gae_tn_kernel<16><<<blocks, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
+    } else {
+      int C = (T + 3) / 4;
+      if (C > 16) C = 16;
+      gae_tn_kernel<4><<<blocks, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
+    }
+  } else {
+    const int warps = 8;
+    gae_nt_kernel<<<(N + warps - 1) / warps, warps * 32, 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
+  }
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}

@@ -1,0 +1,656 @@
+// PPO update: minibatch gather, MLP forward/backward, clipped-surrogate / value / entropy
+// loss, gradient reduction, clip_by_global_norm and Adam.
+//
+// Reference: algorithm/ppo.py:396-467 (ppo_loss), :471-492 (train_batch), :494-521
+// (train_epoch); buffer/base_buffer.py:38-103 (flatten i = n*T + t, gather); optax 0.2.6
+// chain(clip_by_global_norm, adam) (ppo.py:192-194).
+//
+// This file holds the GENERIC path (any layer widths/depths): activations of a row chunk
+// are kept feature-major [width][rows] in the caller's workspace and every Linear is one
+// tiled fp32 SGEMM launch (forward, dX, and split-K dW with the bias gradient folded in as a
+// ones column).  The fused per-warp path for the default widths lives in
+// lrx_update_fused.cu and is tried first.
+#include "lrx_common.cuh"
+#include "lrx_policy.cuh"
+
+constexpr int64_t LRX_CHUNK_ROWS = 1 << 20;  // rows of a minibatch processed per pass
+constexpr int LRX_LOSS_THREADS = 256;
+constexpr int LRX_MAX_SPLIT = 128;
+
+// ============================================================================== SGEMM
+// C[M x N] (+)= op(A)[M x K] * op(B)[K x N], fp32, 64x64x16 tiles, 4x4 micro-tiles.
+struct GemmArgs {
+  const float* A; int lda;
+  const float* B; int ldb;
+  float* C; int ldc;
+  int M, N, K;
+  const float* bias;   // + bias[i]
+  int relu;
+  const float* mask; int ldm;  // *= (mask[i][j] > 0)
+  int accumulate;      // C += result
+  int ones_row;        // additionally write C[M][j] = 1
+  int k_chunk;         // K range per blockIdx.z (split-K)
+  long long c_split_stride;  // C/C2 offset per blockIdx.z
+  float* C2; int n_main;     // column j == n_main is redirected to C2[i]
+};
+
+template <bool AT, bool BT>
+__global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
+  constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+  __shared__ float As[BK][BM + PAD];
+  __shared__ float Bs[BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * g.k_chunk;
+  const int kend = min(g.K, kbeg + g.k_chunk);
+  float acc[4][4] = {};
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    // ---- A tile -> As[k][i]
+    if (AT) {
+      const int k = k0 + (tid >> 4), ib = i0 + (tid & 15) * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = ib + q;
+        As[tid >> 4][(tid & 15) * 4 + q] = (k < kend && i < g.M) ? g.A[(size_t)k * g.lda + i] : 0.f;
+      }
+    } else {
+      const int i = i0 + (tid >> 2), kb = k0 + (tid & 3) * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = kb + q;
+        As[(tid & 3) * 4 + q][tid >> 2] = (k < kend && i < g.M) ? g.A[(size_t)i * g.lda + k] : 0.f;
+      }
+    }
+    // ---- B tile -> Bs[k][j]
+    if (BT) {
+      const int j = j0 + (tid >> 2), kb = k0 + (tid & 3) * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = kb + q;
+        Bs[(tid & 3) * 4 + q][tid >> 2] = (k < kend && j < g.N) ? g.B[(size_t)j * g.ldb + k] : 0.f;
+      }
+    } else {
+      const int k = k0 + (tid >> 4), jb = j0 + (tid & 15) * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = jb + q;
+        Bs[tid >> 4][(tid & 15) * 4 + q] = (k < kend && j < g.N) ? g.B[(size_t)k * g.ldb + j] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+    }
+    __syncthreads();
+  }
+
+  float* C = g.C + (size_t)blockIdx.z * g.c_split_stride;
+  float* C2 = g.C2 ? g.C2 + (size_t)blockIdx.z * g.c_split_stride : nullptr;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int i = i0 + ty * 4 + p;
+    if (i >= g.M) continue;
+    const float bi = g.bias ? g.bias[i] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + tx * 4 + q;
+      if (j >= g.N) continue;
+      float v = acc[p][q] + bi;
+      if (g.relu) v = fmaxf(v, 0.f);
+      if (g.mask) v = (g.mask[(size_t)i * g.ldm + j] > 0.f) ? v : 0.f;
+      float* dst = (C2 && j == g.n_main) ? (C2 + i) : (C + (size_t)i * g.ldc + j);
+      if (g.accumulate) v += *dst;
+      *dst = v;
+    }
+  }
+  if (g.ones_row && blockIdx.y == 0 && blockIdx.z == 0) {
+    for (int j = j0 + tid; j < min(g.N, j0 + BN); j += 256) g.C[(size_t)g.M * g.ldc + j] = 1.0f;
+  }
+}
+
+static int launch_gemm(const GemmArgs& g, bool at, bool bt, int splits, cudaStream_t s) {
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, splits);
+  if (!at && !bt) sgemm_kernel<false, false><<<grid, 256, 0, s>>>(g);
+  else if (at && !bt) sgemm_kernel<true, false><<<grid, 256, 0, s>>>(g);
+  else if (!at && bt) sgemm_kernel<false, true><<<grid, 256, 0, s>>>(g);
+  else sgemm_kernel<true, true><<<grid, 256, 0, s>>>(g);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+// ============================================================================= gather
+// Rows idx[m] (reference order i = n*T + t) -> feature-major obsT [(d+1)][rows] with a ones
+// row, plus the per-row scalars.  buffer/base_buffer.py:90-103 (gather).
+__global__ void gather_kernel(LrxBatchView buf, const int32_t* __restrict__ idx, int rows, int ld,
+                              int d, int is_box, float* obsT, float* act_f, int32_t* act_i,
+                              float* logp, float* adv, float* ret, float* val) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const int i = idx[m];
+  const int n = i / buf.T, t = i - n * buf.T;
+  const size_t src = (size_t)t * buf.N + n;
+  for (int k = 0; k < d; ++k) obsT[(size_t)k * ld + m] = buf.obs[src * d + k];
+  obsT[(size_t)d * ld + m] = 1.0f;
+  if (is_box) act_f[m] = ((const float*)buf.act)[src];
+  else act_i[m] = ((const int32_t*)buf.act)[src];
+  logp[m] = buf.logp[src];
+  adv[m] = buf.adv[src];
+  ret[m] = buf.ret[src];
+  val[m] = buf.val[src];
+}
+
+// ========================================================================== adv sums
+__global__ void adv_sums_kernel(const float* __restrict__ adv, int N, int T,
+                                const int32_t* __restrict__ idx, long long B, double* sums) {
+  const int b = blockIdx.y;
+  const int32_t* row = idx + (size_t)b * B;
+  double s = 0, s2 = 0;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < B;
+       m += (long long)gridDim.x * blockDim.x) {
+    const int i = row[m];
+    const int n = i / T, t = i - n * T;
+    const float a = adv[(size_t)t * N + n];
+    s += a;
+    s2 += (double)a * a;
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  __shared__ double sh[2][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][w] = s; sh[1][w] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh[0][i]; c += sh[1][i]; }
+    atomicAdd(sums + 2 * b, a);
+    atomicAdd(sums + 2 * b + 1, c);
+  }
+}
+
+// =============================================================================== loss
+// Per row: log-prob / entropy of the stored action under the current policy, ratio,
+// normalised advantage, clipped surrogate, value loss; emits dL/dvalue and dL/dhead (already
+// scaled by 1/B_global) and block partial sums of the statistics.   ppo.py:396-467.
+struct LossArgs {
+  const float* value;  // [rows]
+  const float* head; int ld;  // [n_out][ld]
+  const float* act_f; const int32_t* act_i;
+  const float* logp_old; const float* adv; const float* ret; const float* val_old;
+  float* dvalue; float* dhead;  // [rows], [n_out][ld]
+  int rows; int n_out; int is_box;
+  const float* log_std_ptr;  // device scalar (Box only)
+  const double* adv_sums; double B_global;
+  LrxPpoHyper h;
+  double* partial;  // [gridDim.x][8]
+};
+
+__device__ __forceinline__ void tie_weights(float a, float b, float& wa, float& wb) {
+  wa = a < b ? 1.f : (a == b ? 0.5f : 0.f);  // JAX: d min(a,b) splits ties 1/2-1/2
+  wb = 1.f - wa;
+}
+__device__ __forceinline__ float clip_grad(float x, float lo, float hi) {
+  return (x > lo && x < hi) ? 1.f : ((x == lo || x == hi) ? 0.5f : 0.f);
+}
+
+__global__ void __launch_bounds__(LRX_LOSS_THREADS) loss_kernel(const LossArgs a) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const float invB = (float)(1.0 / a.B_global);
+  double s_kl = 0, s_pol = 0, s_val = 0, s_ent = 0, s_dls = 0, s_bad = 0;
+  if (m < a.rows) {
+    const float value = a.value[m];
+    float logp, entropy, z_n = 0.f, scale = 1.f;
+    float lp[LRX_MAX_NOUT], pr[LRX_MAX_NOUT];
+    int ai = 0;
+    if (a.is_box) {
+      scale = expf(__ldg(a.log_std_ptr));
+      const float loc = a.head[m];
+      z_n = (a.act_f[m] - loc) / scale;
+      const float log_scale = logf(scale);
+      logp = -0.5f * (z_n * z_n) - (LRX_HALF_LOG_2PI + log_scale);
+      entropy = 0.5f + LRX_HALF_LOG_2PI + log_scale;
+    } else {
+#pragma unroll
+      for (int j = 0; j < LRX_MAX_NOUT; ++j) lp[j] = j < a.n_out ? a.head[(size_t)j * a.ld + m] : 0.f;
+      log_softmax_n<LRX_MAX_NOUT>(lp, a.n_out);
+      ai = a.act_i[m];
+      logp = 0.f;
+      entropy = 0.f;
+#pragma unroll
+      for (int j = 0; j < LRX_MAX_NOUT; ++j) {
+        if (j < a.n_out) {
+          pr[j] = expf(lp[j]);
+          entropy -= pr[j] * lp[j];
+          if (j == ai) logp = lp[j];
+        }
+      }
+    }
+    if (!(isfinite(value) && isfinite(logp) && isfinite(entropy))) s_bad = 1.0;  // ppo.py:413-417
+
+    const float log_ratio = logp - a.logp_old[m];
+    const float ratio = expf(log_ratio);
+    s_kl = (double)(ratio - log_ratio);
+
+    float A = a.adv[m];
+    if (a.h.normalize_advantages) {
+      const double mean = a.adv_sums[0] / a.B_global;
+      double var = a.adv_sums[1] / a.B_global - mean * mean;
+      var = var > 0 ? var : 0;
+      const float std = (float)sqrt(var);
+      A = (A - (float)mean) / (std + 1.1920928955078125e-07f);  // + finfo(float32).eps
+    }
+    const float c = a.h.clip_coefficient, lo = 1.f - c, hi = 1.f + c;
+    const float s1 = A * ratio, s2 = A * lrx_clipf(ratio, lo, hi);
+    s_pol = (double)fminf(s1, s2);
+    float w1, w2;
+    tie_weights(s1, s2, w1, w2);
+    const float dlogp = -invB * (w1 * A * ratio + w2 * A * clip_grad(ratio, lo, hi) * ratio);
+
+    float dvl;
+    const float e1 = value - a.ret[m];
+    if (a.h.clip_value_loss) {
+      const float dv = value - a.val_old[m];
+      const float clipped = a.val_old[m] + lrx_clipf(dv, -c, c);
+      const float e2 = clipped - a.ret[m];
+      const float q1 = e1 * e1, q2 = e2 * e2;
+      s_val = (double)fminf(q1, q2);
+      float u1, u2;
+      tie_weights(q1, q2, u1, u2);
+      dvl = invB * (u1 * e1 + u2 * e2 * clip_grad(dv, -c, c));
+    } else {
+      s_val = (double)(e1 * e1);
+      dvl = invB * e1;
+    }
+    s_ent = (double)entropy;
+    a.dvalue[m] = a.h.value_loss_coefficient * dvl;
+    const float ch = a.h.entropy_loss_coefficient;
+    if (a.is_box) {
+      a.dhead[m] = dlogp * z_n / scale;
+      s_dls = (double)(dlogp * (z_n * z_n - 1.0f));
+    } else {
+#pragma unroll
+      for (int j = 0; j < LRX_MAX_NOUT; ++j) {
+        if (j < a.n_out) {
+          const float dH = -pr[j] * (lp[j] + entropy);
+          a.dhead[(size_t)j * a.ld + m] = dlogp * ((j == ai ? 1.f : 0.f) - pr[j]) + (-ch * invB) * dH;
+        }
+      }
+    }
+  }
+  // block partial sums (fixed order -> deterministic)
+  __shared__ double sh[6][LRX_LOSS_THREADS / 32];
+  double v[6] = {s_kl, s_pol, s_val, s_ent, s_dls, s_bad};
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    v[q] = warp_sum(v[q]);
+    if (lane == 0) sh[q][w] = v[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double s = 0;
+    for (int i = 0; i < LRX_LOSS_THREADS / 32; ++i) s += sh[threadIdx.x][i];
+    a.partial[(size_t)blockIdx.x * 8 + threadIdx.x] = s;
+  }
+}
+
+// =========================================================== partial-gradient reduction
+// gradbuf[p] = sum_z partial[z][p]; the last block also folds the loss partial sums into
+// the log_std gradient and the stat slots.  Fixed summation order -> deterministic.
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, long long stride,
+                                       int P, const double* __restrict__ loss_partial, int loss_blocks,
+                                       int log_std_off, float ent_coef, double B_global,
+                                       float* gradbuf) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P && p != log_std_off) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * stride + p];
+    gradbuf[p] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 6) {
+    double s = 0;
+    for (int b = 0; b < loss_blocks; ++b) s += loss_partial[(size_t)b * 8 + threadIdx.x];
+    const int q = threadIdx.x;
+    if (q < 4) gradbuf[P + q] = (float)(s / B_global);       // kl, pol, val, ent means' share
+    else if (q == 4) { if (log_std_off >= 0) gradbuf[log_std_off] = (float)s; }
+    else gradbuf[P + 6] = (float)s;                            // non-finite row count
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 6) { gradbuf[P + 4] = 0.f; gradbuf[P + 5] = 0.f; gradbuf[P + 7] = 0.f; }
+}
+
+// ===================================================================== clip + Adam
+// optax.clip_by_global_norm then scale_by_adam (bias-corrected, eps outside the sqrt) then
+// scale(-lr); one block.  Also finalises the minibatch statistics.   ppo.py:471-492.
+__global__ void __launch_bounds__(1024)
+apply_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, int32_t* count,
+             const float* __restrict__ g, int P, int log_std_off, LrxPpoHyper h, float* stats_out,
+             int32_t* nonfinite_flag) {
+  __shared__ double red[32];
+  __shared__ float s_norm;
+  const int tid = threadIdx.x;
+  // d entropy_loss / d log_std = -1 per row mean -> -c_H, contributed once (not per rank):
+  // callers all-reduce gradbuf, so it is added here, after the reduction.
+  const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
+  double ss = 0;
+  for (int p = tid; p < P; p += blockDim.x) {
+    float gp = g[p] + (p == log_std_off ? ls_extra : 0.f);
+    ss += (double)gp * gp;
+  }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    s_norm = (float)sqrt(t);
+  }
+  __syncthreads();
+  const float norm = s_norm;
+  const bool bad = g[P + 6] > 0.f || !isfinite(norm);
+  if (!bad) {
+    const int cnt = *count + 1;
+    const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
+    const float bc2 = 1.0f - powf(h.adam_b2, (float)cnt);
+    const bool keep = norm < h.max_grad_norm;
+    for (int p = tid; p < P; p += blockDim.x) {
+      float gp = g[p] + (p == log_std_off ? ls_extra : 0.f);
+      if (!keep) gp = (gp / norm) * h.max_grad_norm;
+      const float mn = h.adam_b1 * m[p] + (1.0f - h.adam_b1) * gp;
+      const float vn = h.adam_b2 * v[p] + (1.0f - h.adam_b2) * (gp * gp);
+      m[p] = mn;
+      v[p] = vn;
+      const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
+      params[p] = params[p] + (-h.learning_rate) * upd;
+    }
+    __syncthreads();
+    if (tid == 0) *count = cnt;
+  } else if (tid == 0 && nonfinite_flag) {
+    atomicOr(nonfinite_flag, 1);
+  }
+  if (tid == 0 && stats_out) {
+    const float kl = g[P + 0] - 1.0f;
+    const float pl = -g[P + 1];
+    const float vl = g[P + 2] / 2.0f;
+    const float el = -g[P + 3];
+    stats_out[0] = kl;
+    stats_out[1] = pl + vl * h.value_loss_coefficient + el * h.entropy_loss_coefficient;
+    stats_out[2] = pl;
+    stats_out[3] = vl;
+    stats_out[4] = el;
+    stats_out[5] = norm;
+    stats_out[6] = g[P + 6];
+    stats_out[7] = 0.f;
+  }
+}
+
+// ========================================================================= workspace
+struct Workspace {
+  int64_t rows;      // row capacity of one chunk (multiple of 4)
+  int splits;
+  int loss_blocks;
+  size_t P_pad;
+  float* obsT;
+  float* act_out[3][LRX_MAX_LAYERS];  // post-activation outputs (+ ones row), [out+1][rows]
+  float* dA; float* dB; float* dfeat; float* dval; float* dhd;
+  float* act_f; int32_t* act_i; float* logp; float* adv; float* ret; float* val;
+  float* partial;        // [splits][P_pad]
+  double* loss_partial;  // [loss_blocks][8]
+  double* adv_sums;      // [LRX_MAX_BATCHES][2] for lrx_ppo_update
+  size_t total;
+};
+constexpr int LRX_MAX_BATCHES = 4096;
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Workspace carve(const LrxPolicyDesc& pol, int64_t B, void* base) {
+  Workspace w{};
+  int64_t rows = B < LRX_CHUNK_ROWS ? B : LRX_CHUNK_ROWS;
+  rows = (rows + 3) / 4 * 4;
+  if (rows < 4) rows = 4;
+  w.rows = rows;
+  int sp = (int)((rows + 1023) / 1024);
+  w.splits = sp < 1 ? 1 : (sp > LRX_MAX_SPLIT ? LRX_MAX_SPLIT : sp);
+  w.loss_blocks = (int)((rows + LRX_LOSS_THREADS - 1) / LRX_LOSS_THREADS);
+  int np = 0;
+  lrx_policy_layers(pol, nullptr, nullptr, &np);
+  w.P_pad = align_up((size_t)np + LRX_PPO_NSTATS, 32);
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) { void* p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
+  int maxw = 1;
+  for (int c = 0; c < 3; ++c)
+    for (int i = 0; i <= pol.n_layers[c]; ++i) maxw = pol.dims[c][i] > maxw ? pol.dims[c][i] : maxw;
+  w.obsT = (float*)take((size_t)(pol.obs_dim + 1) * rows * 4);
+  for (int c = 0; c < 3; ++c)
+    for (int i = 0; i < pol.n_layers[c]; ++i) w.act_out[c][i] = (float*)take((size_t)(pol.dims[c][i + 1] + 1) * rows * 4);
+  w.dA = (float*)take((size_t)maxw * rows * 4);
+  w.dB = (float*)take((size_t)maxw * rows * 4);
+  w.dfeat = (float*)take((size_t)pol.dims[0][pol.n_layers[0]] * rows * 4);
+  w.dval = (float*)take((size_t)rows * 4);
+  w.dhd = (float*)take((size_t)pol.n_out * rows * 4);
+  w.act_f = (float*)take(rows * 4);
+  w.act_i = (int32_t*)w.act_f;
+  w.logp = (float*)take(rows * 4);
+  w.adv = (float*)take(rows * 4);
+  w.ret = (float*)take(rows * 4);
+  w.val = (float*)take(rows * 4);
+  w.partial = (float*)take((size_t)w.splits * w.P_pad * 4);
+  w.loss_partial = (double*)take((size_t)w.loss_blocks * 8 * sizeof(double) * ((B + rows - 1) / rows));
+  w.adv_sums = (double*)take((size_t)LRX_MAX_BATCHES * 2 * sizeof(double));
+  w.total = off;
+  return w;
+}
+
+size_t lrx_fused_workspace_bytes(const LrxPolicyDesc* pol, int64_t B);
+
+extern "C" size_t lrx_ppo_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) {
+  if (!pol || lrx_validate_policy(pol) != LRX_OK || B <= 0) return 0;
+  Workspace w = carve(*pol, B, nullptr);
+  size_t a = w.total;
+  size_t f = lrx_fused_workspace_bytes(pol, B);
+  // the last slot is the gradbuf lrx_ppo_update hands to grad/apply
+  return (a > f ? a : f) + align_up(w.P_pad * 4, 256);
+}
+
+// ======================================================================== host driver
+extern "C" int lrx_ppo_adv_sums(const float* adv, int32_t N, int32_t T, const int32_t* idx,
+                                int32_t num_batches, int64_t B, double* sums, lrx_stream_t stream) {
+  LRX_REQUIRE(adv && idx && sums && N > 0 && T > 0 && num_batches >= 0 && B > 0, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_adv_sums: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  LRX_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)num_batches * 2 * sizeof(double), s));
+  if (num_batches == 0) return LRX_OK;
+  int bx = (int)((B + 256 * 8 - 1) / (256 * 8));
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  adv_sums_kernel<<<dim3(bx, num_batches), 256, 0, s>>>(adv, N, T, idx, B, sums);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+static int validate_update_args(const LrxPolicyDesc* pol, const LrxBatchView* buf, const LrxPpoHyper* h) {
+  int rc = lrx_validate_policy(pol);
+  if (rc) return rc;
+  LRX_REQUIRE(buf && h, LRX_ERR_INVALID_ARG, "NULL LrxBatchView / LrxPpoHyper");
+  LRX_REQUIRE(buf->obs && buf->act && buf->logp && buf->val && buf->ret && buf->adv && buf->N > 0 && buf->T > 0,
+              LRX_ERR_INVALID_ARG, "LrxBatchView has NULL planes or empty shape");
+  LRX_REQUIRE((int64_t)buf->N * buf->T < ((int64_t)1 << 31), LRX_ERR_UNSUPPORTED,
+              "N*T must fit int32 (reference indices are int32)");
+  return LRX_OK;
+}
+
+int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf,
+                       const int32_t* idx, int64_t B, int64_t B_global, const double* adv_sums,
+                       const LrxPpoHyper* h, float* gradbuf, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream, bool* handled);
+
+extern "C" int lrx_ppo_grad(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf,
+                            const int32_t* idx, int64_t B, int64_t B_global, const double* adv_sums,
+                            const LrxPpoHyper* h, float* gradbuf, void* workspace,
+                            size_t workspace_bytes, lrx_stream_t stream) {
+  int rc = validate_update_args(pol, buf, h);
+  if (rc) return rc;
+  LRX_REQUIRE(params && idx && gradbuf && workspace && B > 0 && B_global >= B, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_grad: bad argument");
+  LRX_REQUIRE(!h->normalize_advantages || adv_sums, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_grad: adv_sums required when normalize_advantages is set");
+  LRX_REQUIRE(workspace_bytes >= lrx_ppo_workspace_bytes(pol, B), LRX_ERR_INVALID_ARG,
+              "lrx_ppo_grad: workspace too small (%zu < %zu)", workspace_bytes, lrx_ppo_workspace_bytes(pol, B));
+  cudaStream_t s = (cudaStream_t)stream;
+
+  bool handled = false;
+  rc = lrx_ppo_grad_fused(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, s, &handled);
+  if (rc) return rc;
+  if (handled) return LRX_OK;
+
+  Workspace w = carve(*pol, B, workspace);
+  PolicyTable tab = lrx_make_table(*pol);
+  const int P = pol->n_params;
+  const int ld = (int)w.rows;
+  const int nchunks = (int)((B + w.rows - 1) / w.rows);
+
+  auto input_of = [&](int c, int i) -> float* {
+    if (i > 0) return w.act_out[c][i - 1];
+    return c == 0 ? w.obsT : w.act_out[0][pol->n_layers[0] - 1];
+  };
+
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int64_t r0 = (int64_t)ch * w.rows;
+    const int rows = (int)((B - r0) < w.rows ? (B - r0) : w.rows);
+    const int splits = w.splits;
+    const int k_chunk = ((rows + splits - 1) / splits + 15) / 16 * 16;
+    gather_kernel<<<(rows + 255) / 256, 256, 0, s>>>(*buf, idx + r0, rows, ld, pol->obs_dim, pol->is_box, w.obsT,
+                                                     w.act_f, w.act_i, w.logp, w.adv, w.ret, w.val);
+    LRX_LAUNCH_CHECK();
+
+    // ---- forward: Out[out x rows] = act(W[out x in] * In[in x rows] + b), plus a ones row
+    for (int c = 0; c < 3; ++c) {
+      for (int i = 0; i < tab.count[c]; ++i) {
+        const LrxLayer& L = tab.L[tab.first[c] + i];
+        GemmArgs g{};
+        g.A = params + L.w_off; g.lda = L.in;
+        g.B = input_of(c, i); g.ldb = ld;
+        g.C = w.act_out[c][i]; g.ldc = ld;
+        g.M = L.out; g.N = rows; g.K = L.in;
+        g.bias = params + L.b_off; g.relu = L.relu; g.ones_row = 1;
+        g.k_chunk = L.in;
+        if ((rc = launch_gemm(g, false, false, 1, s))) return rc;
+      }
+    }
+
+    // ---- loss: dL/dvalue -> dval [1][rows], dL/dhead -> dhd [n_out][rows]
+    LossArgs la{};
+    la.value = w.act_out[1][pol->n_layers[1] - 1];
+    la.head = w.act_out[2][pol->n_layers[2] - 1];
+    la.ld = ld;
+    la.act_f = w.act_f; la.act_i = w.act_i;
+    la.logp_old = w.logp; la.adv = w.adv; la.ret = w.ret; la.val_old = w.val;
+    la.dvalue = w.dval; la.dhead = w.dhd;
+    la.rows = rows; la.n_out = pol->n_out; la.is_box = pol->is_box;
+    la.log_std_ptr = pol->is_box ? params + tab.log_std_off : nullptr;
+    la.adv_sums = adv_sums; la.B_global = (double)B_global; la.h = *h;
+    la.partial = w.loss_partial + (size_t)ch * w.loss_blocks * 8;
+    const int lblocks = (rows + LRX_LOSS_THREADS - 1) / LRX_LOSS_THREADS;
+    loss_kernel<<<lblocks, LRX_LOSS_THREADS, 0, s>>>(la);
+    LRX_LAUNCH_CHECK();
+
+    // ---- backward through one chain, starting from dOut = d_cur [out_last x rows]
+    auto backprop_chain = [&](int c, float* d_cur, float* d_final, bool accumulate_final) -> int {
+      for (int i = tab.count[c] - 1; i >= 0; --i) {
+        const LrxLayer& L = tab.L[tab.first[c] + i];
+        float* in = input_of(c, i);
+        // [dW | db] = dOut[out x rows] * [In ; 1]^T, split-K over the rows
+        GemmArgs g{};
+        g.A = d_cur; g.lda = ld;
+        g.B = in; g.ldb = ld;
+        g.C = w.partial + L.w_off; g.ldc = L.in;
+        g.C2 = w.partial + L.b_off; g.n_main = L.in;
+        g.M = L.out; g.N = L.in + 1; g.K = rows;
+        g.k_chunk = k_chunk; g.c_split_stride = (long long)w.P_pad;
+        g.accumulate = ch > 0;
+        int rcl = launch_gemm(g, false, true, splits, s);
+        if (rcl) return rcl;
+        if (i == 0 && c == 0) break;  // no gradient w.r.t. the observations
+        // dIn[in x rows] = W^T * dOut, masked by the ReLU of the layer that produced In
+        GemmArgs d{};
+        d.A = params + L.w_off; d.lda = L.in;
+        d.B = d_cur; d.ldb = ld;
+        d.M = L.in; d.N = rows; d.K = L.out; d.k_chunk = L.out;
+        float* dst;
+        if (i == 0) {
+          dst = d_final;  // gradient w.r.t. the encoder output (identity activation)
+          d.accumulate = accumulate_final;
+        } else {
+          dst = (d_cur == w.dA) ? w.dB : w.dA;
+          if (tab.L[tab.first[c] + i - 1].relu) { d.mask = in; d.ldm = ld; }
+        }
+        d.C = dst; d.ldc = ld;
+        rcl = launch_gemm(d, true, false, 1, s);
+        if (rcl) return rcl;
+        d_cur = dst;
+      }
+      return LRX_OK;
+    };
+    if ((rc = backprop_chain(1, w.dval, w.dfeat, false))) return rc;
+    if ((rc = backprop_chain(2, w.dhd, w.dfeat, true))) return rc;
+    if ((rc = backprop_chain(0, w.dfeat, nullptr, false))) return rc;
+  }
+
+  reduce_partials_kernel<<<(P + 255) / 256, 256, 0, s>>>(w.partial, w.splits, (long long)w.P_pad, P, w.loss_partial,
+                                                        nchunks * w.loss_blocks, tab.log_std_off,
+                                                        h->entropy_loss_coefficient, (double)B_global, gradbuf);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+extern "C" int lrx_ppo_apply(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
+                             int32_t* adam_count, const float* gradbuf, const LrxPpoHyper* h,
+                             float* stats_out, int32_t* nonfinite_flag, lrx_stream_t stream) {
+  int rc = lrx_validate_policy(pol);
+  if (rc) return rc;
+  LRX_REQUIRE(params && adam_m && adam_v && adam_count && gradbuf && h, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_apply: NULL pointer");
+  PolicyTable tab = lrx_make_table(*pol);
+  apply_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, adam_m, adam_v, adam_count, gradbuf, pol->n_params,
+                                                    tab.log_std_off, *h, stats_out, nonfinite_flag);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+extern "C" int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
+                              int32_t* adam_count, const LrxBatchView* buf, const int32_t* idx,
+                              int32_t num_batches, int64_t B, const LrxPpoHyper* h, float* stats_out,
+                              int32_t* nonfinite_flag, void* workspace, size_t workspace_bytes,
+                              lrx_stream_t stream) {
+  int rc = validate_update_args(pol, buf, h);
+  if (rc) return rc;
+  LRX_REQUIRE(num_batches >= 0 && num_batches <= LRX_MAX_BATCHES, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_update: num_batches out of range [0, %d]", LRX_MAX_BATCHES);
+  LRX_REQUIRE(B > 0 && idx && workspace && stats_out, LRX_ERR_INVALID_ARG, "lrx_ppo_update: bad argument");
+  const size_t need = lrx_ppo_workspace_bytes(pol, B);
+  LRX_REQUIRE(workspace_bytes >= need, LRX_ERR_INVALID_ARG, "lrx_ppo_update: workspace too small (%zu < %zu)",
+              workspace_bytes, need);
+  if (num_batches == 0) return LRX_OK;
+  Workspace w = carve(*pol, B, workspace);
+  // gradbuf lives at the head of the partial buffer region's tail: carve one more slot
+  float* gradbuf = (float*)((char*)workspace + need - align_up(w.P_pad * 4, 256));
+  rc = lrx_ppo_adv_sums(buf->adv, buf->N, buf->T, idx, num_batches, B, w.adv_sums, stream);
+  if (rc) return rc;
+  for (int b = 0; b < num_batches; ++b) {
+    rc = lrx_ppo_grad(pol, params, buf, idx + (size_t)b * B, B, B, w.adv_sums + 2 * b, h, gradbuf, workspace,
+                      workspace_bytes, stream);
+    if (rc) return rc;
+    rc = lrx_ppo_apply(pol, params, adam_m, adam_v, adam_count, gradbuf, h, stats_out + (size_t)b * LRX_PPO_NSTATS,
+                       nonfinite_flag, stream);
+    if (rc) return rc;
+  }
+  return LRX_OK;
+}

@@ -1,0 +1,160 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol declared in
+include/lerax_b200.h; host-side mirror logic (keys, spaces, PPO bookkeeping, descriptors)."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "lerax_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lrx_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    fns = header_functions()
+    for must in ("lrx_rollout", "lrx_gae", "lrx_ppo_update", "lrx_ppo_grad", "lrx_ppo_apply", "lrx_last_error"):
+        assert must in fns
+
+
+def test_library_exports_every_declared_symbol():
+    from lerax_b200 import _lib as L
+
+    raw = ctypes.CDLL(L.LIB_PATH)
+    for name in header_functions():
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+        assert name in L.PROTOTYPES, f"{name} has no ctypes prototype"
+    assert sorted(L.PROTOTYPES) == header_functions()
+    assert L.lib.lrx_version() == 100
+
+
+def test_struct_sizes_match_header_layout():
+    from lerax_b200 import _lib as L
+
+    assert ctypes.sizeof(L.LrxEnvDesc) == 4 + 4 + 4 + 16 * 4
+    assert ctypes.sizeof(L.LrxPolicyDesc) == 4 * 4 + 3 * 4 + 3 * 9 * 4 + 3 * 8 * 4
+    assert ctypes.sizeof(L.LrxRng) == 16
+    assert ctypes.sizeof(L.LrxRolloutOut) == 10 * 8
+    assert ctypes.sizeof(L.LrxPpoHyper) == 8 * 4 + 2 * 4
+    assert ctypes.sizeof(L.LrxBatchView) == 6 * 8 + 8
+
+
+def test_argument_validation_without_gpu():
+    """Validation happens before any CUDA call, so it is checkable on the CPU box."""
+    from lerax_b200 import _lib as L
+
+    assert L.lib.lrx_policy_num_params(None) == -1
+    d = L.LrxPolicyDesc()
+    assert L.lib.lrx_policy_forward(d, None, None, None, None, 1, None) < 0
+    assert L.lib.lrx_last_error() != b""
+    e = L.LrxEnvDesc()
+    e.kind = 9
+    assert L.lib.lrx_env_reset(e, L.LrxEnvState(), 4, L.LrxRng(), None, None) == -2
+    assert b"unsupported env kind" in L.lib.lrx_last_error()
+    assert L.lib.lrx_gae(None, None, None, None, None, None, -1, 4, 0.99, 0.95, 0, None, None) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from lerax_b200 import _lib as L
+    from lerax_b200.env.classic_control import CartPole
+
+    with pytest.raises(L.LeraxB200Error, match="no CPU fallback"):
+        CartPole().initial(key=0)
+
+
+def test_policy_descriptor_matches_oracle_layout():
+    from lerax_b200 import _lib as L
+    from lerax_b200.env.classic_control import Acrobot, CartPole, Pendulum
+    from lerax_b200.policy import MLPActorCriticPolicy
+    from oracle import policy as OP
+
+    for env, n_out, box in ((CartPole(), 2, False), (Pendulum(), 1, True), (Acrobot(), 3, False)):
+        for kw in ({}, dict(feature_width=256, value_width=256, action_width=256), dict(action_depth=1, value_depth=3)):
+            pol = MLPActorCriticPolicy(env, key=0, device="cpu", **kw)
+            spec = OP.make_spec(env.observation_space.flat_size, n_out, box, **kw)
+            assert pol.n_params == spec.n_params == L.lib.lrx_policy_num_params(pol.desc())
+            offs, ls = spec.offsets()
+            assert [(c, i, w, b, k, n) for (c, i, w, b, k, n) in offs] == pol._layout
+            assert ls == pol.log_std_offset
+            d = pol.desc()
+            for c in range(3):
+                assert tuple(d.dims[c][: d.n_layers[c] + 1]) == spec.dims[c]
+                assert tuple(bool(x) for x in d.relu[c][: d.n_layers[c]]) == spec.relu[c]
+            lim = 1 / np.sqrt(env.observation_space.flat_size)
+            w0 = pol.encoder.layers[0].weight.numpy()
+            assert w0.shape == (spec.dims[0][1], spec.dims[0][0]) and np.abs(w0).max() <= lim
+
+
+def test_env_descriptors_and_defaults():
+    from lerax_b200.env.classic_control import Acrobot, CartPole, Pendulum
+    from lerax_b200.wrapper import TimeLimit
+    from oracle import envs as OE
+
+    for env, o in ((CartPole(), OE.cartpole()), (Pendulum(), OE.pendulum()), (Acrobot(), OE.acrobot())):
+        d = env.desc()
+        assert d.kind == o.kind and d.dt == np.float32(o.dt) and d.max_episode_steps == 0
+        vals = [np.float32(v) for v in o.params.values()]
+        assert [d.p[i] for i in range(len(vals))] == vals
+    e = TimeLimit(Pendulum(g=5.0), 200)
+    assert e.desc().max_episode_steps == 200 and e.desc().p[2] == 5.0 and e.g == 5.0
+    with pytest.raises(NotImplementedError):
+        CartPole(solver="euler")
+
+
+def test_ppo_bookkeeping_matches_reference_formulas():
+    from lerax_b200.algorithm import PPO
+
+    a = PPO()
+    assert (a.num_envs, a.num_steps, a.num_epochs, a.batch_size) == (4, 2048, 10, 256)
+    assert a.num_iterations(2**16) == 8 and a.minibatches_per_epoch == 32
+    b = PPO(num_envs=5, num_steps=20, num_batches=32)  # 100 // 32 = 3 -> 33 minibatches (base_buffer.py:85-88)
+    assert b.batch_size == 3 and b.minibatches_per_epoch == 33
+    with pytest.raises(ValueError):
+        PPO(num_envs=1, num_steps=4, num_batches=32)
+    with pytest.raises(TypeError):
+        a.consolidate_callbacks(object())
+
+
+def test_callbacks_with_custom_on_step_are_rejected():
+    from lerax_b200.algorithm import PPO
+    from lerax_b200.callback import AbstractCallback, CallbackList, EmptyCallback
+
+    class Bad(AbstractCallback):
+        def on_step(self, ctx, *, key=None):
+            return 1
+
+    a = PPO()
+    assert isinstance(a.consolidate_callbacks(None), CallbackList)
+    assert isinstance(a.consolidate_callbacks([EmptyCallback()]), CallbackList)
+    with pytest.raises(NotImplementedError):
+        a.consolidate_callbacks([Bad()])
+
+
+def test_keys_split_deterministic_and_distinct():
+    from lerax_b200 import random as jr
+
+    k = jr.key(0)
+    a, b = jr.split(k, 2)
+    assert a != b and jr.split(k, 2) == [a, b]
+    assert len({int(x) for x in jr.split(k, 1000)}) == 1000
+    assert jr.key(0) != jr.key(1)
+
+
+def test_spaces():
+    from lerax_b200.space import Box, Discrete
+
+    b = Box(-2.0, 2.0)
+    assert b.shape == () and b.flat_size == 1 and b.contains(1.0) and not b.contains(3.0)
+    assert Box(-np.ones(3), np.ones(3)).flat_size == 3
+    d = Discrete(3)
+    assert d.n == 3 and d.contains(2) and not d.contains(3)

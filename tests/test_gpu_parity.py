@@ -1,0 +1,320 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the NumPy oracle on identical
+seeded inputs.  Tolerances are the ones BASELINE.json.north_star states: trajectories,
+log-probs, values and advantages within 1e-5 relative (fp32); one PPO update within 1e-4."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import envs as OE
+from oracle import gae as OG
+from oracle import philox as OPh
+from oracle import policy as OP
+from oracle import ppo as OU
+from oracle import rollout as OR
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 2e-6  # north_star: 1e-5 relative in fp32 (atol for values near zero)
+KINDS = ["cartpole", "pendulum", "acrobot"]
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def setup(kind, seed=0, N=64, mes=0, **pkw):
+    oenv = H.oracle_env(kind, max_episode_steps=mes)
+    spec = H.oracle_policy_spec(oenv, **pkw)
+    params = OP.init_params(spec, seed=seed, log_std_init=-0.5)
+    env = H.lib_env(kind, max_episode_steps=mes)
+    pol = H.lib_policy(env, params, **pkw)
+    rng = np.random.default_rng(seed + 1)
+    y0 = OE.initial_from_uniform(oenv, rng.random((oenv.state_dim, N)).astype(np.float32))
+    return oenv, spec, params, env, pol, rng, y0
+
+
+def noise_for(spec, rng, T, N, k):
+    na = (rng.standard_normal((T, N)) if spec.is_box else rng.gumbel(size=(T, N, spec.n_out))).astype(np.float32)
+    ru = rng.random((T, N, k)).astype(np.float32)
+    return na, ru
+
+
+# ------------------------------------------------------------------------ library
+def test_library_loaded_and_version():
+    from lerax_b200 import _lib as L
+
+    assert L.lib.lrx_version() == 100
+    assert os.path.basename(L.LIB_PATH) == "liblerax_b200.so"
+
+
+# --------------------------------------------------------------------------- envs
+@pytest.mark.parametrize("kind", KINDS)
+def test_env_reset_injected_and_philox(kind):
+    import torch
+
+    from lerax_b200 import _lib as L
+
+    oenv, spec, params, env, pol, rng, _ = setup(kind)
+    N, k = 1000, oenv.state_dim
+    u = rng.random((N, k)).astype(np.float32)
+    st = env.initial_from_uniform(H.dev(u))
+    np.testing.assert_array_equal(st.y.cpu().numpy(), OE.initial_from_uniform(oenv, u.T))
+    assert (st.t.cpu().numpy() == 0).all() and (st.step_count.cpu().numpy() == 0).all()
+    # Philox stream 2 (initial reset), counter (env, 0, 2, 0)
+    st = env.initial(key=1234, num_envs=N)
+    uu = OPh.uniforms(1234, np.arange(N, dtype=np.uint32), np.uint32(0), 2, k)
+    np.testing.assert_array_equal(st.y.cpu().numpy(), OE.initial_from_uniform(oenv, uu.T))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_env_step_teacher_forced(kind):
+    """One env.transition/reward/terminal/observation from identical (y, t, action)."""
+    oenv, spec, params, env, pol, rng, _ = setup(kind)
+    N = 4096
+    scale = {"cartpole": [2.0, 2.0, 0.2, 2.0], "pendulum": [3.0, 6.0], "acrobot": [3.0, 3.0, 6.0, 12.0]}[kind]
+    y = (rng.uniform(-1, 1, (oenv.state_dim, N)) * np.array(scale)[:, None]).astype(np.float32)
+    t = (rng.integers(0, 400, N) * np.float32(oenv.dt)).astype(np.float32)
+    a = rng.uniform(-3, 3, N).astype(np.float32) if oenv.is_box else rng.integers(0, oenv.n_actions, N).astype(np.int32)
+    from lerax_b200.env.classic_control import ClassicControlState
+
+    st = ClassicControlState(H.dev(y), H.dev(t), H.dev(np.zeros(N, np.int32)))
+    nxt, rew, term, trunc, obs = env.step_full(st, H.dev(a))
+    y1, t1 = OE.transition(oenv, y, t, a)
+    H.assert_close(nxt.y.cpu().numpy(), y1, 2e-6, 2e-6, "y'")
+    np.testing.assert_array_equal(nxt.t.cpu().numpy(), t1)
+    H.assert_close(rew.cpu().numpy(), OE.reward(oenv, y, a, y1), RTOL, ATOL, "reward")
+    got_term = term.cpu().numpy()
+    want_term = OE.terminal(oenv, y1)
+    assert (got_term != want_term).mean() < 1e-3  # threshold ties only
+    H.assert_close(obs.cpu().numpy(), OE.observation(oenv, nxt.y.cpu().numpy()).T, 2e-6, 2e-6, "obs")
+    np.testing.assert_array_equal(env.terminal(nxt).cpu().numpy(), got_term)
+    assert not trunc.any()
+
+
+# ------------------------------------------------------------------------- policy
+@pytest.mark.parametrize("kind,pkw", [("cartpole", {}), ("pendulum", {}), ("acrobot", {}),
+                                      ("pendulum", dict(feature_width=256, value_width=256, action_width=256)),
+                                      ("cartpole", dict(feature_size=8, feature_width=24, feature_depth=3,
+                                                        value_width=40, value_depth=1, action_width=12,
+                                                        action_depth=1))])
+def test_policy_forward(kind, pkw):
+    oenv, spec, params, env, pol, rng, _ = setup(kind, **pkw)
+    assert pol.n_params == spec.n_params
+    for B in (1, 33, 1000):
+        obs = rng.standard_normal((B, spec.obs_dim)).astype(np.float32)
+        v, head = OP.forward(spec, params, obs)
+        _, gv = pol.value(None, H.dev(obs))
+        H.assert_close(gv.cpu().numpy(), v, RTOL, ATOL, "value")
+        H.assert_close(pol.logits_or_loc(H.dev(obs)).cpu().numpy(), head, RTOL, ATOL, "head")
+
+
+# ------------------------------------------------------------------------ rollout
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("mes", [0, 7])
+def test_rollout_replay_matches_oracle(kind, mes):
+    """Same initial states + same action/reset noise => same trajectories, log-probs, values,
+    rewards (incl. truncation bootstrap) and dones."""
+    N, T = 96, 40
+    oenv, spec, params, env, pol, rng, y0 = setup(kind, N=N, mes=mes)
+    na, ru = noise_for(spec, rng, T, N, oenv.state_dim)
+    t0, sc0 = np.zeros(N, np.float32), np.zeros(N, np.int32)
+    want = OR.rollout(oenv, spec, params, y0, t0, sc0, T, 0.99, na, ru, trace=True)
+    got = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, na, ru)
+    # per-step teacher forcing: from the kernel's own (y_t, t_t, a_t) the oracle reproduces y_{t+1}
+    yk = got["y_trace"].transpose(1, 0, 2).reshape(oenv.state_dim, -1)
+    y1, _ = OE.transition(oenv, yk, got["t_trace"].reshape(-1), got["act"].reshape(-1))
+    H.assert_close(got["y_next_trace"].transpose(1, 0, 2).reshape(oenv.state_dim, -1), y1, 2e-6, 2e-6, "teacher-forced y'")
+    # free-running comparison against the oracle trajectory
+    if spec.is_box:
+        H.assert_close(got["act"], want["act"], RTOL, ATOL, "act")
+    else:
+        assert (got["act"] != want["act"]).mean() == 0
+    assert (got["done"] != want["done"]).mean() == 0
+    for name in ("obs", "logp", "val", "rew", "last_value", "y", "t"):
+        H.assert_close(got[name], want[name], 1e-4 if name in ("obs", "y") else RTOL, 1e-5, name)
+    np.testing.assert_array_equal(got["step_count"], want["step_count"])
+    if mes:
+        assert want["done"].any()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_rollout_free_running_philox(kind):
+    """Kernel-generated Philox noise == the oracle's restatement of the same keying."""
+    N, T, seed, eoff, soff = 64, 24, 0xABCDEF0123, 100, 7
+    oenv, spec, params, env, pol, rng, y0 = setup(kind, N=N)
+    envi = (np.arange(N, dtype=np.uint32) + np.uint32(eoff))[None, :]
+    stepi = (np.arange(T, dtype=np.uint32) + np.uint32(soff))[:, None]
+    na = OPh.normals(seed, envi, stepi) if spec.is_box else OPh.gumbels(seed, envi, stepi, spec.n_out)
+    ru = OPh.reset_uniforms(seed, envi, stepi, oenv.state_dim)
+    t0, sc0 = np.zeros(N, np.float32), np.zeros(N, np.int32)
+    want = OR.rollout(oenv, spec, params, y0, t0, sc0, T, 0.99, na.astype(np.float32), ru)
+    got = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, None, None, seed=seed, env_offset=eoff, step_offset=soff)
+    assert (got["done"] != want["done"]).mean() == 0
+    if not spec.is_box:
+        assert (got["act"] != want["act"]).mean() == 0
+    for name in ("obs", "logp", "val", "rew", "last_value"):
+        H.assert_close(got[name], want[name], 1e-4, 1e-4, name)  # device logf/cosf vs NumPy in the noise
+
+
+def test_rollout_deterministic_and_ragged_sizes():
+    oenv, spec, params, env, pol, rng, y0 = setup("cartpole", N=37)
+    t0, sc0 = np.zeros(37, np.float32), np.zeros(37, np.int32)
+    a = H.run_rollout(env, pol, y0, t0, sc0, 19, 0.99, seed=5)
+    b = H.run_rollout(env, pol, y0, t0, sc0, 19, 0.99, seed=5)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    c = H.run_rollout(env, pol, y0, t0, sc0, 19, 0.99, seed=6)
+    assert (a["act"] != c["act"]).any()
+    # T = 0: only last_value
+    z = H.run_rollout(env, pol, y0, t0, sc0, 0, 0.99, seed=5)
+    H.assert_close(z["last_value"], OP.value_only(spec, params, y0.T.copy()), RTOL, ATOL, "last_value T=0")
+
+
+# ---------------------------------------------------------------------------- GAE
+@pytest.mark.parametrize("layout", ["TN", "NT"])
+def test_gae_reference_known_answers(layout):
+    with open(os.path.join(GOLD, "gae.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        r = np.array(c["rewards"], np.float32)[:, None]
+        v = np.array(c["values"], np.float32)[:, None]
+        d = np.array(c["dones"], bool)[:, None]
+        if layout == "NT":
+            r, v, d = r.T, v.T, d.T
+        adv, ret = H.run_gae(r, v, d, [c["last_value"]], c["gamma"], c["lam"], layout)
+        np.testing.assert_allclose(adv.ravel(), c["advantages"], rtol=1e-6, atol=1e-6, err_msg=c["name"])
+        np.testing.assert_allclose(ret.ravel(), c["returns"], rtol=1e-6, atol=1e-6, err_msg=c["name"])
+
+
+@pytest.mark.parametrize("T,N", [(1, 1), (3, 5), (16, 33), (63, 31), (64, 64), (128, 257), (300, 40), (2048, 4)])
+@pytest.mark.parametrize("layout", ["TN", "NT"])
+def test_gae_matches_oracle(T, N, layout):
+    rng = np.random.default_rng(T * 1000 + N)
+    r = rng.standard_normal((T, N)).astype(np.float32)
+    v = rng.standard_normal((T, N)).astype(np.float32)
+    d = rng.random((T, N)) < 0.05
+    last = rng.standard_normal(N).astype(np.float32)
+    adv, ret = OG.gae(r, v, d, last, 0.99, 0.95)
+    if layout == "TN":
+        ga, gr, ev = H.run_gae(r, v, d, last, 0.99, 0.95, "TN", want_ev=True)
+    else:
+        ga, gr, ev = H.run_gae(r.T.copy(), v.T.copy(), d.T.copy(), last, 0.99, 0.95, "NT", want_ev=True)
+        ga, gr = ga.T, gr.T
+    H.assert_close(ga, adv, RTOL, 1e-5, "adv")
+    H.assert_close(gr, ret, RTOL, 1e-5, "ret")
+    want_ev = [ret.astype(np.float64).sum(), (ret.astype(np.float64) ** 2).sum(), adv.astype(np.float64).sum(),
+               (adv.astype(np.float64) ** 2).sum()]
+    np.testing.assert_allclose(ev, want_ev, rtol=1e-5, atol=1e-4)
+
+
+# ------------------------------------------------------------------------- update
+def synthetic_buffer(kind, T, N, seed=0, **pkw):
+    oenv, spec, params, env, pol, rng, y0 = setup(kind, seed=seed, N=N, **pkw)
+    na, ru = noise_for(spec, rng, T, N, oenv.state_dim)
+    ro = OR.rollout(oenv, spec, params, y0, np.zeros(N, np.float32), np.zeros(N, np.int32), T, 0.99, na, ru)
+    adv, ret = OG.gae(ro["rew"], ro["val"], ro["done"], ro["last_value"], 0.99, 0.95)
+    # decorrelate logp_old / val from the current policy so ratios != 1 and both clip branches occur
+    logp_old = (ro["logp"] + rng.normal(0, 0.25, ro["logp"].shape)).astype(np.float32)
+    planes = dict(obs=ro["obs"], act=ro["act"], logp=logp_old, val=ro["val"], ret=ret, adv=adv)
+    flat = {k: OU.flatten_time_major(v) for k, v in planes.items()}
+    buf = H.DeviceBuffer(**planes)
+    return spec, params, pol, rng, flat, buf
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("clip_v,ch,norm", [(False, 0.0, True), (True, 0.01, True), (False, 0.02, False)])
+def test_ppo_grad_matches_oracle(kind, clip_v, ch, norm):
+    T, N, B = 24, 20, 160
+    spec, params, pol, rng, flat, buf = synthetic_buffer(kind, T, N, seed=3)
+    hp = OU.Hyper(clip_value_loss=clip_v, entropy_loss_coefficient=ch, normalize_advantages=norm)
+    idx = rng.permutation(T * N)[:B].astype(np.int32)
+    _, stats, g = OU.ppo_loss_and_grad(spec, params, OU.gather(flat, idx), hp)
+    gb, sums = H.run_grad(pol, buf, idx, hp)
+    P = spec.n_params
+    a = flat["adv"][idx].astype(np.float64)
+    np.testing.assert_allclose(sums, [a.sum(), (a * a).sum()], rtol=1e-12)
+    gg = gb[:P].copy()
+    if spec.is_box:
+        gg[-1] -= ch  # the -c_H entropy term on log_std is added once, in lrx_ppo_apply
+    scale = np.abs(g).max()
+    H.assert_close(gg, g, 1e-4, 1e-4 * scale * 1e-1, "gradient")
+    got_stats = np.array([gb[P] - 1, 0, -gb[P + 1], gb[P + 2] / 2, -gb[P + 3]])
+    got_stats[1] = got_stats[2] + got_stats[3] * hp.value_loss_coefficient + got_stats[4] * ch
+    H.assert_close(got_stats, stats, 1e-4, 1e-5, "stats")
+    assert gb[P + 6] == 0
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_one_ppo_update_matches_oracle(kind):
+    """north_star: one PPO update from identical weights and minibatch indices matches
+    parameters within 1e-4."""
+    T, N, nb = 32, 16, 4
+    spec, params, pol, rng, flat, buf = synthetic_buffer(kind, T, N, seed=5)
+    hp = OU.Hyper(entropy_loss_coefficient=0.01)
+    idx = OU.batch_indices(T * N, T * N // nb, rng)[None]
+    p1, st, log = OU.train(spec, params.copy(), OU.AdamState.init(params), flat, idx, hp)
+    gp, gm, gv, cnt, stats, flag = H.run_update(pol, buf, idx, hp)
+    assert cnt == nb and flag == 0
+    H.assert_close(gp, p1, 1e-4, 1e-6, "params after one epoch")
+    H.assert_close(gm, st.m, 1e-3, 1e-7, "adam mu")
+    H.assert_close(gv, st.v, 1e-3, 1e-10, "adam nu")
+    s = stats[0].mean(axis=0)
+    H.assert_close(s[:5], [log["approx_kl"], log["loss"], log["policy_loss"], log["value_loss"], log["entropy_loss"]],
+                   1e-4, 1e-5, "log")
+    assert np.abs(gp - params).max() > 1e-5  # the update did something
+
+
+def test_full_train_ten_epochs_matches_oracle():
+    T, N, nb, E = 64, 8, 8, 10
+    spec, params, pol, rng, flat, buf = synthetic_buffer("cartpole", T, N, seed=9)
+    hp = OU.Hyper()
+    idx = np.stack([OU.batch_indices(T * N, T * N // nb, rng) for _ in range(E)])
+    p1, st, log = OU.train(spec, params.copy(), OU.AdamState.init(params), flat, idx, hp)
+    gp, gm, gv, cnt, stats, flag = H.run_update(pol, buf, idx, hp)
+    assert cnt == nb * E and flag == 0
+    # 80 sequential Adam steps: compare the parameter DISPLACEMENT
+    H.assert_close(gp - params, p1 - params, 2e-3, 2e-5, "displacement after full train")
+    H.assert_close(gp, p1, 1e-4, 2e-5, "params after full train")
+
+
+def test_update_wide_pendulum_config3():
+    """configs[2]: Pendulum, Gaussian policy, 256-wide MLPs (generic-width path)."""
+    pkw = dict(feature_width=256, value_width=256, action_width=256)
+    T, N, nb = 16, 24, 3
+    spec, params, pol, rng, flat, buf = synthetic_buffer("pendulum", T, N, seed=11, **pkw)
+    assert spec.n_params == 149811
+    hp = OU.Hyper(entropy_loss_coefficient=0.01)
+    idx = OU.batch_indices(T * N, T * N // nb, rng)[None]
+    p1, st, log = OU.train(spec, params.copy(), OU.AdamState.init(params), flat, idx, hp)
+    gp, gm, gv, cnt, stats, flag = H.run_update(pol, buf, idx, hp)
+    assert cnt == nb and flag == 0
+    H.assert_close(gp, p1, 1e-4, 1e-6, "params (256-wide)")
+
+
+def test_nonfinite_flag_and_skip():
+    T, N = 8, 8
+    spec, params, pol, rng, flat, buf = synthetic_buffer("cartpole", T, N, seed=13)
+    import torch
+
+    buf.t["obs"][0, 0, 0] = float("inf")
+    idx = np.arange(T * N, dtype=np.int32).reshape(1, 1, -1)
+    gp, gm, gv, cnt, stats, flag = H.run_update(pol, buf, idx, OU.Hyper())
+    assert flag == 1 and cnt == 0
+    np.testing.assert_array_equal(gp, params)  # update skipped, parameters untouched
+    torch.cuda.synchronize()
+
+
+def test_invalid_arguments_are_reported():
+    from lerax_b200 import _lib as L
+
+    env = H.lib_env("cartpole")
+    penv = H.lib_env("pendulum")
+    pol = H.lib_policy(penv, np.zeros(12915, np.float32))
+    with pytest.raises(L.LeraxB200Error, match="obs_dim"):
+        H.run_rollout(env, pol, np.zeros((4, 4), np.float32), np.zeros(4, np.float32), np.zeros(4, np.int32), 2, 0.99)
+    d = pol.desc()
+    d.n_params = 7
+    assert L.lib.lrx_policy_forward(d, None, None, None, None, 1, None) == -1
+    assert b"n_params" in L.lib.lrx_last_error()
