@@ -388,7 +388,7 @@ extern "C" int lrx_rollout(const LrxEnvDesc* env, const LrxPolicyDesc* pol, cons
   LRX_REQUIRE(N >= 0 && T >= 0, LRX_ERR_INVALID_ARG, "lrx_rollout: negative N or T");
   LRX_REQUIRE(params && state.y && state.t && state.step_count, LRX_ERR_INVALID_ARG,
               "lrx_rollout: NULL params/state");
-  LRX_REQUIRE(out.obs && out.act && out.rew && out.done && out.logp && out.val && out.last_value,
+  LRX_REQUIRE(out.last_value && (T == 0 || (out.obs && out.act && out.rew && out.done && out.logp && out.val)),
               LRX_ERR_INVALID_ARG, "lrx_rollout: NULL output plane");
   LRX_REQUIRE(pol->obs_dim == lrx_env_obs_dim(env->kind), LRX_ERR_INVALID_ARG,
               "policy obs_dim %d does not match env obs dim %d", pol->obs_dim, lrx_env_obs_dim(env->kind));
