@@ -237,6 +237,23 @@ int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* adam_m, float
                    int32_t* nonfinite_flag, void* workspace, size_t workspace_bytes,
                    lrx_stream_t stream);
 
+/* ------------------------------------------------------------------ diagnostics
+ * Self-test of the tensor-core building blocks the fused kernels are made of (tcgen05.mma
+ * kind::tf32 with the 3xTF32 split, operands in the canonical no-swizzle shared-memory
+ * layout, accumulator in TMEM): D = A[M][K] * B[N][K]^T on ONE SM.  M in {64,128};
+ * N multiple of 8 (16 when M = 128); K multiple of 8.  cfg_host (HOST pointer, 12 ints):
+ * {mn, s_mn, s_k, lbo, sbo, kstep} for A then B -- mn = 1 stages that operand MN-major (the
+ * transposed reading the weight-gradient GEMMs use), s_* are the storage strides between
+ * core-matrix groups and lbo/sbo/kstep the descriptor fields, all in bytes.  split = 1 -> 3xTF32.
+ * dump receives the raw accumulator [128 TMEM lanes][N].  Not part of the reference path. */
+int lrx_debug_umma_gemm(const float* A, const float* B, float* dump, int32_t M, int32_t N, int32_t K,
+                        const int32_t* cfg_host, int32_t split, lrx_stream_t stream);
+
+/* Same for the bf16x3 fp32 emulation (kind::f16, bf16 pieces x = p0+p1+p2, nprod = 1, 3 or 6
+ * products kept; K multiple of 16; 2-byte elements, 8 per 16-byte chunk). */
+int lrx_debug_umma_gemm_bf16(const float* A, const float* B, float* dump, int32_t M, int32_t N, int32_t K,
+                             const int32_t* cfg_host, int32_t nprod, lrx_stream_t stream);
+
 /* ------------------------------------------------------------------------- misc */
 const char* lrx_last_error(void);
 int lrx_version(void);

@@ -1,0 +1,301 @@
+// Self-test of the tcgen05 building blocks (lrx_umma.cuh): one CTA computes D = A * B^T with
+// kind::tf32 MMAs (optionally the 3xTF32 split) from operands staged in the canonical shared
+// memory layout, in K-major or MN-major form, and dumps the raw TMEM accumulator
+// [128 lanes][N columns] so the test can also check the lane mapping of M = 64.
+#include "lrx_common.cuh"
+#include "lrx_umma.cuh"
+
+struct SelftestOperand {
+  int mn;        // 0: K-major core matrices (8 mn x 16 B of k), 1: MN-major (8 k x 16 B of mn)
+  int s_mn;      // storage byte stride between core-matrix groups along MN
+  int s_k;       // storage byte stride between core-matrix groups along K
+  int lbo, sbo;  // descriptor fields (bytes)
+  int kstep;     // start-address advance per MMA (K = 8), bytes
+};
+struct SelftestCfg {
+  SelftestOperand a, b;
+};
+
+__device__ __forceinline__ uint32_t selftest_off(const SelftestOperand& o, int mn, int k) {
+  return o.mn ? (uint32_t)((mn & 3) * 4 + (mn >> 2) * o.s_mn + (k & 7) * 16 + (k >> 3) * o.s_k)
+              : (uint32_t)((mn & 7) * 16 + (mn >> 3) * o.s_mn + (k & 3) * 4 + (k >> 2) * o.s_k);
+}
+
+__global__ void __launch_bounds__(128)
+umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ dump,
+                     int M, int N, int K, SelftestCfg cfg, int split, uint32_t bytesA, uint32_t bytesB) {  // NOLINT
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = a_hi + bytesA;
+  uint8_t* b_hi = a_lo + bytesA;
+  uint8_t* b_lo = b_hi + bytesB;
+  const bool raw_a = cfg.a.mn & 2, raw_b = cfg.b.mn & 2;  // probe mode: fill with the word index
+  const uint32_t lt_a = (cfg.a.mn >> 4) & 7, lt_b = (cfg.b.mn >> 4) & 7;  // descriptor layout_type (probe)
+  cfg.a.mn &= 1;
+  cfg.b.mn &= 1;
+  if (raw_a) {
+    for (uint32_t w = tid; w < bytesA / 4; w += blockDim.x) {
+      ((float*)a_hi)[w] = umma::tf32_hi((float)w);
+      ((float*)a_lo)[w] = umma::tf32_lo((float)w);
+    }
+  } else {
+    for (int i = tid; i < M * K; i += blockDim.x) {
+      const int m = i / K, k = i % K;
+      const float x = A[i];
+      const uint32_t off = selftest_off(cfg.a, m, k);
+      *(float*)(a_hi + off) = umma::tf32_hi(x);
+      *(float*)(a_lo + off) = umma::tf32_lo(x);
+    }
+  }
+  if (raw_b) {
+    for (uint32_t w = tid; w < bytesB / 4; w += blockDim.x) {
+      ((float*)b_hi)[w] = umma::tf32_hi((float)w);
+      ((float*)b_lo)[w] = umma::tf32_lo((float)w);
+    }
+  } else {
+    for (int i = tid; i < N * K; i += blockDim.x) {
+      const int n = i / K, k = i % K;
+      const float x = B[i];
+      const uint32_t off = selftest_off(cfg.b, n, k);
+      *(float*)(b_hi + off) = umma::tf32_hi(x);
+      *(float*)(b_lo + off) = umma::tf32_lo(x);
+    }
+  }
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+
+  // clear the accumulator region through tcgen05.st so untouched lanes read back as zero
+  {
+    float z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0.f;
+    for (int c = 0; c < 256; c += 16) umma::tmem_st16(umma::tmem_addr(tbase, warp * 32, c), z);
+    umma::tmem_st_wait();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    umma::tc_fence_after();
+    const uint32_t idesc = umma::idesc_tf32(M, N, cfg.a.mn, cfg.b.mn);
+    const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo);
+    const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 8; ++ks) {
+      const uint32_t ao = ks * cfg.a.kstep, bo = ks * cfg.b.kstep;
+      if (split) {
+        umma::mma_tf32(tbase, umma::smem_desc(al + ao, cfg.a.lbo, cfg.a.sbo, lt_a), umma::smem_desc(bh + bo, cfg.b.lbo, cfg.b.sbo, lt_b), idesc, acc);
+        umma::mma_tf32(tbase, umma::smem_desc(ah + ao, cfg.a.lbo, cfg.a.sbo, lt_a), umma::smem_desc(bl + bo, cfg.b.lbo, cfg.b.sbo, lt_b), idesc, 1u);
+        acc = 1u;
+      }
+      umma::mma_tf32(tbase, umma::smem_desc(ah + ao, cfg.a.lbo, cfg.a.sbo, lt_a), umma::smem_desc(bh + bo, cfg.b.lbo, cfg.b.sbo, lt_b), idesc, acc);
+      acc = 1u;
+    }
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::tc_fence_after();
+
+  for (int c = 0; c < N; c += 8) {
+    float v[8];
+    umma::tmem_ld8(umma::tmem_addr(tbase, warp * 32, c), v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dump[(size_t)tid * N + c + i] = v[i];
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 256);
+}
+
+static uint32_t selftest_extent(SelftestOperand o, int MN, int K) {
+  // one past the last byte any element touches
+  o.mn &= 1;
+  uint32_t mx = 0;
+  for (int mn = 0; mn < MN; ++mn)
+    for (int k = 0; k < K; ++k) {
+      uint32_t off = o.mn ? (uint32_t)((mn & 3) * 4 + (mn >> 2) * o.s_mn + (k & 7) * 16 + (k >> 3) * o.s_k)
+                          : (uint32_t)((mn & 7) * 16 + (mn >> 3) * o.s_mn + (k & 3) * 4 + (k >> 2) * o.s_k);
+      if (off + 4 > mx) mx = off + 4;
+    }
+  return (mx + 1023u) / 1024u * 1024u;
+}
+
+// D = A[M][K] * B[N][K]^T on one SM's tensor core; dump receives the raw accumulator
+// [128][N] (TMEM lane major).  cfg_host: 12 ints = {mn, s_mn, s_k, lbo, sbo, kstep} for A then B
+// (storage strides and descriptor fields in bytes).  Test-only entry point (tests/test_gpu_umma.py).
+extern "C" int lrx_debug_umma_gemm(const float* A, const float* B, float* dump, int32_t M, int32_t N,
+                                   int32_t K, const int32_t* cfg_host, int32_t split, lrx_stream_t stream) {
+  LRX_REQUIRE(A && B && dump && cfg_host, LRX_ERR_INVALID_ARG, "lrx_debug_umma_gemm: NULL pointer");
+  LRX_REQUIRE((M == 64 || M == 128) && N >= 8 && N <= 256 && N % 8 == 0 && (M == 64 || N % 16 == 0) &&
+                  K >= 8 && K % 8 == 0,
+              LRX_ERR_INVALID_ARG, "lrx_debug_umma_gemm: unsupported shape M=%d N=%d K=%d", M, N, K);
+  SelftestCfg cfg;
+  const int32_t* c = cfg_host;
+  cfg.a = SelftestOperand{c[0], c[1], c[2], c[3], c[4], c[5]};
+  cfg.b = SelftestOperand{c[6], c[7], c[8], c[9], c[10], c[11]};
+  const uint32_t bytesA = (c[0] & 2) ? 32768u : selftest_extent(cfg.a, M, K);
+  const uint32_t bytesB = (c[6] & 2) ? 32768u : selftest_extent(cfg.b, N, K);
+  const size_t smem = (size_t)2 * (bytesA + bytesB);
+  LRX_REQUIRE(smem <= 200 * 1024, LRX_ERR_INVALID_ARG, "lrx_debug_umma_gemm: operands exceed shared memory");
+  LRX_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, dump, M, N, K, cfg, split, bytesA, bytesB);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+// ------------------------------------------------------------------ bf16x3 variant
+// fp32 emulation with bf16 pieces: x = p0 + p1 + p2 (8 mantissa bits each, truncation), products
+// p_i * q_j kept for i + j <= 2 (6 MMAs, kind::f16, fp32 accumulation).  Element size 2 bytes:
+// a 16-byte chunk holds 8 consecutive k (K-major) or 8 consecutive mn (MN-major); K = 16 per MMA.
+#include <cuda_bf16.h>
+
+__device__ __forceinline__ void bf16_split3(float x, __nv_bfloat16 (&p)[3]) {
+  float r = x;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float h = __uint_as_float(__float_as_uint(r) & 0xFFFF0000u);  // exact bf16 (truncation)
+    p[i] = __float2bfloat16_rn(h);
+    r -= h;
+  }
+}
+
+__device__ __forceinline__ uint32_t selftest_off16(const SelftestOperand& o, int mn, int k) {
+  return o.mn ? (uint32_t)((mn & 7) * 2 + (mn >> 3) * o.s_mn + (k & 7) * 16 + (k >> 3) * o.s_k)
+              : (uint32_t)((mn & 7) * 16 + (mn >> 3) * o.s_mn + (k & 7) * 2 + (k >> 3) * o.s_k);
+}
+
+__global__ void __launch_bounds__(128)
+umma_selftest_bf16_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ dump,
+                          int M, int N, int K, SelftestCfg cfg, int nprod, uint32_t bytesA, uint32_t bytesB) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool raw_a = cfg.a.mn & 2, raw_b = cfg.b.mn & 2;
+  const uint32_t lt_a = (cfg.a.mn >> 4) & 7, lt_b = (cfg.b.mn >> 4) & 7;
+  cfg.a.mn &= 1;
+  cfg.b.mn &= 1;
+  uint8_t* a_p[3] = {smem, smem + bytesA, smem + 2 * bytesA};
+  uint8_t* b_p[3] = {smem + 3 * bytesA, smem + 3 * bytesA + bytesB, smem + 3 * bytesA + 2 * bytesB};
+  __nv_bfloat16 pc[3];
+  if (raw_a) {
+    for (uint32_t w = tid; w < bytesA / 2; w += blockDim.x) {
+      bf16_split3((float)w, pc);
+      for (int i = 0; i < 3; ++i) ((__nv_bfloat16*)a_p[i])[w] = pc[i];
+    }
+  } else {
+    for (int i = tid; i < M * K; i += blockDim.x) {
+      bf16_split3(A[i], pc);
+      const uint32_t off = selftest_off16(cfg.a, i / K, i % K);
+      for (int q = 0; q < 3; ++q) *(__nv_bfloat16*)(a_p[q] + off) = pc[q];
+    }
+  }
+  if (raw_b) {
+    for (uint32_t w = tid; w < bytesB / 2; w += blockDim.x) {
+      bf16_split3((float)w, pc);
+      for (int i = 0; i < 3; ++i) ((__nv_bfloat16*)b_p[i])[w] = pc[i];
+    }
+  } else {
+    for (int i = tid; i < N * K; i += blockDim.x) {
+      bf16_split3(B[i], pc);
+      const uint32_t off = selftest_off16(cfg.b, i / K, i % K);
+      for (int q = 0; q < 3; ++q) *(__nv_bfloat16*)(b_p[q] + off) = pc[q];
+    }
+  }
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  {
+    float z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0.f;
+    for (int c = 0; c < 256; c += 16) umma::tmem_st16(umma::tmem_addr(tbase, warp * 32, c), z);
+    umma::tmem_st_wait();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    umma::tc_fence_after();
+    const uint32_t idesc = umma::idesc_bf16(M, N, cfg.a.mn, cfg.b.mn);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t ao = ks * cfg.a.kstep, bo = ks * cfg.b.kstep;
+      // smallest products first: i + j = 2, then 1, then 0
+      for (int sum = (nprod >= 6 ? 2 : (nprod >= 3 ? 1 : 0)); sum >= 0; --sum)
+        for (int i = 0; i <= sum; ++i) {
+          const int j = sum - i;
+          umma::mma_f16(tbase, umma::smem_desc(umma::smem_u32(a_p[i]) + ao, cfg.a.lbo, cfg.a.sbo, lt_a),
+                        umma::smem_desc(umma::smem_u32(b_p[j]) + bo, cfg.b.lbo, cfg.b.sbo, lt_b), idesc, acc);
+          acc = 1u;
+        }
+    }
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::tc_fence_after();
+  for (int c = 0; c < N; c += 8) {
+    float v[8];
+    umma::tmem_ld8(umma::tmem_addr(tbase, warp * 32, c), v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dump[(size_t)tid * N + c + i] = v[i];
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 256);
+}
+
+static uint32_t selftest_extent16(SelftestOperand o, int MN, int K) {
+  o.mn &= 1;
+  uint32_t mx = 0;
+  for (int mn = 0; mn < MN; ++mn)
+    for (int k = 0; k < K; ++k) {
+      uint32_t off = o.mn ? (uint32_t)((mn & 7) * 2 + (mn >> 3) * o.s_mn + (k & 7) * 16 + (k >> 3) * o.s_k)
+                          : (uint32_t)((mn & 7) * 16 + (mn >> 3) * o.s_mn + (k & 7) * 2 + (k >> 3) * o.s_k);
+      if (off + 2 > mx) mx = off + 2;
+    }
+  return (mx + 1023u) / 1024u * 1024u;
+}
+
+// Same contract as lrx_debug_umma_gemm for the bf16x3 emulation (K multiple of 16; nprod = 1, 3 or 6
+// products kept).
+extern "C" int lrx_debug_umma_gemm_bf16(const float* A, const float* B, float* dump, int32_t M, int32_t N,
+                                        int32_t K, const int32_t* cfg_host, int32_t nprod, lrx_stream_t stream) {
+  LRX_REQUIRE(A && B && dump && cfg_host, LRX_ERR_INVALID_ARG, "lrx_debug_umma_gemm_bf16: NULL pointer");
+  LRX_REQUIRE((M == 64 || M == 128) && N >= 8 && N <= 256 && N % 8 == 0 && (M == 64 || N % 16 == 0) &&
+                  K >= 16 && K % 16 == 0,
+              LRX_ERR_INVALID_ARG, "lrx_debug_umma_gemm_bf16: unsupported shape M=%d N=%d K=%d", M, N, K);
+  SelftestCfg cfg;
+  const int32_t* c = cfg_host;
+  cfg.a = SelftestOperand{c[0], c[1], c[2], c[3], c[4], c[5]};
+  cfg.b = SelftestOperand{c[6], c[7], c[8], c[9], c[10], c[11]};
+  const uint32_t bytesA = (c[0] & 2) ? 16384u : selftest_extent16(cfg.a, M, K);
+  const uint32_t bytesB = (c[6] & 2) ? 16384u : selftest_extent16(cfg.b, N, K);
+  const size_t smem = (size_t)3 * (bytesA + bytesB);
+  LRX_REQUIRE(smem <= 200 * 1024, LRX_ERR_INVALID_ARG, "lrx_debug_umma_gemm_bf16: operands exceed shared memory");
+  LRX_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_bf16_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, dump, M, N, K, cfg, nprod, bytesA, bytesB);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}

@@ -403,7 +403,6 @@ struct Workspace {
   float* act_f; int32_t* act_i; float* logp; float* adv; float* ret; float* val;
   float* partial;        // [splits][P_pad]
   double* loss_partial;  // [loss_blocks][8]
-  double* adv_sums;      // [LRX_MAX_BATCHES][2] for lrx_ppo_update
   size_t total;
 };
 constexpr int LRX_MAX_BATCHES = 4096;
@@ -444,20 +443,37 @@ static Workspace carve(const LrxPolicyDesc& pol, int64_t B, void* base) {
   w.val = (float*)take(rows * 4);
   w.partial = (float*)take((size_t)w.splits * w.P_pad * 4);
   w.loss_partial = (double*)take((size_t)w.loss_blocks * 8 * sizeof(double) * ((B + rows - 1) / rows));
-  w.adv_sums = (double*)take((size_t)LRX_MAX_BATCHES * 2 * sizeof(double));
   w.total = off;
   return w;
 }
 
 size_t lrx_fused_workspace_bytes(const LrxPolicyDesc* pol, int64_t B);
 
-extern "C" size_t lrx_ppo_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) {
-  if (!pol || lrx_validate_policy(pol) != LRX_OK || B <= 0) return 0;
+// Workspace = [max(generic scratch, fused scratch)] [adv_sums of lrx_ppo_update] [gradbuf of lrx_ppo_update].
+struct WorkspaceTail {
+  size_t adv_sums_off, gradbuf_off, total;
+};
+static WorkspaceTail workspace_tail(const LrxPolicyDesc* pol, int64_t B) {
   Workspace w = carve(*pol, B, nullptr);
   size_t a = w.total;
   size_t f = lrx_fused_workspace_bytes(pol, B);
-  // the last slot is the gradbuf lrx_ppo_update hands to grad/apply
-  return (a > f ? a : f) + align_up(w.P_pad * 4, 256);
+  WorkspaceTail t{};
+  t.adv_sums_off = a > f ? a : f;
+  t.gradbuf_off = t.adv_sums_off + align_up((size_t)LRX_MAX_BATCHES * 2 * sizeof(double), 256);
+  t.total = t.gradbuf_off + align_up(w.P_pad * 4, 256);
+  return t;
+}
+
+extern "C" size_t lrx_ppo_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) {
+  if (!pol || lrx_validate_policy(pol) != LRX_OK || B <= 0) return 0;
+  return workspace_tail(pol, B).total;
+}
+
+void lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
+                                int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
+                                cudaStream_t s) {
+  reduce_partials_kernel<<<(P + 255) / 256, 256, 0, s>>>(partial, splits, stride, P, loss_partial, loss_blocks,
+                                                       log_std_off, ent_coef, B_global, gradbuf);
 }
 
 // ======================================================================== host driver
@@ -502,8 +518,8 @@ extern "C" int lrx_ppo_grad(const LrxPolicyDesc* pol, const float* params, const
               "lrx_ppo_grad: bad argument");
   LRX_REQUIRE(!h->normalize_advantages || adv_sums, LRX_ERR_INVALID_ARG,
               "lrx_ppo_grad: adv_sums required when normalize_advantages is set");
-  LRX_REQUIRE(workspace_bytes >= lrx_ppo_workspace_bytes(pol, B), LRX_ERR_INVALID_ARG,
-              "lrx_ppo_grad: workspace too small (%zu < %zu)", workspace_bytes, lrx_ppo_workspace_bytes(pol, B));
+  LRX_REQUIRE(workspace_bytes >= workspace_tail(pol, B).adv_sums_off, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_grad: workspace too small (%zu < %zu)", workspace_bytes, workspace_tail(pol, B).adv_sums_off);
   cudaStream_t s = (cudaStream_t)stream;
 
   bool handled = false;
@@ -639,14 +655,14 @@ extern "C" int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* ad
   LRX_REQUIRE(workspace_bytes >= need, LRX_ERR_INVALID_ARG, "lrx_ppo_update: workspace too small (%zu < %zu)",
               workspace_bytes, need);
   if (num_batches == 0) return LRX_OK;
-  Workspace w = carve(*pol, B, workspace);
-  // gradbuf lives at the head of the partial buffer region's tail: carve one more slot
-  float* gradbuf = (float*)((char*)workspace + need - align_up(w.P_pad * 4, 256));
-  rc = lrx_ppo_adv_sums(buf->adv, buf->N, buf->T, idx, num_batches, B, w.adv_sums, stream);
+  const WorkspaceTail tail = workspace_tail(pol, B);
+  double* adv_sums = (double*)((char*)workspace + tail.adv_sums_off);
+  float* gradbuf = (float*)((char*)workspace + tail.gradbuf_off);
+  rc = lrx_ppo_adv_sums(buf->adv, buf->N, buf->T, idx, num_batches, B, adv_sums, stream);
   if (rc) return rc;
   for (int b = 0; b < num_batches; ++b) {
-    rc = lrx_ppo_grad(pol, params, buf, idx + (size_t)b * B, B, B, w.adv_sums + 2 * b, h, gradbuf, workspace,
-                      workspace_bytes, stream);
+    rc = lrx_ppo_grad(pol, params, buf, idx + (size_t)b * B, B, B, adv_sums + 2 * b, h, gradbuf, workspace,
+                      tail.adv_sums_off, stream);
     if (rc) return rc;
     rc = lrx_ppo_apply(pol, params, adam_m, adam_v, adam_count, gradbuf, h, stats_out + (size_t)b * LRX_PPO_NSTATS,
                        nonfinite_flag, stream);

@@ -1,14 +1,595 @@
-// Fused per-warp PPO gradient kernel for the default policy widths (tried before the
-// generic layer-by-layer path).
+// Fused PPO minibatch gradient for the default MLPActorCriticPolicy widths on the tensor
+// cores (tcgen05, bf16x3 fp32 emulation, accumulators in TMEM).
+//
+// Reference: algorithm/ppo.py:396-469 (ppo_loss + filter_value_and_grad) over the gathered
+// minibatch of buffer/base_buffer.py:90-103, i.e. exactly what lrx_ppo_grad's generic
+// layer-by-layer path computes; this kernel is tried first and handles the default widths
+// (encoder d->64->64->16, value head 16->64->64->1, action head 16->64->16->n_out).
+//
+// One persistent CTA per SM.  The Linear weights (bf16 pieces) stay resident in shared
+// memory for the whole launch; a CTA walks 64-row tiles of the minibatch:
+//   gather rows -> encoder fwd -> value head fwd -> value loss -> value head bwd ->
+//   action head fwd -> policy loss -> action head bwd -> encoder bwd,
+// every Linear fwd / dX being one group of tcgen05.mma (M = 64 rows) whose fp32 result is
+// pulled from TMEM by the row's thread for bias / ReLU / loss arithmetic and written back as
+// the next operand.  The weight and bias gradients (contraction over the rows) are
+// tcgen05.mma groups too, ACCUMULATED IN TMEM ACROSS ALL TILES of the CTA and flushed once
+// per launch as a per-CTA partial; a fixed-order reduction over CTAs (reduce_partials_kernel)
+// makes the result deterministic.  HBM traffic per row is the 32-36 gathered bytes.
+#include <stdlib.h>
+
 #include "lrx_common.cuh"
 #include "lrx_policy.cuh"
+#include "lrx_tc.cuh"
 
-size_t lrx_fused_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) { return 0; }
+namespace {
+
+constexpr int ROWS = 64;       // rows per tile = UMMA M
+constexpr int THREADS = 128;   // 4 warps; lanes 0-15 of warp q own rows 16q..16q+15 (TMEM lanes 32q..32q+15)
+
+// ---- shared memory map (bytes).  Matrices: piece stride = R * C * 2.
+constexpr uint32_t PS16 = ROWS * 16 * 2;  // [64][16] piece
+constexpr uint32_t PS64 = ROWS * 64 * 2;  // [64][64] piece
+constexpr uint32_t PS8 = ROWS * 8 * 2;    // [64][8] piece
+constexpr uint32_t OFF_W0 = 0;                         // [64][16]
+constexpr uint32_t OFF_W1 = OFF_W0 + 3 * PS16;         // [64][64]
+constexpr uint32_t OFF_W2 = OFF_W1 + 3 * PS64;         // [16][64]  (piece = 16*64*2 = PS16)
+constexpr uint32_t OFF_WV0 = OFF_W2 + 3 * PS16;        // [64][16]
+constexpr uint32_t OFF_WV1 = OFF_WV0 + 3 * PS16;       // [64][64]
+constexpr uint32_t OFF_WA0 = OFF_WV1 + 3 * PS64;       // [64][16]
+constexpr uint32_t OFF_WA1 = OFF_WA0 + 3 * PS16;       // [16][64]
+constexpr uint32_t OFF_XOBS = OFF_WA1 + 3 * PS16;      // [64][16] observations (zero padded)
+constexpr uint32_t OFF_XH1 = OFF_XOBS + 3 * PS16;      // [64][64]
+constexpr uint32_t OFF_XH2 = OFF_XH1 + 3 * PS64;       // [64][64]
+constexpr uint32_t OFF_XF = OFF_XH2 + 3 * PS64;        // [64][16] features
+constexpr uint32_t OFF_XB1 = OFF_XF + 3 * PS16;        // [64][64] head layer-1 activations (value, then action)
+constexpr uint32_t OFF_XB2 = OFF_XB1 + 3 * PS64;       // [64][64] value layer-2 / [64][16] action layer-2
+constexpr uint32_t OFF_DY64 = OFF_XB2 + 3 * PS64;      // [64][64] current upstream gradient
+constexpr uint32_t OFF_DY16 = OFF_DY64 + 3 * PS64;     // [64][16]
+constexpr uint32_t OFF_DY8 = OFF_DY16 + 3 * PS16;      // [64][8]  dvalue / dlogits
+constexpr uint32_t OFF_ONES = OFF_DY8 + 3 * PS8;       // [64][8]  all ones (one piece)
+constexpr uint32_t OFF_F32 = OFF_ONES + PS8;           // fp32 biases etc. (tc::F_COUNT floats)
+constexpr uint32_t OFF_MISC = OFF_F32 + 640 * 4;       // mbarrier, TMEM slot
+constexpr uint32_t SMEM_BYTES = OFF_MISC + 64;
+static_assert(SMEM_BYTES <= 227 * 1024, "fused update kernel exceeds shared memory");
+static_assert(tc::F_COUNT <= 640, "fp32 parameter block too small");
+
+// ---- TMEM columns (fp32; M = 64 accumulators use lanes 0-15 of every 32-lane quadrant)
+constexpr uint32_t C_D0 = 0;       // 64: layer outputs
+constexpr uint32_t C_DF = 128;     // 16: d(features), summed over both heads
+constexpr uint32_t C_G0 = 144;     // enc0  dW^T [64 out][16 in | 8 bias]
+constexpr uint32_t C_G1 = 168;     // enc1  dW^T [64][64 | 8]
+constexpr uint32_t C_G2 = 240;     // enc2  dW   [64 in][16 out]
+constexpr uint32_t C_GB2 = 256;    // enc2  db   [*][16]
+constexpr uint32_t C_GV0 = 272;    // v0    dW^T [64][16 | 8]
+constexpr uint32_t C_GV1 = 296;    // v1    dW^T [64][64 | 8]
+constexpr uint32_t C_GV2 = 368;    // v2    dW   [64 in][8] (col 0)
+constexpr uint32_t C_GBV2 = 376;   // v2    db   [*][8]  (col 0)
+constexpr uint32_t C_GA0 = 384;    // a0    dW^T [64][16 | 8]
+constexpr uint32_t C_GA1 = 408;    // a1    dW   [64 in][16 out]
+constexpr uint32_t C_GBA1 = 424;   // a1    db   [*][16]
+constexpr uint32_t C_GMAP = 440;   // map   dW   [64 (16 valid) in][8 (n_out valid)]
+constexpr uint32_t C_GBMAP = 448;  // map   db   [*][8]
+constexpr uint32_t TMEM_COLS = 512;
+
+struct FusedArgs {
+  const float* params;
+  LrxBatchView buf;
+  const int32_t* idx;
+  long long B;
+  double B_global;
+  const double* adv_sums;
+  LrxPpoHyper h;
+  float* partial;           // [gridDim.x][partial_stride]
+  long long partial_stride;
+  double* loss_partial;     // [gridDim.x][8]
+  int n_tiles;
+  int obs_dim, n_out, is_box;
+  tc::LayerOffsets lo;
+};
+
+__device__ __forceinline__ void tie_weights_f(float a, float b, float& wa, float& wb) {
+  wa = a < b ? 1.f : (a == b ? 0.5f : 0.f);  // JAX: d min(a,b) splits ties 1/2-1/2
+  wb = 1.f - wa;
+}
+__device__ __forceinline__ float clip_grad_f(float x, float lo, float hi) {
+  return (x > lo && x < hi) ? 1.f : ((x == lo || x == hi) ? 0.5f : 0.f);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid_constant__ FusedArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool active = lane < 16;
+  const int m = warp * 16 + (lane & 15);  // row of the tile owned by this thread (when active)
+  float* fp = reinterpret_cast<float*>(smem + OFF_F32);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_MISC);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 8);
+
+  const tc::Mat W0{smem + OFF_W0, 64, PS16}, W1{smem + OFF_W1, 64, PS64}, W2{smem + OFF_W2, 16, PS16};
+  const tc::Mat WV0{smem + OFF_WV0, 64, PS16}, WV1{smem + OFF_WV1, 64, PS64};
+  const tc::Mat WA0{smem + OFF_WA0, 64, PS16}, WA1{smem + OFF_WA1, 16, PS16};
+  const tc::Mat XOBS{smem + OFF_XOBS, ROWS, PS16}, XH1{smem + OFF_XH1, ROWS, PS64}, XH2{smem + OFF_XH2, ROWS, PS64};
+  const tc::Mat XF{smem + OFF_XF, ROWS, PS16}, XB1{smem + OFF_XB1, ROWS, PS64}, XB2{smem + OFF_XB2, ROWS, PS64};
+  const tc::Mat XA2{smem + OFF_XB2, ROWS, PS64};  // [64][16] action layer-2 output; reads past col 16 stay inside XB2
+  const tc::Mat DY64{smem + OFF_DY64, ROWS, PS64}, DY16{smem + OFF_DY16, ROWS, PS16}, DY8{smem + OFF_DY8, ROWS, PS8};
+  const tc::Mat ONES{smem + OFF_ONES, 0, PS8};  // R = 0: as an MN-major A operand every MN group aliases the same ones
+
+  // ------------------------------------------------------------------ one-time staging
+  tc::stage_weight(a.params + a.lo.w[tc::L_ENC0], 64, a.obs_dim, 16, W0, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_ENC1], 64, 64, 64, W1, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_ENC2], 16, 64, 64, W2, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_V0], 64, 16, 16, WV0, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_V1], 64, 64, 64, WV1, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_A0], 64, 16, 16, WA0, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_A1], 16, 64, 64, WA1, tid, THREADS);
+  tc::stage_f32(a.params, a.lo, a.n_out, fp, tid, THREADS);
+  for (int i = tid; i < (int)(PS8 / 4); i += THREADS)
+    reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;  // two bf16 1.0
+  // XB2 is read past the 16 action columns by the mapping-gradient GEMM: keep it finite
+  for (int i = tid; i < (int)(3 * PS64 / 16); i += THREADS)
+    reinterpret_cast<uint4*>(smem + OFF_XB2)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    umma::mbar_init(bar, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tslot, TMEM_COLS);
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tb = *tslot;
+  const uint32_t tw = umma::tmem_addr(tb, warp * 32, 0);  // this warp's quadrant
+  {
+    float z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0.f;
+    for (int c = 0; c < (int)TMEM_COLS; c += 16) umma::tmem_st16(tw + c, z);
+    umma::tmem_st_wait();
+  }
+
+  uint32_t phase = 0;
+  // make this thread's shared-memory writes visible to the tensor core, let one thread issue a
+  // group of MMAs, and wait for the whole group.
+  auto sync_issue = [&](auto&& issue) {
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      umma::tc_fence_after();
+      issue();
+      umma::mma_commit(bar);
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::tc_fence_after();
+  };
+
+  const LrxPpoHyper h = a.h;
+  const float invB = (float)(1.0 / a.B_global);
+  float adv_mean = 0.f, adv_den = 1.f;
+  if (h.normalize_advantages) {
+    const double mean = a.adv_sums[0] / a.B_global;
+    double var = a.adv_sums[1] / a.B_global - mean * mean;
+    var = var > 0 ? var : 0;
+    adv_mean = (float)mean;
+    adv_den = (float)sqrt(var) + 1.1920928955078125e-07f;  // + finfo(float32).eps   (ppo.py:424-427)
+  }
+  float log_std = 0.f, scale = 1.f, log_scale = 0.f;
+  if (a.is_box) {
+    log_std = __ldg(a.params + a.lo.log_std);
+    scale = expf(log_std);
+    log_scale = logf(scale);
+  }
+  double s_kl = 0, s_pol = 0, s_val = 0, s_ent = 0, s_dls = 0, s_bad = 0;
+
+  // Layer output (TMEM, NC columns) -> + bias -> optional ReLU (mask recorded) -> operand X.
+  // fn(c0, v) sees every 16-column chunk after the activation.
+  auto epilogue_fwd = [&](uint32_t col, int nc, const float* bias, bool relu, const tc::Mat& dst, uint64_t& mask,
+                          auto&& fn) {
+    mask = 0;
+    for (int c0 = 0; c0 < nc; c0 += 16) {
+      float v[16];
+      umma::tmem_ld16(tw + col + c0, v);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] += bias[c0 + j];
+        if (relu) {
+          if (v[j] > 0.f) mask |= (1ull << (c0 + j));
+          v[j] = fmaxf(v[j], 0.f);
+        }
+      }
+      fn(c0, v);
+      if (active) {
+        tc::store8(dst, (c0 >> 3), m, v);
+        tc::store8(dst, (c0 >> 3) + 1, m, v + 8);
+      }
+    }
+  };
+  // dX (TMEM, NC columns) masked by the ReLU of the layer that produced X -> operand dY.
+  auto epilogue_bwd = [&](uint32_t col, int nc, uint64_t mask, bool use_mask, const tc::Mat& dst) {
+    for (int c0 = 0; c0 < nc; c0 += 16) {
+      float v[16];
+      umma::tmem_ld16(tw + col + c0, v);
+      umma::tmem_ld_wait();
+      if (use_mask) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = ((mask >> (c0 + j)) & 1ull) ? v[j] : 0.f;
+      }
+      if (active) {
+        tc::store8(dst, (c0 >> 3), m, v);
+        tc::store8(dst, (c0 >> 3) + 1, m, v + 8);
+      }
+    }
+  };
+  auto nop = [](int, float*) {};
+
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    // ---------------------------------------------------------------- gather (base_buffer.py:90-103)
+    const long long row = (long long)tile * ROWS + m;
+    const bool valid = active && row < a.B;
+    float act_f = 0.f, logp_old = 0.f, A = 0.f, ret = 0.f, val_old = 0.f;
+    int act_i = 0;
+    {
+      float o[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) o[k] = 0.f;
+      if (valid) {
+        const int i = a.idx[row];
+        const int n = i / a.buf.T, t = i - n * a.buf.T;
+        const size_t src = (size_t)t * a.buf.N + n;
+        const float* op = a.buf.obs + src * a.obs_dim;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (k < a.obs_dim) o[k] = __ldg(op + k);
+        if (a.is_box) act_f = __ldg((const float*)a.buf.act + src);
+        else act_i = __ldg((const int32_t*)a.buf.act + src);
+        logp_old = __ldg(a.buf.logp + src);
+        A = __ldg(a.buf.adv + src);
+        ret = __ldg(a.buf.ret + src);
+        if (h.clip_value_loss) val_old = __ldg(a.buf.val + src);
+        if (h.normalize_advantages) A = (A - adv_mean) / adv_den;
+      }
+      if (active) {
+        tc::store8(XOBS, 0, m, o);
+        tc::store8(XOBS, 1, m, o + 8);
+      }
+    }
+
+    // ---------------------------------------------------------------- encoder forward
+    uint64_t mk_h1, mk_h2, mk_b1, mk_b2, mk_none;
+    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XOBS, W0, 64, 64, 1, 0u); });
+    epilogue_fwd(C_D0, 64, fp + tc::F_B0, true, XH1, mk_h1, nop);
+    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XH1, W1, 64, 64, 4, 0u); });
+    epilogue_fwd(C_D0, 64, fp + tc::F_B1, true, XH2, mk_h2, nop);
+    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XH2, W2, 64, 16, 4, 0u); });
+    epilogue_fwd(C_D0, 16, fp + tc::F_B2, false, XF, mk_none, nop);
+
+    // ---------------------------------------------------------------- value head forward
+    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XF, WV0, 64, 64, 1, 0u); });
+    epilogue_fwd(C_D0, 64, fp + tc::F_BV0, true, XB1, mk_b1, nop);
+    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XB1, WV1, 64, 64, 4, 0u); });
+    float value = fp[tc::F_BV2];
+    epilogue_fwd(C_D0, 64, fp + tc::F_BV1, true, XB2, mk_b2, [&](int c0, float* v) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) value = fmaf(fp[tc::F_WV2 + c0 + j], v[j], value);
+    });
+
+    // ---------------------------------------------------------------- value loss (ppo.py:435-451)
+    float dvalue = 0.f;
+    bool bad = false;
+    if (valid) {
+      bad = !isfinite(value);
+      const float c = h.clip_coefficient;
+      const float e1 = value - ret;
+      float dvl;
+      if (h.clip_value_loss) {
+        const float dv = value - val_old;
+        const float clipped = val_old + lrx_clipf(dv, -c, c);
+        const float e2 = clipped - ret;
+        const float q1 = e1 * e1, q2 = e2 * e2;
+        s_val += (double)fminf(q1, q2);
+        float u1, u2;
+        tie_weights_f(q1, q2, u1, u2);
+        dvl = invB * (u1 * e1 + u2 * e2 * clip_grad_f(dv, -c, c));
+      } else {
+        s_val += (double)(e1 * e1);
+        dvl = invB * e1;
+      }
+      dvalue = h.value_loss_coefficient * dvl;
+    }
+    // ---------------------------------------------------------------- value head backward
+    if (active) {
+      float d8[8] = {dvalue, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      tc::store8(DY8, 0, m, d8);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = ((mk_b2 >> (c0 + j)) & 1ull) ? dvalue * fp[tc::F_WV2 + c0 + j] : 0.f;
+        tc::store8(DY64, c0 >> 3, m, v);
+      }
+    }
+    sync_issue([&] {
+      tc::gemm<true, true>(tb + C_GV2, XB2, DY8, 64, 8, 4, 1u);            // dW_v2[in] += X^T dvalue
+      tc::gemm<true, true>(tb + C_GBV2, ONES, DY8, 64, 8, 4, 1u, 1, 3);    // db_v2
+      tc::gemm<false, true>(tb + C_D0, DY64, WV1, 64, 64, 4, 0u);          // dX = dY W
+      tc::gemm<true, true>(tb + C_GV1, DY64, XB1, 64, 64, 4, 1u);          // dW^T[out][in] += dY^T X
+      tc::gemm<true, true>(tb + C_GV1 + 64, DY64, ONES, 64, 8, 4, 1u, 3, 1);  // db
+    });
+    epilogue_bwd(C_D0, 64, mk_b1, true, DY64);
+    sync_issue([&] {
+      tc::gemm<false, true>(tb + C_DF, DY64, WV0, 64, 16, 4, 0u);          // d(features) from the value head
+      tc::gemm<true, true>(tb + C_GV0, DY64, XF, 64, 16, 4, 1u);
+      tc::gemm<true, true>(tb + C_GV0 + 16, DY64, ONES, 64, 8, 4, 1u, 3, 1);
+    });
+
+    // ---------------------------------------------------------------- action head forward
+    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XF, WA0, 64, 64, 1, 0u); });
+    epilogue_fwd(C_D0, 64, fp + tc::F_BA0, true, XB1, mk_b1, nop);
+    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XB1, WA1, 64, 16, 4, 0u); });
+    float a2[16];
+    epilogue_fwd(C_D0, 16, fp + tc::F_BA1, false, XA2, mk_none, [&](int, float* v) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a2[j] = v[j];
+    });
+    // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261) on the FMA pipe
+    float head[LRX_MAX_NOUT];
+#pragma unroll
+    for (int o = 0; o < LRX_MAX_NOUT; ++o) {
+      float s = fp[tc::F_BMAP + o];
+      if (o < a.n_out) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s = fmaf(fp[tc::F_WMAP + o * 16 + i], a2[i], s);
+      }
+      head[o] = s;
+    }
+
+    // ---------------------------------------------------------------- policy loss (ppo.py:405-434,452-467)
+    float dhead[LRX_MAX_NOUT];
+#pragma unroll
+    for (int o = 0; o < LRX_MAX_NOUT; ++o) dhead[o] = 0.f;
+    if (valid) {
+      float logp, entropy, z_n = 0.f;
+      float lp[LRX_MAX_NOUT], pr[LRX_MAX_NOUT];
+      if (a.is_box) {
+        const float loc = head[0];
+        z_n = (act_f - loc) / scale;
+        logp = -0.5f * (z_n * z_n) - (LRX_HALF_LOG_2PI + log_scale);
+        entropy = 0.5f + LRX_HALF_LOG_2PI + log_scale;
+      } else {
+#pragma unroll
+        for (int j = 0; j < LRX_MAX_NOUT; ++j) lp[j] = j < a.n_out ? head[j] : 0.f;
+        log_softmax_n<LRX_MAX_NOUT>(lp, a.n_out);
+        logp = 0.f;
+        entropy = 0.f;
+#pragma unroll
+        for (int j = 0; j < LRX_MAX_NOUT; ++j) {
+          if (j < a.n_out) {
+            pr[j] = expf(lp[j]);
+            entropy -= pr[j] * lp[j];
+            if (j == act_i) logp = lp[j];
+          }
+        }
+      }
+      bad = bad || !(isfinite(logp) && isfinite(entropy));  // ppo.py:413-417
+      if (bad) s_bad += 1.0;
+      const float log_ratio = logp - logp_old;
+      const float ratio = expf(log_ratio);
+      s_kl += (double)(ratio - log_ratio);
+      const float c = h.clip_coefficient, lo = 1.f - c, hi = 1.f + c;
+      const float s1 = A * ratio, s2 = A * lrx_clipf(ratio, lo, hi);
+      s_pol += (double)fminf(s1, s2);
+      float w1, w2;
+      tie_weights_f(s1, s2, w1, w2);
+      const float dlogp = -invB * (w1 * A * ratio + w2 * A * clip_grad_f(ratio, lo, hi) * ratio);
+      s_ent += (double)entropy;
+      const float ch = h.entropy_loss_coefficient;
+      if (a.is_box) {
+        dhead[0] = dlogp * z_n / scale;
+        s_dls += (double)(dlogp * (z_n * z_n - 1.0f));
+      } else {
+#pragma unroll
+        for (int j = 0; j < LRX_MAX_NOUT; ++j) {
+          if (j < a.n_out) {
+            const float dH = -pr[j] * (lp[j] + entropy);
+            dhead[j] = dlogp * ((j == act_i ? 1.f : 0.f) - pr[j]) + (-ch * invB) * dH;
+          }
+        }
+      }
+    }
+    // ---------------------------------------------------------------- action head backward
+    if (active) {
+      tc::store8(DY8, 0, m, dhead);
+      float d16[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int o = 0; o < LRX_MAX_NOUT; ++o)
+          if (o < a.n_out) s = fmaf(dhead[o], fp[tc::F_WMAP + o * 16 + i], s);
+        d16[i] = s;
+      }
+      tc::store8(DY16, 0, m, d16);
+      tc::store8(DY16, 1, m, d16 + 8);
+    }
+    sync_issue([&] {
+      tc::gemm<true, true>(tb + C_GMAP, XA2, DY8, 64, 8, 4, 1u);           // dW_map[in (16 valid)][out]
+      tc::gemm<true, true>(tb + C_GBMAP, ONES, DY8, 64, 8, 4, 1u, 1, 3);
+      tc::gemm<false, true>(tb + C_D0, DY16, WA1, 64, 64, 1, 0u);          // dX = dY16 W_a1   (K = 16 outputs)
+      tc::gemm<true, true>(tb + C_GA1, XB1, DY16, 64, 16, 4, 1u);          // dW[in][out] += X^T dY
+      tc::gemm<true, true>(tb + C_GBA1, ONES, DY16, 64, 16, 4, 1u, 1, 3);
+    });
+    epilogue_bwd(C_D0, 64, mk_b1, true, DY64);
+    sync_issue([&] {
+      tc::gemm<false, true>(tb + C_DF, DY64, WA0, 64, 16, 4, 1u);          // d(features) += action head
+      tc::gemm<true, true>(tb + C_GA0, DY64, XF, 64, 16, 4, 1u);
+      tc::gemm<true, true>(tb + C_GA0 + 16, DY64, ONES, 64, 8, 4, 1u, 3, 1);
+    });
+
+    // ---------------------------------------------------------------- encoder backward
+    epilogue_bwd(C_DF, 16, 0, false, DY16);
+    sync_issue([&] {
+      tc::gemm<false, true>(tb + C_D0, DY16, W2, 64, 64, 1, 0u);
+      tc::gemm<true, true>(tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
+      tc::gemm<true, true>(tb + C_GB2, ONES, DY16, 64, 16, 4, 1u, 1, 3);
+    });
+    epilogue_bwd(C_D0, 64, mk_h2, true, DY64);
+    sync_issue([&] {
+      tc::gemm<false, true>(tb + C_D0, DY64, W1, 64, 64, 4, 0u);
+      tc::gemm<true, true>(tb + C_G1, DY64, XH1, 64, 64, 4, 1u);
+      tc::gemm<true, true>(tb + C_G1 + 64, DY64, ONES, 64, 8, 4, 1u, 3, 1);
+    });
+    epilogue_bwd(C_D0, 64, mk_h1, true, DY64);
+    sync_issue([&] {
+      tc::gemm<true, true>(tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
+      tc::gemm<true, true>(tb + C_G0 + 16, DY64, ONES, 64, 8, 4, 1u, 3, 1);
+    });
+  }
+
+  // ------------------------------------------------------------------ flush the gradient partial
+  float* part = a.partial + (size_t)blockIdx.x * a.partial_stride;
+  const tc::LayerOffsets& lo = a.lo;
+  // dW^T accumulators: TMEM row = output unit (this thread's m), columns = inputs then bias
+  auto flush_T = [&](uint32_t col, int in_real, int in_pad, int layer) {
+    for (int c0 = 0; c0 < in_pad + 8; c0 += 8) {
+      float v[8];
+      umma::tmem_ld8(tw + col + c0, v);
+      umma::tmem_ld_wait();
+      if (active) {
+        if (c0 < in_pad) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c0 + j < in_real) part[lo.w[layer] + m * in_real + c0 + j] = v[j];
+        } else {
+          part[lo.b[layer] + m] = v[0];
+        }
+      }
+    }
+  };
+  // dW accumulators: TMEM row = input unit (m), columns = outputs; db in row 0 of its own block
+  auto flush_N = [&](uint32_t col, uint32_t colb, int in_real, int out_real, int out_pad, int layer) {
+    for (int c0 = 0; c0 < out_pad; c0 += 8) {
+      float v[8], b[8];
+      umma::tmem_ld8(tw + col + c0, v);
+      umma::tmem_ld8(tw + colb + c0, b);
+      umma::tmem_ld_wait();
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (c0 + j < out_real) {
+            if (m < in_real) part[lo.w[layer] + (c0 + j) * in_real + m] = v[j];
+            if (m == 0) part[lo.b[layer] + c0 + j] = b[j];
+          }
+        }
+      }
+    }
+  };
+  flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0);
+  flush_T(C_G1, 64, 64, tc::L_ENC1);
+  flush_N(C_G2, C_GB2, 64, 16, 16, tc::L_ENC2);
+  flush_T(C_GV0, 16, 16, tc::L_V0);
+  flush_T(C_GV1, 64, 64, tc::L_V1);
+  flush_N(C_GV2, C_GBV2, 64, 1, 8, tc::L_V2);
+  flush_T(C_GA0, 16, 16, tc::L_A0);
+  flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1);
+  flush_N(C_GMAP, C_GBMAP, 16, a.n_out, 8, tc::L_MAP);
+
+  // ------------------------------------------------------------------ loss statistics (fixed order)
+  __syncthreads();
+  double* sh = reinterpret_cast<double*>(smem + OFF_DY64);  // [6][4 warps]
+  double v6[6] = {s_kl, s_pol, s_val, s_ent, s_dls, s_bad};
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    v6[q] = warp_sum(v6[q]);
+    if (lane == 0) sh[q * 4 + warp] = v6[q];
+  }
+  __syncthreads();
+  if (tid < 6) {
+    double s = 0;
+    for (int w = 0; w < 4; ++w) s += sh[tid * 4 + w];
+    a.loss_partial[(size_t)blockIdx.x * 8 + tid] = s;
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tb, TMEM_COLS);
+}
+
+struct FusedWorkspace {
+  float* partial;        // [LRX_NUM_SMS][P_pad]
+  double* loss_partial;  // [LRX_NUM_SMS][8]
+  size_t P_pad, total;
+};
+size_t align_up_(size_t x, size_t al) { return (x + al - 1) / al * al; }
+FusedWorkspace carve_fused(const LrxPolicyDesc& pol, void* base) {
+  FusedWorkspace w{};
+  w.P_pad = align_up_((size_t)pol.n_params + LRX_PPO_NSTATS, 32);
+  char* b = (char*)base;
+  size_t off = 0;
+  w.partial = (float*)(b ? b + off : nullptr);
+  off += align_up_((size_t)LRX_NUM_SMS * w.P_pad * 4, 256);
+  w.loss_partial = (double*)(b ? b + off : nullptr);
+  off += align_up_((size_t)LRX_NUM_SMS * 8 * sizeof(double), 256);
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+// defined in lrx_update.cu
+void lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
+                                int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
+                                cudaStream_t s);
+
+size_t lrx_fused_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) {
+  if (!tc::is_default_policy(*pol)) return 0;
+  return carve_fused(*pol, nullptr).total;
+}
+
+static int fused_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LRX_DISABLE_FUSED");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
 
 int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf,
                        const int32_t* idx, int64_t B, int64_t B_global, const double* adv_sums,
                        const LrxPpoHyper* h, float* gradbuf, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream, bool* handled) {
   *handled = false;
+  if (!tc::is_default_policy(*pol) || fused_disabled()) return LRX_OK;
+  FusedWorkspace w = carve_fused(*pol, workspace);
+  LRX_REQUIRE(workspace_bytes >= w.total, LRX_ERR_INVALID_ARG, "lrx_ppo_grad: workspace too small for the fused path");
+  FusedArgs a{};
+  a.params = params;
+  a.buf = *buf;
+  a.idx = idx;
+  a.B = B;
+  a.B_global = (double)B_global;
+  a.adv_sums = adv_sums;
+  a.h = *h;
+  a.partial = w.partial;
+  a.partial_stride = (long long)w.P_pad;
+  a.loss_partial = w.loss_partial;
+  a.n_tiles = (int)((B + ROWS - 1) / ROWS);
+  a.obs_dim = pol->obs_dim;
+  a.n_out = pol->n_out;
+  a.is_box = pol->is_box;
+  a.lo = tc::layer_offsets(*pol);
+  const int grid = a.n_tiles < LRX_NUM_SMS ? a.n_tiles : LRX_NUM_SMS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  ppo_grad_fused_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(a);
+  LRX_LAUNCH_CHECK();
+  lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid, a.lo.log_std,
+                             h->entropy_loss_coefficient, (double)B_global, gradbuf, stream);
+  LRX_LAUNCH_CHECK();
+  *handled = true;
   return LRX_OK;
 }
