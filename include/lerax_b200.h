@@ -254,6 +254,14 @@ int lrx_debug_umma_gemm(const float* A, const float* B, float* dump, int32_t M, 
 int lrx_debug_umma_gemm_bf16(const float* A, const float* B, float* dump, int32_t M, int32_t N, int32_t K,
                              const int32_t* cfg_host, int32_t nprod, lrx_stream_t stream);
 
+/* Timing probe for the same MMA sequence: cycles[0] = issue, cycles[1] = issue + completion. */
+int lrx_debug_umma_time_bf16(const float* A, const float* B, float* dump, int32_t M, int32_t N, int32_t K,
+                             const int32_t* cfg_host, int32_t nprod, int32_t reps, long long* cycles,
+                             lrx_stream_t stream);
+
+/* Dispatch-rate probe: 256 back-to-back MMAs with constant descriptors over `dsplit` accumulators. */
+int lrx_debug_umma_rate(int32_t M, int32_t N, int32_t dsplit, long long* cycles, lrx_stream_t stream);
+
 /* ------------------------------------------------------------------------- misc */
 const char* lrx_last_error(void);
 int lrx_version(void);

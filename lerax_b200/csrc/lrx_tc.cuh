@@ -49,6 +49,10 @@ struct Mat {
   uint32_t R;
   uint32_t piece_bytes;
   __device__ __forceinline__ uint32_t saddr(int piece) const { return umma::smem_u32(ptr) + piece * piece_bytes; }
+  // Operand starting at MN index mn0 (multiple of 8): K-major view -> rows r >= mn0;
+  // MN-major view -> columns c >= mn0.
+  __device__ __forceinline__ Mat rows_from(uint32_t r0) const { return Mat{ptr + r0 * 16u, R, piece_bytes}; }
+  __device__ __forceinline__ Mat cols_from(uint32_t c0) const { return Mat{ptr + (c0 >> 3) * (R * 16u), R, piece_bytes}; }
 };
 
 // Store 8 consecutive values (columns 8*chunk .. +7 of row r) as the three pieces.
@@ -61,34 +65,55 @@ __device__ __forceinline__ void store8(const Mat& m, int chunk, int r, const flo
   *reinterpret_cast<uint4*>(d + 2 * m.piece_bytes) = p2;
 }
 
-// One K = 16 slice of the operand.  K-major view: K runs along c (2 chunks per MMA);
-// MN-major view: K runs along r (16 rows per MMA).
+// Descriptor halves of an operand view.  K-major view: K runs along c (2 chunks per K = 16 MMA);
+// MN-major view: K runs along r (16 rows per MMA).  Only the start-address field (low word,
+// 16-byte units) changes between pieces and K slices, so the issue loop is integer adds.
 template <bool MN>
-__device__ __forceinline__ uint64_t desc(const Mat& m, int piece, int kstep) {
-  return MN ? umma::smem_desc(m.saddr(piece) + (uint32_t)kstep * 256u, 128u, m.R * 16u)
-            : umma::smem_desc(m.saddr(piece) + (uint32_t)kstep * 2u * m.R * 16u, m.R * 16u, 128u);
+__device__ __forceinline__ uint32_t desc_hi(const Mat& m) {
+  return ((MN ? m.R * 16u : 128u) >> 4) | (1u << 14);  // SBO | version
 }
+template <bool MN>
+__device__ __forceinline__ uint32_t desc_lo(const Mat& m) {
+  return ((umma::smem_u32(m.ptr) >> 4) & 0x3FFFu) | (((MN ? 128u : m.R * 16u) >> 4) << 16);  // addr | LBO
+}
+template <bool MN>
+__device__ __forceinline__ uint32_t desc_kstep(const Mat& m) {
+  return (MN ? 256u : 2u * m.R * 16u) >> 4;
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 // D[tmem] (+)= A * B^T over `ksteps` slices of K = 16, bf16x3 with the six leading products
-// (smallest first).  pa / pb: pieces present in A / B (1 for exact constants such as ones).
-// Issued by ONE thread; completion is observed through umma::mma_commit.
-template <bool A_MN, bool B_MN>
-__device__ __forceinline__ void gemm(uint32_t d_tmem, const Mat& A, const Mat& B, int M, int N, int ksteps,
-                                     uint32_t accumulate, int pa = 3, int pb = 3) {
+// (smallest first).  PA / PB: pieces present in A / B (1 for exact constants such as ones).
+// Called by a whole CONVERGED warp; `leader` (umma::elect_one()) predicates the instructions.
+// Completion is observed through umma::mma_commit by the same lane.
+template <bool A_MN, bool B_MN, int PA = 3, int PB = 3>
+__device__ __forceinline__ void gemm(bool leader, uint32_t d_tmem, const Mat& A, const Mat& B, int M, int N,
+                                     int ksteps, uint32_t accumulate) {
   const uint32_t idesc = umma::idesc_bf16(M, N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  uint64_t ad[PA], bd[PB];
+#pragma unroll
+  for (int i = 0; i < PA; ++i) ad[i] = make_desc(desc_lo<A_MN>(A) + i * (A.piece_bytes >> 4), desc_hi<A_MN>(A));
+#pragma unroll
+  for (int j = 0; j < PB; ++j) bd[j] = make_desc(desc_lo<B_MN>(B) + j * (B.piece_bytes >> 4), desc_hi<B_MN>(B));
+  const uint64_t aks = desc_kstep<A_MN>(A), bks = desc_kstep<B_MN>(B);
   uint32_t acc = accumulate;
+#pragma unroll 1
   for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
     for (int sum = 2; sum >= 0; --sum) {
 #pragma unroll
       for (int i = 0; i <= sum; ++i) {
         const int j = sum - i;
-        if (i < pa && j < pb) {
-          umma::mma_f16(d_tmem, desc<A_MN>(A, i, ks), desc<B_MN>(B, j, ks), idesc, acc);
+        if (i < PA && j < PB) {
+          if (leader) umma::mma_f16(d_tmem, ad[i], bd[j], idesc, acc);
           acc = 1u;
         }
       }
     }
+#pragma unroll
+    for (int i = 0; i < PA; ++i) ad[i] += aks;  // start-address field only; never carries out of it
+#pragma unroll
+    for (int j = 0; j < PB; ++j) bd[j] += bks;
   }
 }
 
@@ -112,7 +137,7 @@ __device__ __forceinline__ void stage_weight(const float* __restrict__ W, int ou
 // The default policy this path is specialised for (policy/actor_critic/mlp.py:64-78 defaults):
 // encoder d->64->64->16, value head 16->64->64->1, action head 16->64->16->n_out.
 __host__ inline bool is_default_policy(const LrxPolicyDesc& p) {
-  if (p.obs_dim < 1 || p.obs_dim > 16 || p.n_out < 1 || p.n_out > 8) return false;
+  if (p.obs_dim < 1 || p.obs_dim > 8 || p.n_out < 1 || p.n_out > 8) return false;
   const int want[3][4] = {{p.obs_dim, 64, 64, 16}, {16, 64, 64, 1}, {16, 64, 16, p.n_out}};
   const int relu[3][3] = {{1, 1, 0}, {1, 1, 0}, {1, 0, 0}};
   for (int c = 0; c < 3; ++c) {

@@ -172,6 +172,8 @@ __device__ __forceinline__ void bf16_split3(float x, __nv_bfloat16 (&p)[3]) {
   }
 }
 
+__device__ __forceinline__ uint64_t tc_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 __device__ __forceinline__ uint32_t selftest_off16(const SelftestOperand& o, int mn, int k) {
   return o.mn ? (uint32_t)((mn & 7) * 2 + (mn >> 3) * o.s_mn + (k & 7) * 16 + (k >> 3) * o.s_k)
               : (uint32_t)((mn & 7) * 16 + (mn >> 3) * o.s_mn + (k & 7) * 2 + (k >> 3) * o.s_k);
@@ -179,7 +181,8 @@ __device__ __forceinline__ uint32_t selftest_off16(const SelftestOperand& o, int
 
 __global__ void __launch_bounds__(128)
 umma_selftest_bf16_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ dump,
-                          int M, int N, int K, SelftestCfg cfg, int nprod, uint32_t bytesA, uint32_t bytesB) {
+                          int M, int N, int K, SelftestCfg cfg, int nprod, uint32_t bytesA, uint32_t bytesB,
+                          int reps, long long* cycles_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -235,22 +238,42 @@ umma_selftest_bf16_kernel(const float* __restrict__ A, const float* __restrict__
   umma::tc_fence_before();
   __syncthreads();
 
-  if (tid == 0) {
+  if (umma::warp_idx_sync() == 0) {
     umma::tc_fence_after();
+    const bool leader = umma::elect_one();
     const uint32_t idesc = umma::idesc_bf16(M, N, cfg.a.mn, cfg.b.mn);
+    const uint32_t ahi = ((uint32_t)cfg.a.sbo >> 4) | (1u << 14) | (lt_a << 29);
+    const uint32_t bhi = ((uint32_t)cfg.b.sbo >> 4) | (1u << 14) | (lt_b << 29);
+    const uint32_t alo0 = ((umma::smem_u32(a_p[0]) >> 4) & 0x3FFFu) | (((uint32_t)cfg.a.lbo >> 4) << 16);
+    const uint32_t blo0 = ((umma::smem_u32(b_p[0]) >> 4) & 0x3FFFu) | (((uint32_t)cfg.b.lbo >> 4) << 16);
+    const uint32_t aps = bytesA >> 4, bps = bytesB >> 4, aks = (uint32_t)cfg.a.kstep >> 4, bks = (uint32_t)cfg.b.kstep >> 4;
     uint32_t acc = 0;
-    for (int ks = 0; ks < K / 16; ++ks) {
-      const uint32_t ao = ks * cfg.a.kstep, bo = ks * cfg.b.kstep;
-      // smallest products first: i + j = 2, then 1, then 0
-      for (int sum = (nprod >= 6 ? 2 : (nprod >= 3 ? 1 : 0)); sum >= 0; --sum)
-        for (int i = 0; i <= sum; ++i) {
-          const int j = sum - i;
-          umma::mma_f16(tbase, umma::smem_desc(umma::smem_u32(a_p[i]) + ao, cfg.a.lbo, cfg.a.sbo, lt_a),
-                        umma::smem_desc(umma::smem_u32(b_p[j]) + bo, cfg.b.lbo, cfg.b.sbo, lt_b), idesc, acc);
-          acc = 1u;
-        }
+    const int dsplit = (nprod >> 8) ? (nprod >> 8) : 1;  // timing: rotate over independent accumulators
+    nprod &= 0xFF;
+    uint32_t dn = 0;
+    const long long t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep) {
+      uint32_t alo = alo0, blo = blo0;
+      for (int ks = 0; ks < K / 16; ++ks) {
+        // smallest products first: i + j = 2, then 1, then 0
+        for (int sum = (nprod >= 6 ? 2 : (nprod >= 3 ? 1 : 0)); sum >= 0; --sum)
+          for (int i = 0; i <= sum; ++i) {
+            const int j = sum - i;
+            if (leader)
+              umma::mma_f16(tbase + dn * N, tc_desc(alo + i * aps, ahi), tc_desc(blo + j * bps, bhi), idesc, acc);
+            dn = (dn + 1 == (uint32_t)dsplit) ? 0u : dn + 1;
+            acc = (reps > 1) ? 0u : 1u;  // timing mode overwrites (keeps values finite)
+          }
+        alo += aks;
+        blo += bks;
+      }
     }
-    umma::mma_commit(&bar);
+    const long long t1 = clock64();
+    if (leader) umma::mma_commit(&bar);
+    __syncwarp();
+    umma::mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if (leader && cycles_out) { cycles_out[0] = t1 - t0; cycles_out[1] = t2 - t0; }
   }
   umma::mbar_wait(&bar, 0);
   umma::tc_fence_after();
@@ -295,7 +318,85 @@ extern "C" int lrx_debug_umma_gemm_bf16(const float* A, const float* B, float* d
   const size_t smem = (size_t)3 * (bytesA + bytesB);
   LRX_REQUIRE(smem <= 200 * 1024, LRX_ERR_INVALID_ARG, "lrx_debug_umma_gemm_bf16: operands exceed shared memory");
   LRX_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  umma_selftest_bf16_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, dump, M, N, K, cfg, nprod, bytesA, bytesB);
+  umma_selftest_bf16_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, dump, M, N, K, cfg, nprod & 0xFF, bytesA,
+                                                                      bytesB, 1, nullptr);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+// Timing probe: the same MMA sequence repeated `reps` times by one thread; cycles[0] = issue time,
+// cycles[1] = issue + completion (SM clocks).  Used to size the fused kernels (tools/umma_time.py).
+extern "C" int lrx_debug_umma_time_bf16(const float* A, const float* B, float* dump, int32_t M, int32_t N, int32_t K,
+                                        const int32_t* cfg_host, int32_t nprod, int32_t reps, long long* cycles,
+                                        lrx_stream_t stream) {
+  LRX_REQUIRE(A && B && dump && cfg_host && cycles && reps >= 1, LRX_ERR_INVALID_ARG, "lrx_debug_umma_time_bf16: bad argument");
+  SelftestCfg cfg;
+  const int32_t* c = cfg_host;
+  cfg.a = SelftestOperand{c[0], c[1], c[2], c[3], c[4], c[5]};
+  cfg.b = SelftestOperand{c[6], c[7], c[8], c[9], c[10], c[11]};
+  const uint32_t bytesA = selftest_extent16(cfg.a, M, K), bytesB = selftest_extent16(cfg.b, N, K);
+  const size_t smem = (size_t)3 * (bytesA + bytesB);
+  LRX_REQUIRE(smem <= 200 * 1024, LRX_ERR_INVALID_ARG, "lrx_debug_umma_time_bf16: operands exceed shared memory");
+  LRX_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_bf16_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, dump, M, N, K, cfg, nprod, bytesA, bytesB,
+                                                                      reps, cycles);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+// ------------------------------------------------------------------ MMA dispatch-rate probe
+// 256 back-to-back tcgen05.mma with CONSTANT descriptors (no per-instruction arithmetic) rotating
+// over DS independent accumulators: the tensor pipe's own cost per instruction for small shapes.
+template <int DS>
+__global__ void __launch_bounds__(128) umma_rate_kernel(int M, int N, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = umma::warp_idx_sync();
+  for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3F803F80u;
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  if (warp == 0) {
+    const bool leader = umma::elect_one();
+    const uint32_t idesc = umma::idesc_bf16(M, N, 0, 0);
+    const uint64_t ad = umma::smem_desc(umma::smem_u32(smem), (uint32_t)M * 16u, 128u);
+    const uint64_t bd = umma::smem_desc(umma::smem_u32(smem) + 8192u, (uint32_t)N * 16u, 128u);
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int rep = 0; rep < 16; ++rep) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (leader) umma::mma_f16(tbase + (uint32_t)((i % DS) * 64), ad, bd, idesc, 1u);
+    }
+    const long long t1 = clock64();
+    if (leader) umma::mma_commit(&bar);
+    __syncwarp();
+    umma::mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if (leader) { cycles_out[0] = t1 - t0; cycles_out[1] = t2 - t0; }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+
+extern "C" int lrx_debug_umma_rate(int32_t M, int32_t N, int32_t dsplit, long long* cycles, lrx_stream_t stream) {
+  LRX_REQUIRE(cycles && (M == 64 || M == 128) && N >= 8 && N <= 64 && N % 8 == 0 && (M == 64 || N % 16 == 0),
+              LRX_ERR_INVALID_ARG, "lrx_debug_umma_rate: bad argument");
+  const size_t smem = 16384;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dsplit == 1) umma_rate_kernel<1><<<1, 128, smem, s>>>(M, N, cycles);
+  else if (dsplit == 2) umma_rate_kernel<2><<<1, 128, smem, s>>>(M, N, cycles);
+  else if (dsplit == 4) umma_rate_kernel<4><<<1, 128, smem, s>>>(M, N, cycles);
+  else umma_rate_kernel<8><<<1, 128, smem, s>>>(M, N, cycles);
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }

@@ -22,10 +22,20 @@
 #include "lrx_policy.cuh"
 #include "lrx_tc.cuh"
 
+// Build with -DLRX_FUSED_PROFILE to collect per-phase SM cycle counters (printed when
+// LRX_FUSED_PROF=1); the product build carries none of it.
+#ifdef LRX_FUSED_PROFILE
+#define PF_CLOCK() clock64()
+#else
+#define PF_CLOCK() 0ll
+#endif
+
 namespace {
 
-constexpr int ROWS = 64;       // rows per tile = UMMA M
-constexpr int THREADS = 128;   // 4 warps; lanes 0-15 of warp q own rows 16q..16q+15 (TMEM lanes 32q..32q+15)
+constexpr int ROWS = 64;        // rows per tile = UMMA M
+constexpr int THREADS = 512;    // 16 warps: warp w serves TMEM quadrant q = w & 3 (rows 16q..16q+15 on lanes 0-15)
+                                // and column group g = w >> 2 (16 of the 64 columns of a layer output)
+constexpr int ISSUERS = 4;      // warps 0..3 also issue the MMAs (independent GEMMs of a step in parallel)
 
 // ---- shared memory map (bytes).  Matrices: piece stride = R * C * 2.
 constexpr uint32_t PS16 = ROWS * 16 * 2;  // [64][16] piece
@@ -49,13 +59,15 @@ constexpr uint32_t OFF_DY16 = OFF_DY64 + 3 * PS64;     // [64][16]
 constexpr uint32_t OFF_DY8 = OFF_DY16 + 3 * PS16;      // [64][8]  dvalue / dlogits
 constexpr uint32_t OFF_ONES = OFF_DY8 + 3 * PS8;       // [64][8]  all ones (one piece)
 constexpr uint32_t OFF_F32 = OFF_ONES + PS8;           // fp32 biases etc. (tc::F_COUNT floats)
-constexpr uint32_t OFF_MISC = OFF_F32 + 640 * 4;       // mbarrier, TMEM slot
+constexpr uint32_t OFF_VPART = OFF_F32 + 640 * 4;      // [4 column groups][64 rows] partial value dot products
+constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ROWS * 4;  // mbarrier, TMEM slot
 constexpr uint32_t SMEM_BYTES = OFF_MISC + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "fused update kernel exceeds shared memory");
 static_assert(tc::F_COUNT <= 640, "fp32 parameter block too small");
 
 // ---- TMEM columns (fp32; M = 64 accumulators use lanes 0-15 of every 32-lane quadrant)
 constexpr uint32_t C_D0 = 0;       // 64: layer outputs
+constexpr uint32_t C_D1 = 64;      // 64: action head layer-1 pre-activations (issued with the value head's)
 constexpr uint32_t C_DF = 128;     // 16: d(features), summed over both heads
 constexpr uint32_t C_G0 = 144;     // enc0  dW^T [64 out][16 in | 8 bias]
 constexpr uint32_t C_G1 = 168;     // enc1  dW^T [64][64 | 8]
@@ -86,6 +98,7 @@ struct FusedArgs {
   int n_tiles;
   int obs_dim, n_out, is_box;
   tc::LayerOffsets lo;
+  long long* prof;  // debug (LRX_FUSED_PROF=1): per-phase SM cycles of CTA 0, else NULL
 };
 
 __device__ __forceinline__ void tie_weights_f(float a, float b, float& wa, float& wb) {
@@ -98,10 +111,13 @@ __device__ __forceinline__ float clip_grad_f(float x, float lo, float hi) {
 
 __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
+  const int q = warp & 3, g = warp >> 2;
   const bool active = lane < 16;
-  const int m = warp * 16 + (lane & 15);  // row of the tile owned by this thread (when active)
+  const int m = q * 16 + (lane & 15);  // row of the tile owned by this thread (when active)
+  const bool g0 = (g == 0);
   float* fp = reinterpret_cast<float*>(smem + OFF_F32);
+  float* vpart = reinterpret_cast<float*>(smem + OFF_VPART);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_MISC);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 8);
 
@@ -129,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   for (int i = tid; i < (int)(3 * PS64 / 16); i += THREADS)
     reinterpret_cast<uint4*>(smem + OFF_XB2)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    umma::mbar_init(bar, 1);
+    umma::mbar_init(bar, ISSUERS);
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc(tslot, TMEM_COLS);
@@ -138,30 +154,58 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tb = *tslot;
-  const uint32_t tw = umma::tmem_addr(tb, warp * 32, 0);  // this warp's quadrant
+  const uint32_t tw = umma::tmem_addr(tb, q * 32, 0);  // this warp's quadrant
   {
     float z[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) z[i] = 0.f;
-    for (int c = 0; c < (int)TMEM_COLS; c += 16) umma::tmem_st16(tw + c, z);
+    for (int c = g * 128; c < g * 128 + 128; c += 16) umma::tmem_st16(tw + c, z);
     umma::tmem_st_wait();
   }
 
   uint32_t phase = 0;
-  // make this thread's shared-memory writes visible to the tensor core, let one thread issue a
-  // group of MMAs, and wait for the whole group.
+  // Make this thread's shared-memory writes visible to the tensor core, let the issuing warps
+  // (converged, one elected lane each) enqueue their share of the step's MMAs, and wait for all
+  // of them.  issue(leader, part) with part = 0..ISSUERS-1.
+  long long pf_epi = 0, pf_sync = 0, pf_issue = 0, pf_wait = 0, pf_last = PF_CLOCK();
+  long long pf_ld = 0, pf_st = 0, pf_fence = 0;
   auto sync_issue = [&](auto&& issue) {
+    const long long t_a = PF_CLOCK();
     umma::fence_async_smem();
     umma::tc_fence_before();
+    const long long t_f = PF_CLOCK();
+    pf_fence += t_f - t_a;
     __syncthreads();
-    if (tid == 0) {
+    const long long t_b = PF_CLOCK();
+    if (warp < ISSUERS) {
       umma::tc_fence_after();
-      issue();
-      umma::mma_commit(bar);
+      const bool leader = umma::elect_one();
+      issue(leader, warp);
+      if (leader) umma::mma_commit(bar);
+      __syncwarp();
     }
+    const long long t_c = PF_CLOCK();
     umma::mbar_wait(bar, phase);
     phase ^= 1u;
     umma::tc_fence_after();
+    const long long t_d = PF_CLOCK();
+    pf_epi += t_a - pf_last;
+    pf_sync += t_b - t_a;
+    pf_issue += t_c - t_b;
+    pf_wait += t_d - t_c;
+    pf_last = t_d;
+  };
+
+  auto issue_nowait = [&](auto&& issue) {
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp < ISSUERS) {
+      umma::tc_fence_after();
+      const bool leader = umma::elect_one();
+      issue(leader, warp);
+      __syncwarp();
+    }
   };
 
   const LrxPpoHyper h = a.h;
@@ -182,271 +226,333 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   }
   double s_kl = 0, s_pol = 0, s_val = 0, s_ent = 0, s_dls = 0, s_bad = 0;
 
-  // Layer output (TMEM, NC columns) -> + bias -> optional ReLU (mask recorded) -> operand X.
-  // fn(c0, v) sees every 16-column chunk after the activation.
-  auto epilogue_fwd = [&](uint32_t col, int nc, const float* bias, bool relu, const tc::Mat& dst, uint64_t& mask,
+  // This thread's 16 columns [c0, c0+16) of a layer output in TMEM -> + bias -> optional ReLU (mask
+  // recorded) -> operand X.  fn(v) sees the 16 activated values.
+  auto epilogue_fwd = [&](uint32_t col, int c0, const float* bias, bool relu, const tc::Mat& dst, uint32_t& mask,
                           auto&& fn) {
+    float v[16];
+    const long long t0 = PF_CLOCK();
+    umma::tmem_ld16(tw + col + c0, v);
+    umma::tmem_ld_wait();
+    const long long t1 = PF_CLOCK();
+    pf_ld += t1 - t0;
     mask = 0;
-    for (int c0 = 0; c0 < nc; c0 += 16) {
-      float v[16];
-      umma::tmem_ld16(tw + col + c0, v);
-      umma::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v[j] += bias[c0 + j];
-        if (relu) {
-          if (v[j] > 0.f) mask |= (1ull << (c0 + j));
-          v[j] = fmaxf(v[j], 0.f);
-        }
-      }
-      fn(c0, v);
-      if (active) {
-        tc::store8(dst, (c0 >> 3), m, v);
-        tc::store8(dst, (c0 >> 3) + 1, m, v + 8);
+    for (int j = 0; j < 16; ++j) {
+      v[j] += bias[c0 + j];
+      if (relu) {
+        if (v[j] > 0.f) mask |= (1u << j);
+        v[j] = fmaxf(v[j], 0.f);
       }
     }
+    fn(v);
+    const long long t2 = PF_CLOCK();
+    if (active) {
+      tc::store8(dst, (c0 >> 3), m, v);
+      tc::store8(dst, (c0 >> 3) + 1, m, v + 8);
+    }
+    pf_st += PF_CLOCK() - t2;
   };
-  // dX (TMEM, NC columns) masked by the ReLU of the layer that produced X -> operand dY.
-  auto epilogue_bwd = [&](uint32_t col, int nc, uint64_t mask, bool use_mask, const tc::Mat& dst) {
-    for (int c0 = 0; c0 < nc; c0 += 16) {
-      float v[16];
-      umma::tmem_ld16(tw + col + c0, v);
-      umma::tmem_ld_wait();
-      if (use_mask) {
+  // dX columns [c0, c0+16) masked by the ReLU of the layer that produced X -> operand dY.
+  auto epilogue_bwd = [&](uint32_t col, int c0, uint32_t mask, bool use_mask, const tc::Mat& dst) {
+    float v[16];
+    umma::tmem_ld16(tw + col + c0, v);
+    umma::tmem_ld_wait();
+    if (use_mask) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = ((mask >> (c0 + j)) & 1ull) ? v[j] : 0.f;
-      }
-      if (active) {
-        tc::store8(dst, (c0 >> 3), m, v);
-        tc::store8(dst, (c0 >> 3) + 1, m, v + 8);
-      }
+      for (int j = 0; j < 16; ++j) v[j] = ((mask >> j) & 1u) ? v[j] : 0.f;
+    }
+    if (active) {
+      tc::store8(dst, (c0 >> 3), m, v);
+      tc::store8(dst, (c0 >> 3) + 1, m, v + 8);
     }
   };
-  auto nop = [](int, float*) {};
+  auto nop = [](float*) {};
+  const int cg = g * 16;  // first column of this thread's group in a 64-wide layer
 
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    // ---------------------------------------------------------------- gather (base_buffer.py:90-103)
-    const long long row = (long long)tile * ROWS + m;
-    const bool valid = active && row < a.B;
-    float act_f = 0.f, logp_old = 0.f, A = 0.f, ret = 0.f, val_old = 0.f;
-    int act_i = 0;
-    {
-      float o[16];
+  // Row data of a tile (gather of base_buffer.py:90-103).  Lanes 0-15 own the rows of the CURRENT
+  // tile; the otherwise idle lanes 16-31 load the same rows of the NEXT tile of this CTA a whole tile
+  // ahead and hand them down by shuffle, so the two dependent global loads are never waited for.
+  float act_f = 0.f, logp_old = 0.f, A = 0.f, ret = 0.f, val_old = 0.f, o[8];
+  int act_i = 0;
+  bool valid = false;
+  auto load_row = [&](int tile_of_lane) {
+    const long long row = (long long)tile_of_lane * ROWS + m;
+    valid = tile_of_lane < a.n_tiles && row < a.B;
+    act_f = logp_old = A = ret = val_old = 0.f;
+    act_i = 0;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) o[k] = 0.f;
-      if (valid) {
-        const int i = a.idx[row];
-        const int n = i / a.buf.T, t = i - n * a.buf.T;
-        const size_t src = (size_t)t * a.buf.N + n;
+    for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    if (valid) {
+      const int i = a.idx[row];
+      const int n = i / a.buf.T, t = i - n * a.buf.T;
+      const size_t src = (size_t)t * a.buf.N + n;
+      ret = __ldg(a.buf.ret + src);
+      if (h.clip_value_loss) val_old = __ldg(a.buf.val + src);
+      if (g0) {
         const float* op = a.buf.obs + src * a.obs_dim;
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
+        for (int k = 0; k < 8; ++k)
           if (k < a.obs_dim) o[k] = __ldg(op + k);
         if (a.is_box) act_f = __ldg((const float*)a.buf.act + src);
         else act_i = __ldg((const int32_t*)a.buf.act + src);
         logp_old = __ldg(a.buf.logp + src);
         A = __ldg(a.buf.adv + src);
-        ret = __ldg(a.buf.ret + src);
-        if (h.clip_value_loss) val_old = __ldg(a.buf.val + src);
         if (h.normalize_advantages) A = (A - adv_mean) / adv_den;
       }
-      if (active) {
-        tc::store8(XOBS, 0, m, o);
-        tc::store8(XOBS, 1, m, o + 8);
-      }
+    }
+  };
+  load_row(active ? (int)blockIdx.x : (int)(blockIdx.x + gridDim.x));
+
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    if (active && g0) {
+      float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      tc::store8(XOBS, 0, m, o);
+      tc::store8(XOBS, 1, m, z8);
     }
 
     // ---------------------------------------------------------------- encoder forward
-    uint64_t mk_h1, mk_h2, mk_b1, mk_b2, mk_none;
-    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XOBS, W0, 64, 64, 1, 0u); });
-    epilogue_fwd(C_D0, 64, fp + tc::F_B0, true, XH1, mk_h1, nop);
-    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XH1, W1, 64, 64, 4, 0u); });
-    epilogue_fwd(C_D0, 64, fp + tc::F_B1, true, XH2, mk_h2, nop);
-    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XH2, W2, 64, 16, 4, 0u); });
-    epilogue_fwd(C_D0, 16, fp + tc::F_B2, false, XF, mk_none, nop);
+    uint32_t mk_h1, mk_h2, mk_b1, mk_b2, mk_none;
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XOBS, W0, 64, 64, 1, 0u);
+    });
+    epilogue_fwd(C_D0, cg, fp + tc::F_B0, true, XH1, mk_h1, nop);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH1, W1, 64, 64, 4, 0u);
+    });
+    epilogue_fwd(C_D0, cg, fp + tc::F_B1, true, XH2, mk_h2, nop);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH2, W2, 64, 16, 4, 0u);
+    });
+    if (g0) epilogue_fwd(C_D0, 0, fp + tc::F_B2, false, XF, mk_none, nop);
 
     // ---------------------------------------------------------------- value head forward
-    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XF, WV0, 64, 64, 1, 0u); });
-    epilogue_fwd(C_D0, 64, fp + tc::F_BV0, true, XB1, mk_b1, nop);
-    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XB1, WV1, 64, 64, 4, 0u); });
-    float value = fp[tc::F_BV2];
-    epilogue_fwd(C_D0, 64, fp + tc::F_BV1, true, XB2, mk_b2, [&](int c0, float* v) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) value = fmaf(fp[tc::F_WV2 + c0 + j], v[j], value);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XF, WV0, 64, 64, 1, 0u);
+      if (p == 1) tc::gemm<false, false>(ld, tb + C_D1, XF, WA0, 64, 64, 1, 0u);  // action head layer 1, consumed later
     });
+    epilogue_fwd(C_D0, cg, fp + tc::F_BV0, true, XB1, mk_b1, nop);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XB1, WV1, 64, 64, 4, 0u);
+    });
+    {
+      float part = 0.f;
+      epilogue_fwd(C_D0, cg, fp + tc::F_BV1, true, XB2, mk_b2, [&](float* v) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) part = fmaf(fp[tc::F_WV2 + cg + j], v[j], part);
+      });
+      if (active) vpart[g * ROWS + m] = part;
+    }
+    __syncthreads();
+    const float value = active ? (((fp[tc::F_BV2] + vpart[m]) + vpart[ROWS + m]) + vpart[2 * ROWS + m]) + vpart[3 * ROWS + m]
+                               : 0.f;
 
     // ---------------------------------------------------------------- value loss (ppo.py:435-451)
     float dvalue = 0.f;
     bool bad = false;
-    if (valid) {
+    if (valid && active) {
       bad = !isfinite(value);
       const float c = h.clip_coefficient;
       const float e1 = value - ret;
-      float dvl;
+      float dvl, sv;
       if (h.clip_value_loss) {
         const float dv = value - val_old;
         const float clipped = val_old + lrx_clipf(dv, -c, c);
         const float e2 = clipped - ret;
         const float q1 = e1 * e1, q2 = e2 * e2;
-        s_val += (double)fminf(q1, q2);
+        sv = fminf(q1, q2);
         float u1, u2;
         tie_weights_f(q1, q2, u1, u2);
         dvl = invB * (u1 * e1 + u2 * e2 * clip_grad_f(dv, -c, c));
       } else {
-        s_val += (double)(e1 * e1);
+        sv = e1 * e1;
         dvl = invB * e1;
       }
+      if (g0) s_val += (double)sv;
       dvalue = h.value_loss_coefficient * dvl;
     }
     // ---------------------------------------------------------------- value head backward
     if (active) {
-      float d8[8] = {dvalue, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      tc::store8(DY8, 0, m, d8);
-#pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 8) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = ((mk_b2 >> (c0 + j)) & 1ull) ? dvalue * fp[tc::F_WV2 + c0 + j] : 0.f;
-        tc::store8(DY64, c0 >> 3, m, v);
+      if (g0) {
+        float d8[8] = {dvalue, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        tc::store8(DY8, 0, m, d8);
       }
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ((mk_b2 >> j) & 1u) ? dvalue * fp[tc::F_WV2 + cg + j] : 0.f;
+      tc::store8(DY64, (cg >> 3), m, v);
+      tc::store8(DY64, (cg >> 3) + 1, m, v + 8);
     }
-    sync_issue([&] {
-      tc::gemm<true, true>(tb + C_GV2, XB2, DY8, 64, 8, 4, 1u);            // dW_v2[in] += X^T dvalue
-      tc::gemm<true, true>(tb + C_GBV2, ONES, DY8, 64, 8, 4, 1u, 1, 3);    // db_v2
-      tc::gemm<false, true>(tb + C_D0, DY64, WV1, 64, 64, 4, 0u);          // dX = dY W
-      tc::gemm<true, true>(tb + C_GV1, DY64, XB1, 64, 64, 4, 1u);          // dW^T[out][in] += dY^T X
-      tc::gemm<true, true>(tb + C_GV1 + 64, DY64, ONES, 64, 8, 4, 1u, 3, 1);  // db
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, true>(ld, tb + C_D0, DY64, WV1, 64, 64, 4, 0u);            // dX = dY W
+      if (p == 1) tc::gemm<true, true>(ld, tb + C_GV1, DY64, XB1, 64, 64, 4, 1u);            // dW^T[out][in] += dY^T X
+      if (p == 2) tc::gemm<true, true>(ld, tb + C_GV2, XB2, DY8, 64, 8, 4, 1u);              // dW_v2[in] += X^T dvalue
+      if (p == 3) {
+        tc::gemm<true, true, 1, 3>(ld, tb + C_GBV2, ONES, DY8, 64, 8, 4, 1u);                // db_v2
+        tc::gemm<true, true, 3, 1>(ld, tb + C_GV1 + 64, DY64, ONES, 64, 8, 4, 1u);           // db_v1
+      }
     });
-    epilogue_bwd(C_D0, 64, mk_b1, true, DY64);
-    sync_issue([&] {
-      tc::gemm<false, true>(tb + C_DF, DY64, WV0, 64, 16, 4, 0u);          // d(features) from the value head
-      tc::gemm<true, true>(tb + C_GV0, DY64, XF, 64, 16, 4, 1u);
-      tc::gemm<true, true>(tb + C_GV0 + 16, DY64, ONES, 64, 8, 4, 1u, 3, 1);
+    epilogue_bwd(C_D0, cg, mk_b1, true, DY64);
+    // not waited for: nothing below touches DY64 / XF / C_DF / C_GV0 before the next waited step, whose
+    // commits (one per issuing warp, covering all its earlier MMAs) also cover these
+    issue_nowait([&](bool ld, int p) {
+      if (p == 1) tc::gemm<false, true>(ld, tb + C_DF, DY64, WV0, 64, 16, 4, 0u);            // d(features) from the value head
+      if (p == 2) tc::gemm<true, true>(ld, tb + C_GV0, DY64, XF, 64, 16, 4, 1u);
+      if (p == 3) tc::gemm<true, true, 3, 1>(ld, tb + C_GV0 + 16, DY64, ONES, 64, 8, 4, 1u);
     });
 
     // ---------------------------------------------------------------- action head forward
-    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XF, WA0, 64, 64, 1, 0u); });
-    epilogue_fwd(C_D0, 64, fp + tc::F_BA0, true, XB1, mk_b1, nop);
-    sync_issue([&] { tc::gemm<false, false>(tb + C_D0, XB1, WA1, 64, 16, 4, 0u); });
-    float a2[16];
-    epilogue_fwd(C_D0, 16, fp + tc::F_BA1, false, XA2, mk_none, [&](int, float* v) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) a2[j] = v[j];
+    epilogue_fwd(C_D1, cg, fp + tc::F_BA0, true, XB1, mk_b1, nop);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XB1, WA1, 64, 16, 4, 0u);
     });
-    // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261) on the FMA pipe
-    float head[LRX_MAX_NOUT];
+    if (g0) {
+      float a2[16];
+      epilogue_fwd(C_D0, 0, fp + tc::F_BA1, false, XA2, mk_none, [&](float* v) {
 #pragma unroll
-    for (int o = 0; o < LRX_MAX_NOUT; ++o) {
-      float s = fp[tc::F_BMAP + o];
-      if (o < a.n_out) {
+        for (int j = 0; j < 16; ++j) a2[j] = v[j];
+      });
+      // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261) on the FMA pipe
+      float head[LRX_MAX_NOUT];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s = fmaf(fp[tc::F_WMAP + o * 16 + i], a2[i], s);
+      for (int o = 0; o < LRX_MAX_NOUT; ++o) {
+        float s = fp[tc::F_BMAP + o];
+        if (o < a.n_out) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s = fmaf(fp[tc::F_WMAP + o * 16 + i], a2[i], s);
+        }
+        head[o] = s;
       }
-      head[o] = s;
-    }
 
-    // ---------------------------------------------------------------- policy loss (ppo.py:405-434,452-467)
-    float dhead[LRX_MAX_NOUT];
+      // -------------------------------------------------------------- policy loss (ppo.py:405-434,452-467)
+      float dhead[LRX_MAX_NOUT];
 #pragma unroll
-    for (int o = 0; o < LRX_MAX_NOUT; ++o) dhead[o] = 0.f;
-    if (valid) {
-      float logp, entropy, z_n = 0.f;
-      float lp[LRX_MAX_NOUT], pr[LRX_MAX_NOUT];
-      if (a.is_box) {
-        const float loc = head[0];
-        z_n = (act_f - loc) / scale;
-        logp = -0.5f * (z_n * z_n) - (LRX_HALF_LOG_2PI + log_scale);
-        entropy = 0.5f + LRX_HALF_LOG_2PI + log_scale;
-      } else {
+      for (int o = 0; o < LRX_MAX_NOUT; ++o) dhead[o] = 0.f;
+      if (valid && active) {
+        float logp, entropy, z_n = 0.f;
+        float lp[LRX_MAX_NOUT], pr[LRX_MAX_NOUT];
+        if (a.is_box) {
+          const float loc = head[0];
+          z_n = (act_f - loc) / scale;
+          logp = -0.5f * (z_n * z_n) - (LRX_HALF_LOG_2PI + log_scale);
+          entropy = 0.5f + LRX_HALF_LOG_2PI + log_scale;
+        } else {
 #pragma unroll
-        for (int j = 0; j < LRX_MAX_NOUT; ++j) lp[j] = j < a.n_out ? head[j] : 0.f;
-        log_softmax_n<LRX_MAX_NOUT>(lp, a.n_out);
-        logp = 0.f;
-        entropy = 0.f;
+          for (int j = 0; j < LRX_MAX_NOUT; ++j) lp[j] = j < a.n_out ? head[j] : 0.f;
+          log_softmax_n<LRX_MAX_NOUT>(lp, a.n_out);
+          logp = 0.f;
+          entropy = 0.f;
 #pragma unroll
-        for (int j = 0; j < LRX_MAX_NOUT; ++j) {
-          if (j < a.n_out) {
-            pr[j] = expf(lp[j]);
-            entropy -= pr[j] * lp[j];
-            if (j == act_i) logp = lp[j];
+          for (int j = 0; j < LRX_MAX_NOUT; ++j) {
+            if (j < a.n_out) {
+              pr[j] = expf(lp[j]);
+              entropy -= pr[j] * lp[j];
+              if (j == act_i) logp = lp[j];
+            }
+          }
+        }
+        bad = bad || !(isfinite(logp) && isfinite(entropy));  // ppo.py:413-417
+        if (bad) s_bad += 1.0;
+        const float log_ratio = logp - logp_old;
+        const float ratio = expf(log_ratio);
+        s_kl += (double)(ratio - log_ratio);
+        const float c = h.clip_coefficient, lo = 1.f - c, hi = 1.f + c;
+        const float s1 = A * ratio, s2 = A * lrx_clipf(ratio, lo, hi);
+        s_pol += (double)fminf(s1, s2);
+        float w1, w2;
+        tie_weights_f(s1, s2, w1, w2);
+        const float dlogp = -invB * (w1 * A * ratio + w2 * A * clip_grad_f(ratio, lo, hi) * ratio);
+        s_ent += (double)entropy;
+        const float ch = h.entropy_loss_coefficient;
+        if (a.is_box) {
+          dhead[0] = dlogp * z_n / scale;
+          s_dls += (double)(dlogp * (z_n * z_n - 1.0f));
+        } else {
+#pragma unroll
+          for (int j = 0; j < LRX_MAX_NOUT; ++j) {
+            if (j < a.n_out) {
+              const float dH = -pr[j] * (lp[j] + entropy);
+              dhead[j] = dlogp * ((j == act_i ? 1.f : 0.f) - pr[j]) + (-ch * invB) * dH;
+            }
           }
         }
       }
-      bad = bad || !(isfinite(logp) && isfinite(entropy));  // ppo.py:413-417
-      if (bad) s_bad += 1.0;
-      const float log_ratio = logp - logp_old;
-      const float ratio = expf(log_ratio);
-      s_kl += (double)(ratio - log_ratio);
-      const float c = h.clip_coefficient, lo = 1.f - c, hi = 1.f + c;
-      const float s1 = A * ratio, s2 = A * lrx_clipf(ratio, lo, hi);
-      s_pol += (double)fminf(s1, s2);
-      float w1, w2;
-      tie_weights_f(s1, s2, w1, w2);
-      const float dlogp = -invB * (w1 * A * ratio + w2 * A * clip_grad_f(ratio, lo, hi) * ratio);
-      s_ent += (double)entropy;
-      const float ch = h.entropy_loss_coefficient;
-      if (a.is_box) {
-        dhead[0] = dlogp * z_n / scale;
-        s_dls += (double)(dlogp * (z_n * z_n - 1.0f));
-      } else {
+      // -------------------------------------------------------------- action head backward (mapping, FMA)
+      if (active) {
+        tc::store8(DY8, 0, m, dhead);
+        float d16[16];
 #pragma unroll
-        for (int j = 0; j < LRX_MAX_NOUT; ++j) {
-          if (j < a.n_out) {
-            const float dH = -pr[j] * (lp[j] + entropy);
-            dhead[j] = dlogp * ((j == act_i ? 1.f : 0.f) - pr[j]) + (-ch * invB) * dH;
-          }
+        for (int i = 0; i < 16; ++i) {
+          float s = 0.f;
+#pragma unroll
+          for (int o = 0; o < LRX_MAX_NOUT; ++o)
+            if (o < a.n_out) s = fmaf(dhead[o], fp[tc::F_WMAP + o * 16 + i], s);
+          d16[i] = s;
         }
+        tc::store8(DY16, 0, m, d16);
+        tc::store8(DY16, 1, m, d16 + 8);
       }
     }
-    // ---------------------------------------------------------------- action head backward
-    if (active) {
-      tc::store8(DY8, 0, m, dhead);
-      float d16[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float s = 0.f;
-#pragma unroll
-        for (int o = 0; o < LRX_MAX_NOUT; ++o)
-          if (o < a.n_out) s = fmaf(dhead[o], fp[tc::F_WMAP + o * 16 + i], s);
-        d16[i] = s;
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, true>(ld, tb + C_D0, DY16, WA1, 64, 64, 1, 0u);            // dX = dY16 W_a1 (K = 16 outputs)
+      if (p == 1) tc::gemm<true, true>(ld, tb + C_GA1, XB1, DY16, 64, 16, 4, 1u);            // dW[in][out] += X^T dY
+      if (p == 2) tc::gemm<true, true>(ld, tb + C_GMAP, XA2, DY8, 64, 8, 4, 1u);             // dW_map[in (16 valid)][out]
+      if (p == 3) {
+        tc::gemm<true, true, 1, 3>(ld, tb + C_GBMAP, ONES, DY8, 64, 8, 4, 1u);
+        tc::gemm<true, true, 1, 3>(ld, tb + C_GBA1, ONES, DY16, 64, 16, 4, 1u);
       }
-      tc::store8(DY16, 0, m, d16);
-      tc::store8(DY16, 1, m, d16 + 8);
-    }
-    sync_issue([&] {
-      tc::gemm<true, true>(tb + C_GMAP, XA2, DY8, 64, 8, 4, 1u);           // dW_map[in (16 valid)][out]
-      tc::gemm<true, true>(tb + C_GBMAP, ONES, DY8, 64, 8, 4, 1u, 1, 3);
-      tc::gemm<false, true>(tb + C_D0, DY16, WA1, 64, 64, 1, 0u);          // dX = dY16 W_a1   (K = 16 outputs)
-      tc::gemm<true, true>(tb + C_GA1, XB1, DY16, 64, 16, 4, 1u);          // dW[in][out] += X^T dY
-      tc::gemm<true, true>(tb + C_GBA1, ONES, DY16, 64, 16, 4, 1u, 1, 3);
     });
-    epilogue_bwd(C_D0, 64, mk_b1, true, DY64);
-    sync_issue([&] {
-      tc::gemm<false, true>(tb + C_DF, DY64, WA0, 64, 16, 4, 1u);          // d(features) += action head
-      tc::gemm<true, true>(tb + C_GA0, DY64, XF, 64, 16, 4, 1u);
-      tc::gemm<true, true>(tb + C_GA0 + 16, DY64, ONES, 64, 8, 4, 1u, 3, 1);
+    epilogue_bwd(C_D0, cg, mk_b1, true, DY64);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, true>(ld, tb + C_DF, DY64, WA0, 64, 16, 4, 1u);            // d(features) += action head
+      if (p == 1) tc::gemm<true, true>(ld, tb + C_GA0, DY64, XF, 64, 16, 4, 1u);
+      if (p == 2) tc::gemm<true, true, 3, 1>(ld, tb + C_GA0 + 16, DY64, ONES, 64, 8, 4, 1u);
     });
 
     // ---------------------------------------------------------------- encoder backward
-    epilogue_bwd(C_DF, 16, 0, false, DY16);
-    sync_issue([&] {
-      tc::gemm<false, true>(tb + C_D0, DY16, W2, 64, 64, 1, 0u);
-      tc::gemm<true, true>(tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
-      tc::gemm<true, true>(tb + C_GB2, ONES, DY16, 64, 16, 4, 1u, 1, 3);
+    if (g0) epilogue_bwd(C_DF, 0, 0, false, DY16);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, true>(ld, tb + C_D0, DY16, W2, 64, 64, 1, 0u);
+      if (p == 1) tc::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
+      if (p == 2) tc::gemm<true, true, 1, 3>(ld, tb + C_GB2, ONES, DY16, 64, 16, 4, 1u);
     });
-    epilogue_bwd(C_D0, 64, mk_h2, true, DY64);
-    sync_issue([&] {
-      tc::gemm<false, true>(tb + C_D0, DY64, W1, 64, 64, 4, 0u);
-      tc::gemm<true, true>(tb + C_G1, DY64, XH1, 64, 64, 4, 1u);
-      tc::gemm<true, true>(tb + C_G1 + 64, DY64, ONES, 64, 8, 4, 1u, 3, 1);
+    epilogue_bwd(C_D0, cg, mk_h2, true, DY64);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, true>(ld, tb + C_D0, DY64, W1, 64, 64, 4, 0u);
+      if (p == 1) tc::gemm<true, true>(ld, tb + C_G1, DY64, XH1, 64, 64, 4, 1u);
+      if (p == 2) tc::gemm<true, true, 3, 1>(ld, tb + C_G1 + 64, DY64, ONES, 64, 8, 4, 1u);
     });
-    epilogue_bwd(C_D0, 64, mk_h1, true, DY64);
-    sync_issue([&] {
-      tc::gemm<true, true>(tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
-      tc::gemm<true, true>(tb + C_G0 + 16, DY64, ONES, 64, 8, 4, 1u, 3, 1);
+    epilogue_bwd(C_D0, cg, mk_h1, true, DY64);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<true, true>(ld, tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
+      if (p == 1) tc::gemm<true, true, 3, 1>(ld, tb + C_G0 + 16, DY64, ONES, 64, 8, 4, 1u);
     });
+
+    // hand the prefetched rows down to lanes 0-15; lanes 16-31 fetch the tile after next
+    {
+      const unsigned full = 0xffffffffu;
+      const float s_actf = __shfl_down_sync(full, act_f, 16), s_lp = __shfl_down_sync(full, logp_old, 16);
+      const float s_A = __shfl_down_sync(full, A, 16), s_ret = __shfl_down_sync(full, ret, 16);
+      const float s_vo = __shfl_down_sync(full, val_old, 16);
+      const int s_acti = __shfl_down_sync(full, act_i, 16);
+      const int s_valid = __shfl_down_sync(full, (int)valid, 16);
+      float so[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) so[k] = __shfl_down_sync(full, o[k], 16);
+      if (active) {
+        act_f = s_actf; logp_old = s_lp; A = s_A; ret = s_ret; val_old = s_vo; act_i = s_acti; valid = s_valid != 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = so[k];
+      } else {
+        load_row(tile + 2 * (int)gridDim.x);
+      }
+    }
   }
 
+  if (a.prof && blockIdx.x == 0 && (tid == 0 || tid == 128)) {
+    long long* o = a.prof + (tid ? 8 : 0);
+    o[0] = pf_epi; o[1] = pf_sync; o[2] = pf_issue; o[3] = pf_wait; o[4] = pf_ld; o[5] = pf_st; o[6] = pf_fence; o[7] = 0;
+  }
   // ------------------------------------------------------------------ flush the gradient partial
   float* part = a.partial + (size_t)blockIdx.x * a.partial_stride;
   const tc::LayerOffsets& lo = a.lo;
@@ -485,24 +591,22 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       }
     }
   };
-  flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0);
-  flush_T(C_G1, 64, 64, tc::L_ENC1);
-  flush_N(C_G2, C_GB2, 64, 16, 16, tc::L_ENC2);
-  flush_T(C_GV0, 16, 16, tc::L_V0);
-  flush_T(C_GV1, 64, 64, tc::L_V1);
-  flush_N(C_GV2, C_GBV2, 64, 1, 8, tc::L_V2);
-  flush_T(C_GA0, 16, 16, tc::L_A0);
-  flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1);
-  flush_N(C_GMAP, C_GBMAP, 16, a.n_out, 8, tc::L_MAP);
+  // nine layers over the four column groups of warps
+  if (g == 0) { flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0); flush_N(C_G2, C_GB2, 64, 16, 16, tc::L_ENC2); flush_N(C_GMAP, C_GBMAP, 16, a.n_out, 8, tc::L_MAP); }
+  if (g == 1) { flush_T(C_G1, 64, 64, tc::L_ENC1); flush_N(C_GV2, C_GBV2, 64, 1, 8, tc::L_V2); }
+  if (g == 2) { flush_T(C_GV1, 64, 64, tc::L_V1); flush_T(C_GV0, 16, 16, tc::L_V0); }
+  if (g == 3) { flush_T(C_GA0, 16, 16, tc::L_A0); flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1); }
 
   // ------------------------------------------------------------------ loss statistics (fixed order)
   __syncthreads();
   double* sh = reinterpret_cast<double*>(smem + OFF_DY64);  // [6][4 warps]
   double v6[6] = {s_kl, s_pol, s_val, s_ent, s_dls, s_bad};
+  if (g0) {
 #pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    v6[q] = warp_sum(v6[q]);
-    if (lane == 0) sh[q * 4 + warp] = v6[q];
+    for (int k = 0; k < 6; ++k) {
+      v6[k] = warp_sum(v6[k]);
+      if (lane == 0) sh[k * 4 + q] = v6[k];
+    }
   }
   __syncthreads();
   if (tid < 6) {
@@ -580,6 +684,14 @@ int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxB
   a.is_box = pol->is_box;
   a.lo = tc::layer_offsets(*pol);
   const int grid = a.n_tiles < LRX_NUM_SMS ? a.n_tiles : LRX_NUM_SMS;
+  static long long* prof_dev = nullptr;
+  static int prof_left = -1;
+  if (prof_left < 0) {
+    const char* e = getenv("LRX_FUSED_PROF");
+    prof_left = (e && e[0] == '1') ? 3 : 0;
+    if (prof_left) cudaMalloc(&prof_dev, 16 * sizeof(long long));
+  }
+  a.prof = prof_left > 0 ? prof_dev : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -590,6 +702,17 @@ int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxB
   lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid, a.lo.log_std,
                              h->entropy_loss_coefficient, (double)B_global, gradbuf, stream);
   LRX_LAUNCH_CHECK();
+  if (a.prof) {
+    long long hp[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost);
+    const int tiles0 = (a.n_tiles + grid - 1) / grid;
+    for (int w = 0; w < 2; ++w)
+      fprintf(stderr, "[fused prof] tiles/CTA %d; cycles/tile warp%d: between-steps %lld (tmem-ld %lld, split+store %lld) fence %lld barrier %lld issue %lld mma-wait %lld\n",
+              tiles0, w * 4, hp[8 * w + 0] / tiles0, hp[8 * w + 4] / tiles0, hp[8 * w + 5] / tiles0, hp[8 * w + 6] / tiles0,
+              (hp[8 * w + 1] - hp[8 * w + 6]) / tiles0, hp[8 * w + 2] / tiles0, hp[8 * w + 3] / tiles0);
+    --prof_left;
+  }
   *handled = true;
   return LRX_OK;
 }
