@@ -93,6 +93,101 @@ gae_tn_kernel(const float* __restrict__ rew, const float* __restrict__ val,
   }
 }
 
+// Two adjacent envs per lane (float2 / uchar2 accesses: 256-byte rows per warp, half the
+// instructions); requires N even.  Same chunked affine scan as gae_tn_kernel.
+template <int L>
+__global__ void __launch_bounds__(512)
+gae_tn2_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+               const uint8_t* __restrict__ done, const float* __restrict__ last_val,
+               float* __restrict__ adv, float* __restrict__ ret, int N, int T, float gamma,
+               float lam, double* ev_sums) {
+  __shared__ float2 sA[16][32], sP[16][32];
+  __shared__ double sEv[16][4];
+  const int lane = threadIdx.x, c = threadIdx.y, C = blockDim.y;
+  const int n = (blockIdx.x * 32 + lane) * 2;
+  const bool live = n < N;
+  const int nl = live ? n : N - 2;
+  const float gl = gamma * lam;
+  const int seg_len = C * L;
+  const int num_seg = (T + seg_len - 1) / seg_len;
+  const float2 lv = *reinterpret_cast<const float2*>(last_val + nl);
+  float2 seg_carry = make_float2(0.f, 0.f);
+  double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+
+  for (int seg = num_seg - 1; seg >= 0; --seg) {
+    const int t0 = seg * seg_len + c * L;
+    float2 r[L], v[L + 1], nd[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int t = t0 + i;
+      const bool ok = t < T;
+      const size_t off = (size_t)(ok ? t : T - 1) * N + nl;
+      r[i] = ok ? *reinterpret_cast<const float2*>(rew + off) : make_float2(0.f, 0.f);
+      v[i] = ok ? *reinterpret_cast<const float2*>(val + off) : lv;
+      const uchar2 d = ok ? *reinterpret_cast<const uchar2*>(done + off) : make_uchar2(0, 0);
+      nd[i] = make_float2(1.0f - (float)d.x, 1.0f - (float)d.y);
+    }
+    v[L] = (t0 + L < T) ? *reinterpret_cast<const float2*>(val + (size_t)(t0 + L) * N + nl) : lv;
+
+    float2 a = make_float2(0.f, 0.f), p = make_float2(1.f, 1.f);
+    float2 A[L], P[L];
+#pragma unroll
+    for (int i = L - 1; i >= 0; --i) {
+      const bool ok = t0 + i < T;
+      const float dx = ok ? r[i].x + gamma * v[i + 1].x * nd[i].x - v[i].x : 0.f;
+      const float dy = ok ? r[i].y + gamma * v[i + 1].y * nd[i].y - v[i].y : 0.f;
+      const float cx = ok ? gl * nd[i].x : 1.f, cy = ok ? gl * nd[i].y : 1.f;
+      a.x = dx + cx * a.x; a.y = dy + cy * a.y;
+      p.x = cx * p.x; p.y = cy * p.y;
+      A[i] = a;
+      P[i] = p;
+    }
+    sA[c][lane] = a;
+    sP[c][lane] = p;
+    __syncthreads();
+    float2 carry = seg_carry;
+    for (int cc = C - 1; cc > c; --cc) {
+      const float2 qa = sA[cc][lane], qp = sP[cc][lane];
+      carry.x = qa.x + qp.x * carry.x;
+      carry.y = qa.y + qp.y * carry.y;
+    }
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;  // <= 2L terms per chunk in fp32, then fp64
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int t = t0 + i;
+      if (t < T && live) {
+        const float2 Ai = make_float2(A[i].x + P[i].x * carry.x, A[i].y + P[i].y * carry.y);
+        const float2 Ri = make_float2(Ai.x + v[i].x, Ai.y + v[i].y);
+        const size_t off = (size_t)t * N + n;
+        *reinterpret_cast<float2*>(adv + off) = Ai;
+        *reinterpret_cast<float2*>(ret + off) = Ri;
+        f0 += Ri.x + Ri.y; f1 = fmaf(Ri.x, Ri.x, fmaf(Ri.y, Ri.y, f1));
+        f2 += Ai.x + Ai.y; f3 = fmaf(Ai.x, Ai.x, fmaf(Ai.y, Ai.y, f3));
+      }
+    }
+    e0 += f0; e1 += f1; e2 += f2; e3 += f3;
+    float2 cr = carry;
+    for (int cc = c; cc >= 0; --cc) {
+      const float2 qa = sA[cc][lane], qp = sP[cc][lane];
+      cr.x = qa.x + qp.x * cr.x;
+      cr.y = qa.y + qp.y * cr.y;
+    }
+    seg_carry = cr;
+    __syncthreads();
+  }
+
+  if (ev_sums) {
+    e0 = warp_sum(e0); e1 = warp_sum(e1); e2 = warp_sum(e2); e3 = warp_sum(e3);
+    if (lane == 0) { sEv[c][0] = e0; sEv[c][1] = e1; sEv[c][2] = e2; sEv[c][3] = e3; }
+    __syncthreads();
+    if (c == 0 && lane < 4) {
+      double s = 0;
+      for (int cc = 0; cc < C; ++cc) s += sEv[cc][lane];
+      atomicAdd(ev_sums + lane, s);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 gae_nt_kernel(const float* __restrict__ rew, const float* __restrict__ val,
               const uint8_t* __restrict__ done, const float* __restrict__ last_val,
@@ -144,6 +239,9 @@ gae_nt_kernel(const float* __restrict__ rew, const float* __restrict__ val,
   }
 }
 
+static int g_gae_chunk = 0;  // 0 = automatic; tools/gae_time.py sweeps it
+extern "C" void lrx_debug_set_gae_chunk(int L) { g_gae_chunk = L; }
+
 extern "C" int lrx_gae(const float* rew, const float* val, const uint8_t* done,
                        const float* last_value, float* adv, float* ret, int32_t N, int32_t T,
                        float gamma, float lam, int32_t layout, double* ev_sums,
@@ -157,10 +255,26 @@ extern "C" int lrx_gae(const float* rew, const float* val, const uint8_t* done,
   LRX_REQUIRE(rew && val && done && last_value && adv && ret, LRX_ERR_INVALID_ARG, "lrx_gae: NULL pointer");
   if (layout == LRX_LAYOUT_TN) {
     const int blocks = (N + 31) / 32;
-    if (T >= 64) {
+    const int Lsel = g_gae_chunk > 0 ? g_gae_chunk : 24;
+    if (T >= 64 && (N % 2) == 0 && N >= 64 && (Lsel == 8 || Lsel == 28 || Lsel == 24)) {
+      const int blocks2 = (N / 2 + 31) / 32;
+      if (Lsel == 24) {
+        int C = (T + 3) / 4;
+        if (C > 16) C = 16;
+        gae_tn2_kernel<4><<<blocks2, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
+      } else {
+        int C = (T + 7) / 8;
+        if (C > 16) C = 16;
+        gae_tn2_kernel<8><<<blocks2, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
+      }
+    } else if (T >= 64 && Lsel == 16) {
       int C = (T + 15) / 16;
       if (C > 16) C = 16;
       gae_tn_kernel<16><<<blocks, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
+    } else if (T >= 64 && (Lsel == 8 || Lsel == 18)) {
+      int C = (T + 7) / 8;
+      if (C > 16) C = 16;
+      gae_tn_kernel<8><<<blocks, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
     } else {
       int C = (T + 3) / 4;
       if (C > 16) C = 16;

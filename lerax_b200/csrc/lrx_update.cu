@@ -305,25 +305,41 @@ __global__ void __launch_bounds__(LRX_LOSS_THREADS) loss_kernel(const LossArgs a
 // =========================================================== partial-gradient reduction
 // gradbuf[p] = sum_z partial[z][p]; the last block also folds the loss partial sums into
 // the log_std gradient and the stat slots.  Fixed summation order -> deterministic.
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, long long stride,
-                                       int P, const double* __restrict__ loss_partial, int loss_blocks,
-                                       int log_std_off, float ent_coef, double B_global,
-                                       float* gradbuf) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P && p != log_std_off) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * stride + p];
-    gradbuf[p] = s;
+// Block = 32 parameters x 8 row groups: each thread sums every 8th partial row of one parameter
+// (independent loads in flight), the 8 sub-sums are combined in a fixed order.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int splits, long long stride, int P,
+                       const double* __restrict__ loss_partial, int loss_blocks, int log_std_off,
+                       float ent_coef, double B_global, float* gradbuf) {
+  __shared__ float sub[8][33];
+  const int pl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + pl;
+  float s = 0.f;
+  if (p < P) {
+#pragma unroll 4
+    for (int z = rg; z < splits; z += 8) s += partial[(size_t)z * stride + p];
   }
-  if (blockIdx.x == 0 && threadIdx.x < 6) {
-    double s = 0;
-    for (int b = 0; b < loss_blocks; ++b) s += loss_partial[(size_t)b * 8 + threadIdx.x];
-    const int q = threadIdx.x;
-    if (q < 4) gradbuf[P + q] = (float)(s / B_global);       // kl, pol, val, ent means' share
-    else if (q == 4) { if (log_std_off >= 0) gradbuf[log_std_off] = (float)s; }
-    else gradbuf[P + 6] = (float)s;                            // non-finite row count
+  sub[rg][pl] = s;
+  __syncthreads();
+  if (rg == 0 && p < P && p != log_std_off) {
+    float t = sub[0][pl];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sub[k][pl];
+    gradbuf[p] = t;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 6) { gradbuf[P + 4] = 0.f; gradbuf[P + 5] = 0.f; gradbuf[P + 7] = 0.f; }
+  // loss statistics: warp q (< 6) of block 0 reduces quantity q; lane-strided sums then a
+  // fixed-order shuffle tree
+  if (blockIdx.x == 0 && rg < 6) {
+    double d = 0;
+    for (int b = pl; b < loss_blocks; b += 32) d += loss_partial[(size_t)b * 8 + rg];
+    d = warp_sum(d);
+    if (pl == 0) {
+      if (rg < 4) gradbuf[P + rg] = (float)(d / B_global);       // kl, pol, val, ent means' share
+      else if (rg == 4) { if (log_std_off >= 0) gradbuf[log_std_off] = (float)d; }
+      else gradbuf[P + 6] = (float)d;                              // non-finite row count
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 255) { gradbuf[P + 4] = 0.f; gradbuf[P + 5] = 0.f; gradbuf[P + 7] = 0.f; }
 }
 
 // ===================================================================== clip + Adam
@@ -344,7 +360,7 @@ apply_kernel(float* __restrict__ params, float* __restrict__ m, float* __restric
     float gp = g[p] + (p == log_std_off ? ls_extra : 0.f);
     ss += (double)gp * gp;
   }
-  ss = warp_sum(ss);
+  ss = warp_sum(ss);  // fixed order -> deterministic
   if ((tid & 31) == 0) red[tid >> 5] = ss;
   __syncthreads();
   if (tid == 0) {
@@ -472,7 +488,7 @@ extern "C" size_t lrx_ppo_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) {
 void lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
                                 int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
                                 cudaStream_t s) {
-  reduce_partials_kernel<<<(P + 255) / 256, 256, 0, s>>>(partial, splits, stride, P, loss_partial, loss_blocks,
+  reduce_partials_kernel<<<(P + 31) / 32, 256, 0, s>>>(partial, splits, stride, P, loss_partial, loss_blocks,
                                                        log_std_off, ent_coef, B_global, gradbuf);
 }
 
@@ -620,7 +636,7 @@ extern "C" int lrx_ppo_grad(const LrxPolicyDesc* pol, const float* params, const
     if ((rc = backprop_chain(0, w.dfeat, nullptr, false))) return rc;
   }
 
-  reduce_partials_kernel<<<(P + 255) / 256, 256, 0, s>>>(w.partial, w.splits, (long long)w.P_pad, P, w.loss_partial,
+  reduce_partials_kernel<<<(P + 31) / 32, 256, 0, s>>>(w.partial, w.splits, (long long)w.P_pad, P, w.loss_partial,
                                                         nchunks * w.loss_blocks, tab.log_std_off,
                                                         h->entropy_loss_coefficient, (double)B_global, gradbuf);
   LRX_LAUNCH_CHECK();
