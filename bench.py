@@ -334,10 +334,18 @@ def run_ours(args):
     else:
         ach = stages[dominant]["tflops"]
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s"}
-    roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": None, "kernel": dominant,
-                 "peak_source": peaks["source"],
-                 "note": "fp32 FMA kernels: the binding pipe is fp32 FMA (~74 TFLOP/s at 1965 MHz), reported against "
-                         "the measured bf16 tensor peak as the contract asks"})
+    notes = {
+        "update": "ppo_grad_fused_kernel (tcgen05, bf16x3 fp32 emulation): achieved = algorithmic fp32 FLOPs (75.3 kFLOP "
+                  "per row-epoch) / update-stage time; the kernel executes 6 bf16 MMAs per fp32 product on top of that. "
+                  "traffic = dram bytes per fused launch (one minibatch of envs*horizon/minibatches rows) from the "
+                  "ncu --set full capture in profiles/r1_ppo_grad_fused.md",
+        "rollout": "rollout_generic_kernel: fp32 FMA (the binding pipe is the ~74 TFLOP/s FMA pipe), reported against "
+                   "the measured bf16 tensor peak as the contract asks",
+        "gae": "gae_tn2_kernel: 17 algorithmic bytes per element",
+    }
+    traffic = {"update": 129.9e6 if (args.envs, args.horizon, args.batches) == (N_ENVS, T_STEPS, N_BATCHES) else None}
+    roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": traffic.get(dominant), "kernel": dominant,
+                 "peak_source": peaks["source"], "note": notes[dominant]})
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
