@@ -1,10 +1,419 @@
-// Register-tiled rollout for the default policy widths (tried before the generic kernel).
+// Fused persistent rollout for the default MLPActorCriticPolicy widths on the tensor cores.
+//
+// Reference: algorithm/ppo.py:199-316 (PPO.step / collect_rollout) under the vmap of :360-368;
+// policy/actor_critic/mlp.py:133-157; the env functors of lrx_env.cuh.  Same contract as the
+// generic kernel in lrx_rollout.cu (which keeps serving non-default widths); tried first.
+//
+// One CTA owns 128 envs for all T steps (one UMMA M = 128 tile: env i of the CTA = TMEM lane i).
+// The Linear weights sit in shared memory as bf16 pieces (lrx_tc.cuh, fp32 emulation with six
+// bf16 products per fp32 product); every policy layer is one group of tcgen05.mma whose fp32
+// result is pulled from TMEM by the env's thread (warp w: TMEM quadrant w & 3, column group
+// w >> 2), biased / ReLU'd and written back to shared memory as the next layer's operand.  The
+// env state, the Tsit5 step, sampling (Philox4x32-10), reward / done / reset stay in registers
+// of the 128 threads of column group 0, which also stream the buffer row to HBM (coalesced over
+// envs).  Per env-step: 5 MMA round trips (enc0, enc1, enc2, both heads' layer 1, both heads'
+// layer 2); the value bootstrap of a truncated step (ppo.py:248-259) re-runs the value path for
+// the whole tile only on steps where some env of the CTA truncates.
 #include "lrx_env.cuh"
 #include "lrx_policy.cuh"
+#include "lrx_tc.cuh"
+
+namespace {
+
+constexpr int ENVS = 128;      // envs per CTA = UMMA M
+constexpr int THREADS = 512;   // 16 warps
+constexpr int ISSUERS = 2;     // warps 0 and 1 issue (value / action head GEMMs in parallel)
+constexpr uint32_t LRX_STREAM_INIT_ = 2;
+
+constexpr uint32_t PW16 = 64 * 16 * 2, PW64 = 64 * 64 * 2;          // weight pieces ([64][16], [64][64] / [16][64] = PW16)
+constexpr uint32_t PX16 = ENVS * 16 * 2, PX64 = ENVS * 64 * 2;      // activation pieces
+constexpr uint32_t OFF_W0 = 0;
+constexpr uint32_t OFF_W1 = OFF_W0 + 3 * PW16;
+constexpr uint32_t OFF_W2 = OFF_W1 + 3 * PW64;
+constexpr uint32_t OFF_WV0 = OFF_W2 + 3 * PW16;
+constexpr uint32_t OFF_WV1 = OFF_WV0 + 3 * PW16;
+constexpr uint32_t OFF_WA0 = OFF_WV1 + 3 * PW64;
+constexpr uint32_t OFF_WA1 = OFF_WA0 + 3 * PW16;
+constexpr uint32_t OFF_XOBS = OFF_WA1 + 3 * PW16;
+constexpr uint32_t OFF_XH1 = OFF_XOBS + 3 * PX16;   // encoder layer 1, then value head layer 1
+constexpr uint32_t OFF_XH2 = OFF_XH1 + 3 * PX64;    // encoder layer 2, then action head layer 1
+constexpr uint32_t OFF_XF = OFF_XH2 + 3 * PX64;
+constexpr uint32_t OFF_F32 = OFF_XF + 3 * PX16;
+constexpr uint32_t OFF_VPART = OFF_F32 + 640 * 4;   // [4][128] partial value dot products
+constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ENVS * 4;
+constexpr uint32_t SMEM_BYTES = OFF_MISC + 64;
+static_assert(SMEM_BYTES <= 227 * 1024, "fused rollout kernel exceeds shared memory");
+
+constexpr uint32_t C_D0 = 0, C_D1 = 64, TMEM_COLS = 128;
+
+struct RolloutArgs {
+  LrxEnvDesc env;
+  const float* params;
+  LrxEnvState st;
+  LrxRng rng;
+  LrxReplay rp;
+  LrxRolloutOut out;
+  int N, T;
+  float gamma;
+  int n_out;
+  tc::LayerOffsets lo;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(THREADS, 1) rollout_tc_kernel(const __grid_constant__ RolloutArgs a) {
+  using E = Env<KIND>;
+  constexpr int SD = E::SD, OD = E::OD;
+  constexpr bool BOX = EnvDims<KIND>::BOX;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
+  const int q = warp & 3, g = warp >> 2;
+  const bool g0 = (g == 0);
+  const int m = q * 32 + lane;  // env of the CTA owned by this thread = TMEM lane
+  float* fp = reinterpret_cast<float*>(smem + OFF_F32);
+  float* vpart = reinterpret_cast<float*>(smem + OFF_VPART);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_MISC);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 8);
+
+  const tc::Mat W0{smem + OFF_W0, 64, PW16}, W1{smem + OFF_W1, 64, PW64}, W2{smem + OFF_W2, 16, PW16};
+  const tc::Mat WV0{smem + OFF_WV0, 64, PW16}, WV1{smem + OFF_WV1, 64, PW64};
+  const tc::Mat WA0{smem + OFF_WA0, 64, PW16}, WA1{smem + OFF_WA1, 16, PW16};
+  const tc::Mat XOBS{smem + OFF_XOBS, ENVS, PX16}, XH1{smem + OFF_XH1, ENVS, PX64}, XH2{smem + OFF_XH2, ENVS, PX64};
+  const tc::Mat XF{smem + OFF_XF, ENVS, PX16};
+
+  tc::stage_weight(a.params + a.lo.w[tc::L_ENC0], 64, OD, 16, W0, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_ENC1], 64, 64, 64, W1, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_ENC2], 16, 64, 64, W2, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_V0], 64, 16, 16, WV0, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_V1], 64, 64, 64, WV1, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_A0], 64, 16, 16, WA0, tid, THREADS);
+  tc::stage_weight(a.params + a.lo.w[tc::L_A1], 16, 64, 64, WA1, tid, THREADS);
+  tc::stage_f32(a.params, a.lo, a.n_out, fp, tid, THREADS);
+  if (tid == 0) {
+    umma::mbar_init(bar, ISSUERS);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tslot, TMEM_COLS);
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tb = *tslot;
+  const uint32_t tw = umma::tmem_addr(tb, q * 32, 0);
+  uint32_t phase = 0;
+
+  auto sync_issue = [&](auto&& issue) {
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp < ISSUERS) {
+      umma::tc_fence_after();
+      const bool leader = umma::elect_one();
+      issue(leader, warp);
+      if (leader) umma::mma_commit(bar);
+      __syncwarp();
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::tc_fence_after();
+  };
+  // columns [c0, c0+16) of a layer output -> + bias -> optional ReLU -> operand; fn sees the values
+  auto epilogue = [&](uint32_t col, int c0, const float* bias, bool relu, const tc::Mat& dst, auto&& fn) {
+    float v[16];
+    umma::tmem_ld16(tw + col + c0, v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] += bias[c0 + j];
+      if (relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    fn(v);
+    tc::store8(dst, (c0 >> 3), m, v);
+    tc::store8(dst, (c0 >> 3) + 1, m, v + 8);
+  };
+  auto nop = [](float*) {};
+  const int cg = g * 16;
+
+  // MLPActorCriticPolicy forward for the tile (mlp.py:133-157): value for every thread of the env's
+  // row, raw action-head outputs (logits / loc) in `head` for column group 0 when want_head.
+  float head[LRX_MAX_NOUT];
+  auto forward = [&](const float (&o)[OD], bool want_head) -> float {
+    if (g0) {
+      float ob[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) ob[k] = (k < OD) ? o[k < OD ? k : 0] : 0.f;
+      tc::store8(XOBS, 0, m, ob);
+      tc::store8(XOBS, 1, m, ob + 8);
+    }
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XOBS, W0, 128, 64, 1, 0u);
+    });
+    epilogue(C_D0, cg, fp + tc::F_B0, true, XH1, nop);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH1, W1, 128, 64, 4, 0u);
+    });
+    epilogue(C_D0, cg, fp + tc::F_B1, true, XH2, nop);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH2, W2, 128, 16, 4, 0u);
+    });
+    if (g0) epilogue(C_D0, 0, fp + tc::F_B2, false, XF, nop);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XF, WV0, 128, 64, 1, 0u);
+      if (p == 1 && want_head) tc::gemm<false, false>(ld, tb + C_D1, XF, WA0, 128, 64, 1, 0u);
+    });
+    epilogue(C_D0, cg, fp + tc::F_BV0, true, XH1, nop);
+    if (want_head) epilogue(C_D1, cg, fp + tc::F_BA0, true, XH2, nop);
+    sync_issue([&](bool ld, int p) {
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH1, WV1, 128, 64, 4, 0u);
+      if (p == 1 && want_head) tc::gemm<false, false>(ld, tb + C_D1, XH2, WA1, 128, 16, 4, 0u);
+    });
+    {
+      float v[16];
+      umma::tmem_ld16(tw + C_D0 + cg, v);
+      umma::tmem_ld_wait();
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) part = fmaf(fp[tc::F_WV2 + cg + j], fmaxf(v[j] + fp[tc::F_BV1 + cg + j], 0.f), part);
+      vpart[g * ENVS + m] = part;
+    }
+    if (want_head && g0) {
+      float a2[16];
+      umma::tmem_ld16(tw + C_D1, a2);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a2[j] += fp[tc::F_BA1 + j];
+      // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261)
+#pragma unroll
+      for (int o2 = 0; o2 < LRX_MAX_NOUT; ++o2) {
+        float s = fp[tc::F_BMAP + o2];
+        if (o2 < a.n_out) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s = fmaf(fp[tc::F_WMAP + o2 * 16 + i], a2[i], s);
+        }
+        head[o2] = s;
+      }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    return (((fp[tc::F_BV2] + vpart[m]) + vpart[ENVS + m]) + vpart[2 * ENVS + m]) + vpart[3 * ENVS + m];
+  };
+
+  // ------------------------------------------------------------------ env state (column group 0)
+  const int N = a.N, T = a.T;
+  const int n = blockIdx.x * ENVS + m;
+  const bool live = g0 && n < N;
+  const int nl = n < N ? n : N - 1;
+  E env;
+  env.load(a.env);
+  float y[SD], t = 0.f;
+  int sc = 0;
+#pragma unroll
+  for (int i = 0; i < SD; ++i) y[i] = 0.f;
+  if (g0) {
+#pragma unroll
+    for (int i = 0; i < SD; ++i) y[i] = a.st.y[(size_t)i * N + nl];
+    t = a.st.t[nl];
+    sc = a.st.step_count[nl];
+  }
+  float scale = 1.f, log_scale = 0.f;
+  if (BOX) {
+    const float log_std = __ldg(a.params + a.lo.log_std);
+    scale = expf(log_std);     // actor.py:68-72: Normal(loc, exp(log_std))
+    log_scale = logf(scale);   // distreqx takes log(scale)
+  }
+  const LrxRolloutOut& out = a.out;
+  const LrxReplay& rp = a.rp;
+  const LrxRng& rng = a.rng;
+  const int n_out = a.n_out;
+
+  for (int s = 0; s < T; ++s) {
+    const size_t row = (size_t)s * N + nl;
+    if (out.y_trace && live) {
+#pragma unroll
+      for (int i = 0; i < SD; ++i) out.y_trace[((size_t)s * SD + i) * N + n] = y[i];
+    }
+    if (out.t_trace && live) out.t_trace[row] = t;
+
+    // ---- observation of the PRE-transition state, policy.action_and_value (mlp.py:133-152)
+    float o[OD];
+    env.observe(y, o);
+    const float value = forward(o, true);
+
+    EnvAction act;
+    act.i = 0; act.f = 0.f;
+    float logp = 0.f, r = 0.f;
+    float y1[SD], t1 = 0.f;
+    int sc1 = 0;
+    bool done = false, trunc = false;
+    if (g0) {
+      if (BOX) {
+        const float loc = head[0];
+        float eps;
+        if (rp.action_noise) {
+          eps = rp.action_noise[row];
+        } else {
+          Philox4 w = lrx_noise_words(rng, n, s, LRX_STREAM_ACTION);
+          float u1 = lrx_u32_to_unit(w.x), u2 = lrx_u32_to_unit(w.y);
+          eps = sqrtf(-2.0f * logf(u1)) * cosf(6.28318530717958647692f * u2);
+        }
+        const float a_raw = loc + scale * eps;
+        logp = normal_log_prob(loc, scale, log_scale, a_raw);  // log-prob of the UNCLIPPED sample
+        act.f = lrx_clipf(a_raw, -env.c[1], env.c[1]);         // ppo.py:228-235 (Box bounds = +-max_torque)
+      } else {
+        float z[LRX_MAX_NOUT];
+#pragma unroll
+        for (int j = 0; j < LRX_MAX_NOUT; ++j) z[j] = (j < n_out) ? head[j] : 0.f;
+        log_softmax_n<LRX_MAX_NOUT>(z, n_out);
+        Philox4 w{0u, 0u, 0u, 0u};
+        if (!rp.action_noise) w = lrx_noise_words(rng, n, s, LRX_STREAM_ACTION);
+        uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        float best = -INFINITY;
+        int bi = 0;
+#pragma unroll
+        for (int j = 0; j < LRX_MAX_NOUT; ++j) {
+          if (j < n_out) {
+            float gm;
+            if (rp.action_noise) {
+              gm = rp.action_noise[row * n_out + j];
+            } else {
+              if (j >= 4 && (j & 3) == 0) {
+                Philox4 w2 = philox4x32_10(rng.env_offset + n, rng.step_offset + s, LRX_STREAM_ACTION,
+                                           (uint32_t)(j >> 2), (uint32_t)rng.seed, (uint32_t)(rng.seed >> 32));
+                ww[0] = w2.x; ww[1] = w2.y; ww[2] = w2.z; ww[3] = w2.w;
+              }
+              gm = -logf(-logf(lrx_u32_to_unit(ww[j & 3])));
+            }
+            const float v = z[j] + gm;
+            if (v > best) { best = v; bi = j; }  // first maximum wins (jnp.argmax)
+          }
+        }
+        act.i = bi;
+#pragma unroll
+        for (int j = 0; j < LRX_MAX_NOUT; ++j) if (j == bi) logp = z[j];
+      }
+
+      // ---- env.transition / reward / terminal / truncate (ppo.py:237-246)
+      env.transition(y, t, act, y1, t1);
+      sc1 = sc + 1;
+      r = env.reward(act, y1);
+      const bool term = env.terminal(y1);
+      trunc = env.truncate(sc1);
+      done = term || trunc;
+    }
+    // ppo.py:248-259: r += gamma * V(obs(next_state)) with the PRE-reset next state; the value path
+    // runs for the whole tile, only on steps where some env of the CTA truncates
+    if (__syncthreads_or(live && trunc)) {
+      float o1[OD];
+#pragma unroll
+      for (int k = 0; k < OD; ++k) o1[k] = 0.f;
+      if (g0) env.observe(y1, o1);
+      const float vn = forward(o1, false);
+      if (trunc) r = r + a.gamma * vn;
+    }
+    if (g0) {
+      if (out.y_next_trace && live) {
+#pragma unroll
+        for (int i = 0; i < SD; ++i) out.y_next_trace[((size_t)s * SD + i) * N + n] = y1[i];
+      }
+      // ---- emit the buffer row (ppo.py:276-288)
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < OD; ++k) out.obs[row * OD + k] = o[k];
+        if (BOX) ((float*)out.act)[row] = act.f; else ((int32_t*)out.act)[row] = act.i;
+        out.rew[row] = r;
+        out.done[row] = done ? 1 : 0;
+        out.logp[row] = logp;
+        out.val[row] = value;
+      }
+      // ---- reset-on-done (ppo.py:261-263): env.initial(fresh noise), t = 0, step_count = 0
+      if (done) {
+        float u[SD];
+        if (rp.reset_uniform) {
+#pragma unroll
+          for (int i = 0; i < SD; ++i) u[i] = rp.reset_uniform[row * SD + i];
+        } else {
+          Philox4 w = lrx_noise_words(rng, n, s, LRX_STREAM_RESET);
+          uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int i = 0; i < SD; ++i) u[i] = lrx_u32_to_unit(ww[i]);
+        }
+        env.initial(u, y);
+        t = 0.f;
+        sc = 0;
+      } else {
+#pragma unroll
+        for (int i = 0; i < SD; ++i) y[i] = y1[i];
+        t = t1;
+        sc = sc1;
+      }
+    }
+  }
+
+  // ---- last_value = V(obs(final state)) (ppo.py:311-312)
+  {
+    float o[OD];
+    env.observe(y, o);
+    const float lv = forward(o, false);
+    if (live) {
+      out.last_value[n] = lv;
+#pragma unroll
+      for (int i = 0; i < SD; ++i) a.st.y[(size_t)i * N + n] = y[i];
+      a.st.t[n] = t;
+      a.st.step_count[n] = sc;
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tb, TMEM_COLS);
+}
+
+template <int KIND>
+int launch_tc(const RolloutArgs& a, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    LRX_CUDA_CHECK(cudaFuncSetAttribute(rollout_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  rollout_tc_kernel<KIND><<<(a.N + ENVS - 1) / ENVS, THREADS, SMEM_BYTES, stream>>>(a);
+  return LRX_OK;
+}
+
+int fast_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LRX_DISABLE_FUSED");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
+}  // namespace
 
 int lrx_rollout_fast(const LrxEnvDesc* env, const LrxPolicyDesc* pol, const float* params,
                      LrxEnvState state, LrxRng rng, const LrxReplay* replay, LrxRolloutOut out,
                      int32_t N, int32_t T, float gamma, cudaStream_t stream, bool* handled) {
   *handled = false;
+  if (!tc::is_default_policy(*pol) || fast_disabled()) return LRX_OK;
+  RolloutArgs a{};
+  a.env = *env;
+  a.params = params;
+  a.st = state;
+  a.rng = rng;
+  a.rp = *replay;
+  a.out = out;
+  a.N = N;
+  a.T = T;
+  a.gamma = gamma;
+  a.n_out = pol->n_out;
+  a.lo = tc::layer_offsets(*pol);
+  int rc;
+  switch (env->kind) {
+    case LRX_ENV_CARTPOLE: rc = launch_tc<LRX_ENV_CARTPOLE>(a, stream); break;
+    case LRX_ENV_PENDULUM: rc = launch_tc<LRX_ENV_PENDULUM>(a, stream); break;
+    case LRX_ENV_ACROBOT: rc = launch_tc<LRX_ENV_ACROBOT>(a, stream); break;
+    default: return LRX_OK;
+  }
+  if (rc) return rc;
+  LRX_LAUNCH_CHECK();
+  *handled = true;
   return LRX_OK;
 }
