@@ -65,6 +65,14 @@ __device__ __forceinline__ void store8(const Mat& m, int chunk, int r, const flo
   *reinterpret_cast<uint4*>(d + 2 * m.piece_bytes) = p2;
 }
 
+__device__ __forceinline__ void store_pieces(const Mat& m, int chunk, int r, const uint4& p0, const uint4& p1,
+                                             const uint4& p2) {
+  uint8_t* d = m.ptr + (uint32_t)chunk * (m.R * 16u) + (uint32_t)r * 16u;
+  *reinterpret_cast<uint4*>(d) = p0;
+  *reinterpret_cast<uint4*>(d + m.piece_bytes) = p1;
+  *reinterpret_cast<uint4*>(d + 2 * m.piece_bytes) = p2;
+}
+
 // Descriptor halves of an operand view.  K-major view: K runs along c (2 chunks per K = 16 MMA);
 // MN-major view: K runs along r (16 rows per MMA).  Only the start-address field (low word,
 // 16-byte units) changes between pieces and K slices, so the issue loop is integer adds.

@@ -22,20 +22,12 @@
 #include "lrx_policy.cuh"
 #include "lrx_tc.cuh"
 
-// Build with -DLRX_FUSED_PROFILE to collect per-phase SM cycle counters (printed when
-// LRX_FUSED_PROF=1); the product build carries none of it.
-#ifdef LRX_FUSED_PROFILE
-#define PF_CLOCK() clock64()
-#else
-#define PF_CLOCK() 0ll
-#endif
-
 namespace {
 
 constexpr int ROWS = 64;        // rows per tile = UMMA M
-constexpr int THREADS = 512;    // 16 warps: warp w serves TMEM quadrant q = w & 3 (rows 16q..16q+15 on lanes 0-15)
-                                // and column group g = w >> 2 (16 of the 64 columns of a layer output)
-constexpr int ISSUERS = 4;      // warps 0..3 also issue the MMAs (independent GEMMs of a step in parallel)
+constexpr int WORKERS = 512;    // 16 epilogue warps: warp w serves TMEM quadrant q = w & 3 (rows 16q..16q+15 on lanes
+                                // 0-15) and column group g = w >> 2 (16 of the 64 columns of a layer output)
+constexpr int THREADS = WORKERS + 32;  // + warp 16: issues every tcgen05.mma (converged, one elected lane)
 
 // ---- shared memory map (bytes).  Matrices: piece stride = R * C * 2.
 constexpr uint32_t PS16 = ROWS * 16 * 2;  // [64][16] piece
@@ -60,7 +52,7 @@ constexpr uint32_t OFF_DY8 = OFF_DY16 + 3 * PS16;      // [64][8]  dvalue / dlog
 constexpr uint32_t OFF_ONES = OFF_DY8 + 3 * PS8;       // [64][8]  all ones (one piece)
 constexpr uint32_t OFF_F32 = OFF_ONES + PS8;           // fp32 biases etc. (tc::F_COUNT floats)
 constexpr uint32_t OFF_VPART = OFF_F32 + 640 * 4;      // [4 column groups][64 rows] partial value dot products
-constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ROWS * 4;  // mbarrier, TMEM slot
+constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ROWS * 4;  // 2 mbarriers, TMEM slot
 constexpr uint32_t SMEM_BYTES = OFF_MISC + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "fused update kernel exceeds shared memory");
 static_assert(tc::F_COUNT <= 640, "fp32 parameter block too small");
@@ -98,7 +90,6 @@ struct FusedArgs {
   int n_tiles;
   int obs_dim, n_out, is_box;
   tc::LayerOffsets lo;
-  long long* prof;  // debug (LRX_FUSED_PROF=1): per-phase SM cycles of CTA 0, else NULL
 };
 
 __device__ __forceinline__ void tie_weights_f(float a, float b, float& wa, float& wb) {
@@ -112,14 +103,16 @@ __device__ __forceinline__ float clip_grad_f(float x, float lo, float hi) {
 __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
-  const int q = warp & 3, g = warp >> 2;
-  const bool active = lane < 16;
+  const bool worker = warp < WORKERS / 32;  // warp-uniform
+  const int q = warp & 3, g = worker ? (warp >> 2) : 0;
+  const bool active = worker && lane < 16;
   const int m = q * 16 + (lane & 15);  // row of the tile owned by this thread (when active)
-  const bool g0 = (g == 0);
+  const bool g0 = worker && (g == 0);
   float* fp = reinterpret_cast<float*>(smem + OFF_F32);
   float* vpart = reinterpret_cast<float*>(smem + OFF_VPART);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_MISC);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 8);
+  uint64_t* barA = reinterpret_cast<uint64_t*>(smem + OFF_MISC);      // critical GEMM(s) of a step done
+  uint64_t* barB = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 8);  // background GEMMs of a step done
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 16);
 
   const tc::Mat W0{smem + OFF_W0, 64, PS16}, W1{smem + OFF_W1, 64, PS64}, W2{smem + OFF_W2, 16, PS16};
   const tc::Mat WV0{smem + OFF_WV0, 64, PS16}, WV1{smem + OFF_WV1, 64, PS64};
@@ -145,7 +138,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   for (int i = tid; i < (int)(3 * PS64 / 16); i += THREADS)
     reinterpret_cast<uint4*>(smem + OFF_XB2)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    umma::mbar_init(bar, ISSUERS);
+    umma::mbar_init(barA, 1);
+    umma::mbar_init(barB, 1);
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc(tslot, TMEM_COLS);
@@ -155,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   umma::tc_fence_after();
   const uint32_t tb = *tslot;
   const uint32_t tw = umma::tmem_addr(tb, q * 32, 0);  // this warp's quadrant
-  {
+  if (worker) {
     float z[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) z[i] = 0.f;
@@ -163,50 +157,51 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     umma::tmem_st_wait();
   }
 
-  uint32_t phase = 0;
-  // Make this thread's shared-memory writes visible to the tensor core, let the issuing warps
-  // (converged, one elected lane each) enqueue their share of the step's MMAs, and wait for all
-  // of them.  issue(leader, part) with part = 0..ISSUERS-1.
-  long long pf_epi = 0, pf_sync = 0, pf_issue = 0, pf_wait = 0, pf_last = PF_CLOCK();
-  long long pf_ld = 0, pf_st = 0, pf_fence = 0;
-  auto sync_issue = [&](auto&& issue) {
-    const long long t_a = PF_CLOCK();
-    umma::fence_async_smem();
-    umma::tc_fence_before();
-    const long long t_f = PF_CLOCK();
-    pf_fence += t_f - t_a;
-    __syncthreads();
-    const long long t_b = PF_CLOCK();
-    if (warp < ISSUERS) {
+  // One step = the epilogue warps publish their shared-memory operands, the issuer warp enqueues the
+  // step's CRITICAL GEMM(s) (the result the next epilogue consumes) and commits barA, then the
+  // BACKGROUND GEMMs (weight / bias gradients accumulating in TMEM) and commits barB.  An epilogue
+  // waits for barA, does its TMEM load and arithmetic while the background GEMMs run, and waits
+  // for barB only before overwriting a buffer they read.  Every phase of both barriers is consumed
+  // before the next step's barrier, so a waiter is never more than one phase behind.
+  uint32_t phA = 0, phB = 0;
+  bool pendA = false, pendB = false;
+  auto wait_crit = [&]() {
+    if (pendA) {
+      umma::mbar_wait(barA, phA);
+      phA ^= 1u;
+      pendA = false;
       umma::tc_fence_after();
-      const bool leader = umma::elect_one();
-      issue(leader, warp);
-      if (leader) umma::mma_commit(bar);
-      __syncwarp();
-    }
-    const long long t_c = PF_CLOCK();
-    umma::mbar_wait(bar, phase);
-    phase ^= 1u;
-    umma::tc_fence_after();
-    const long long t_d = PF_CLOCK();
-    pf_epi += t_a - pf_last;
-    pf_sync += t_b - t_a;
-    pf_issue += t_c - t_b;
-    pf_wait += t_d - t_c;
-    pf_last = t_d;
-  };
-
-  auto issue_nowait = [&](auto&& issue) {
-    umma::fence_async_smem();
-    umma::tc_fence_before();
-    __syncthreads();
-    if (warp < ISSUERS) {
-      umma::tc_fence_after();
-      const bool leader = umma::elect_one();
-      issue(leader, warp);
-      __syncwarp();
     }
   };
+  auto wait_bg = [&]() {
+    if (pendB) {
+      umma::mbar_wait(barB, phB);
+      phB ^= 1u;
+      pendB = false;
+      umma::tc_fence_after();
+    }
+  };
+  auto step = [&](auto&& crit, auto&& bg) {
+    if (worker) {
+      wait_crit();
+      wait_bg();
+      umma::fence_async_smem();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (!worker) {
+      umma::tc_fence_after();
+      const bool leader = umma::elect_one();
+      crit(leader);
+      if (leader) umma::mma_commit(barA);
+      bg(leader);
+      if (leader) umma::mma_commit(barB);
+      __syncwarp();
+    } else {
+      pendA = pendB = true;
+    }
+  };
+  auto none = [](bool) {};
 
   const LrxPpoHyper h = a.h;
   const float invB = (float)(1.0 / a.B_global);
@@ -227,15 +222,14 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   double s_kl = 0, s_pol = 0, s_val = 0, s_ent = 0, s_dls = 0, s_bad = 0;
 
   // This thread's 16 columns [c0, c0+16) of a layer output in TMEM -> + bias -> optional ReLU (mask
-  // recorded) -> operand X.  fn(v) sees the 16 activated values.
+  // recorded) -> operand X.  fn(v) sees the 16 activated values.  need_bg: the destination is still
+  // read by this step's background GEMMs.
   auto epilogue_fwd = [&](uint32_t col, int c0, const float* bias, bool relu, const tc::Mat& dst, uint32_t& mask,
-                          auto&& fn) {
+                          bool need_bg, auto&& fn) {
+    wait_crit();
     float v[16];
-    const long long t0 = PF_CLOCK();
     umma::tmem_ld16(tw + col + c0, v);
     umma::tmem_ld_wait();
-    const long long t1 = PF_CLOCK();
-    pf_ld += t1 - t0;
     mask = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -246,15 +240,18 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       }
     }
     fn(v);
-    const long long t2 = PF_CLOCK();
+    uint4 p[6];
+    tc::split8(v, p[0], p[1], p[2]);
+    tc::split8(v + 8, p[3], p[4], p[5]);
+    if (need_bg) wait_bg();
     if (active) {
-      tc::store8(dst, (c0 >> 3), m, v);
-      tc::store8(dst, (c0 >> 3) + 1, m, v + 8);
+      tc::store_pieces(dst, (c0 >> 3), m, p[0], p[1], p[2]);
+      tc::store_pieces(dst, (c0 >> 3) + 1, m, p[3], p[4], p[5]);
     }
-    pf_st += PF_CLOCK() - t2;
   };
   // dX columns [c0, c0+16) masked by the ReLU of the layer that produced X -> operand dY.
-  auto epilogue_bwd = [&](uint32_t col, int c0, uint32_t mask, bool use_mask, const tc::Mat& dst) {
+  auto epilogue_bwd = [&](uint32_t col, int c0, uint32_t mask, bool use_mask, const tc::Mat& dst, bool need_bg) {
+    wait_crit();
     float v[16];
     umma::tmem_ld16(tw + col + c0, v);
     umma::tmem_ld_wait();
@@ -262,9 +259,13 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = ((mask >> j) & 1u) ? v[j] : 0.f;
     }
+    uint4 p[6];
+    tc::split8(v, p[0], p[1], p[2]);
+    tc::split8(v + 8, p[3], p[4], p[5]);
+    if (need_bg) wait_bg();
     if (active) {
-      tc::store8(dst, (c0 >> 3), m, v);
-      tc::store8(dst, (c0 >> 3) + 1, m, v + 8);
+      tc::store_pieces(dst, (c0 >> 3), m, p[0], p[1], p[2]);
+      tc::store_pieces(dst, (c0 >> 3) + 1, m, p[3], p[4], p[5]);
     }
   };
   auto nop = [](float*) {};
@@ -302,42 +303,36 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       }
     }
   };
-  load_row(active ? (int)blockIdx.x : (int)(blockIdx.x + gridDim.x));
+  if (worker) load_row(lane < 16 ? (int)blockIdx.x : (int)(blockIdx.x + gridDim.x));
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    if (active && g0) {
-      float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      tc::store8(XOBS, 0, m, o);
-      tc::store8(XOBS, 1, m, z8);
+    if (g0) {
+      wait_crit();
+      wait_bg();  // the previous tile's layer-0 gradient GEMM still reads XOBS
+      if (active) {
+        float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        tc::store8(XOBS, 0, m, o);
+        tc::store8(XOBS, 1, m, z8);
+      }
     }
 
     // ---------------------------------------------------------------- encoder forward
-    uint32_t mk_h1, mk_h2, mk_b1, mk_b2, mk_none;
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XOBS, W0, 64, 64, 1, 0u);
-    });
-    epilogue_fwd(C_D0, cg, fp + tc::F_B0, true, XH1, mk_h1, nop);
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH1, W1, 64, 64, 4, 0u);
-    });
-    epilogue_fwd(C_D0, cg, fp + tc::F_B1, true, XH2, mk_h2, nop);
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH2, W2, 64, 16, 4, 0u);
-    });
-    if (g0) epilogue_fwd(C_D0, 0, fp + tc::F_B2, false, XF, mk_none, nop);
+    uint32_t mk_h1 = 0, mk_h2 = 0, mk_b1 = 0, mk_b2 = 0, mk_none = 0;
+    step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XOBS, W0, 64, 64, 1, 0u); }, none);
+    if (worker) epilogue_fwd(C_D0, cg, fp + tc::F_B0, true, XH1, mk_h1, false, nop);
+    step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH1, W1, 64, 64, 4, 0u); }, none);
+    if (worker) epilogue_fwd(C_D0, cg, fp + tc::F_B1, true, XH2, mk_h2, false, nop);
+    step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH2, W2, 64, 16, 4, 0u); }, none);
+    if (g0) epilogue_fwd(C_D0, 0, fp + tc::F_B2, false, XF, mk_none, false, nop);
 
     // ---------------------------------------------------------------- value head forward
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XF, WV0, 64, 64, 1, 0u);
-      if (p == 1) tc::gemm<false, false>(ld, tb + C_D1, XF, WA0, 64, 64, 1, 0u);  // action head layer 1, consumed later
-    });
-    epilogue_fwd(C_D0, cg, fp + tc::F_BV0, true, XB1, mk_b1, nop);
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XB1, WV1, 64, 64, 4, 0u);
-    });
-    {
+    step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XF, WV0, 64, 64, 1, 0u); },
+         [&](bool ld) { tc::gemm<false, false>(ld, tb + C_D1, XF, WA0, 64, 64, 1, 0u); });  // action head layer 1, consumed later
+    if (worker) epilogue_fwd(C_D0, cg, fp + tc::F_BV0, true, XB1, mk_b1, false, nop);
+    step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XB1, WV1, 64, 64, 4, 0u); }, none);
+    if (worker) {
       float part = 0.f;
-      epilogue_fwd(C_D0, cg, fp + tc::F_BV1, true, XB2, mk_b2, [&](float* v) {
+      epilogue_fwd(C_D0, cg, fp + tc::F_BV1, true, XB2, mk_b2, false, [&](float* v) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) part = fmaf(fp[tc::F_WV2 + cg + j], v[j], part);
       });
@@ -383,51 +378,47 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       tc::store8(DY64, (cg >> 3), m, v);
       tc::store8(DY64, (cg >> 3) + 1, m, v + 8);
     }
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, true>(ld, tb + C_D0, DY64, WV1, 64, 64, 4, 0u);            // dX = dY W
-      if (p == 1) tc::gemm<true, true>(ld, tb + C_GV1, DY64, XB1, 64, 64, 4, 1u);            // dW^T[out][in] += dY^T X
-      if (p == 2) tc::gemm<true, true>(ld, tb + C_GV2, XB2, DY8, 64, 8, 4, 1u);              // dW_v2[in] += X^T dvalue
-      if (p == 3) {
-        tc::gemm<true, true, 1, 3>(ld, tb + C_GBV2, ONES, DY8, 64, 8, 4, 1u);                // db_v2
-        tc::gemm<true, true, 3, 1>(ld, tb + C_GV1 + 64, DY64, ONES, 64, 8, 4, 1u);           // db_v1
-      }
-    });
-    epilogue_bwd(C_D0, cg, mk_b1, true, DY64);
-    // not waited for: nothing below touches DY64 / XF / C_DF / C_GV0 before the next waited step, whose
-    // commits (one per issuing warp, covering all its earlier MMAs) also cover these
-    issue_nowait([&](bool ld, int p) {
-      if (p == 1) tc::gemm<false, true>(ld, tb + C_DF, DY64, WV0, 64, 16, 4, 0u);            // d(features) from the value head
-      if (p == 2) tc::gemm<true, true>(ld, tb + C_GV0, DY64, XF, 64, 16, 4, 1u);
-      if (p == 3) tc::gemm<true, true, 3, 1>(ld, tb + C_GV0 + 16, DY64, ONES, 64, 8, 4, 1u);
+    step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, WV1, 64, 64, 4, 0u); },        // dX = dY W
+         [&](bool ld) {
+           tc::gemm<true, true>(ld, tb + C_GV1, DY64, XB1, 64, 64, 4, 1u);                        // dW^T[out][in] += dY^T X
+           tc::gemm<true, true, 3, 1>(ld, tb + C_GV1 + 64, DY64, ONES, 64, 8, 4, 1u);             // db_v1
+           tc::gemm<true, true>(ld, tb + C_GV2, XB2, DY8, 64, 8, 4, 1u);                          // dW_v2[in] += X^T dvalue
+           tc::gemm<true, true, 1, 3>(ld, tb + C_GBV2, ONES, DY8, 64, 8, 4, 1u);                  // db_v2
+         });
+    if (worker) epilogue_bwd(C_D0, cg, mk_b1, true, DY64, true);  // background GEMMs read DY64
+    // all background: d(features) from the value head and the layer-0 gradients; nothing below touches
+    // DY64 / XF / C_DF / C_GV0 before these are waited for at the next step
+    step(none, [&](bool ld) {
+      tc::gemm<false, true>(ld, tb + C_DF, DY64, WV0, 64, 16, 4, 0u);
+      tc::gemm<true, true>(ld, tb + C_GV0, DY64, XF, 64, 16, 4, 1u);
+      tc::gemm<true, true, 3, 1>(ld, tb + C_GV0 + 16, DY64, ONES, 64, 8, 4, 1u);
     });
 
     // ---------------------------------------------------------------- action head forward
-    epilogue_fwd(C_D1, cg, fp + tc::F_BA0, true, XB1, mk_b1, nop);
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XB1, WA1, 64, 16, 4, 0u);
-    });
+    if (worker) epilogue_fwd(C_D1, cg, fp + tc::F_BA0, true, XB1, mk_b1, false, nop);
+    step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XB1, WA1, 64, 16, 4, 0u); }, none);
     if (g0) {
       float a2[16];
-      epilogue_fwd(C_D0, 0, fp + tc::F_BA1, false, XA2, mk_none, [&](float* v) {
+      epilogue_fwd(C_D0, 0, fp + tc::F_BA1, false, XA2, mk_none, false, [&](float* v) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) a2[j] = v[j];
       });
       // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261) on the FMA pipe
       float head[LRX_MAX_NOUT];
 #pragma unroll
-      for (int o = 0; o < LRX_MAX_NOUT; ++o) {
-        float s = fp[tc::F_BMAP + o];
-        if (o < a.n_out) {
+      for (int o2 = 0; o2 < LRX_MAX_NOUT; ++o2) {
+        float sacc = fp[tc::F_BMAP + o2];
+        if (o2 < a.n_out) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) s = fmaf(fp[tc::F_WMAP + o * 16 + i], a2[i], s);
+          for (int i = 0; i < 16; ++i) sacc = fmaf(fp[tc::F_WMAP + o2 * 16 + i], a2[i], sacc);
         }
-        head[o] = s;
+        head[o2] = sacc;
       }
 
       // -------------------------------------------------------------- policy loss (ppo.py:405-434,452-467)
       float dhead[LRX_MAX_NOUT];
 #pragma unroll
-      for (int o = 0; o < LRX_MAX_NOUT; ++o) dhead[o] = 0.f;
+      for (int o2 = 0; o2 < LRX_MAX_NOUT; ++o2) dhead[o2] = 0.f;
       if (valid && active) {
         float logp, entropy, z_n = 0.f;
         float lp[LRX_MAX_NOUT], pr[LRX_MAX_NOUT];
@@ -483,53 +474,51 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
         float d16[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float s = 0.f;
+          float sacc = 0.f;
 #pragma unroll
-          for (int o = 0; o < LRX_MAX_NOUT; ++o)
-            if (o < a.n_out) s = fmaf(dhead[o], fp[tc::F_WMAP + o * 16 + i], s);
-          d16[i] = s;
+          for (int o2 = 0; o2 < LRX_MAX_NOUT; ++o2)
+            if (o2 < a.n_out) sacc = fmaf(dhead[o2], fp[tc::F_WMAP + o2 * 16 + i], sacc);
+          d16[i] = sacc;
         }
         tc::store8(DY16, 0, m, d16);
         tc::store8(DY16, 1, m, d16 + 8);
       }
     }
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, true>(ld, tb + C_D0, DY16, WA1, 64, 64, 1, 0u);            // dX = dY16 W_a1 (K = 16 outputs)
-      if (p == 1) tc::gemm<true, true>(ld, tb + C_GA1, XB1, DY16, 64, 16, 4, 1u);            // dW[in][out] += X^T dY
-      if (p == 2) tc::gemm<true, true>(ld, tb + C_GMAP, XA2, DY8, 64, 8, 4, 1u);             // dW_map[in (16 valid)][out]
-      if (p == 3) {
-        tc::gemm<true, true, 1, 3>(ld, tb + C_GBMAP, ONES, DY8, 64, 8, 4, 1u);
-        tc::gemm<true, true, 1, 3>(ld, tb + C_GBA1, ONES, DY16, 64, 16, 4, 1u);
-      }
-    });
-    epilogue_bwd(C_D0, cg, mk_b1, true, DY64);
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, true>(ld, tb + C_DF, DY64, WA0, 64, 16, 4, 1u);            // d(features) += action head
-      if (p == 1) tc::gemm<true, true>(ld, tb + C_GA0, DY64, XF, 64, 16, 4, 1u);
-      if (p == 2) tc::gemm<true, true, 3, 1>(ld, tb + C_GA0 + 16, DY64, ONES, 64, 8, 4, 1u);
-    });
+    step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY16, WA1, 64, 64, 1, 0u); },        // dX = dY16 W_a1 (K = 16 outputs)
+         [&](bool ld) {
+           tc::gemm<true, true>(ld, tb + C_GA1, XB1, DY16, 64, 16, 4, 1u);                        // dW[in][out] += X^T dY
+           tc::gemm<true, true, 1, 3>(ld, tb + C_GBA1, ONES, DY16, 64, 16, 4, 1u);
+           tc::gemm<true, true>(ld, tb + C_GMAP, XA2, DY8, 64, 8, 4, 1u);                         // dW_map[in (16 valid)][out]
+           tc::gemm<true, true, 1, 3>(ld, tb + C_GBMAP, ONES, DY8, 64, 8, 4, 1u);
+         });
+    if (worker) epilogue_bwd(C_D0, cg, mk_b1, true, DY64, false);  // this step's background GEMMs do not read DY64
+    step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_DF, DY64, WA0, 64, 16, 4, 1u); },        // d(features) += action head
+         [&](bool ld) {
+           tc::gemm<true, true>(ld, tb + C_GA0, DY64, XF, 64, 16, 4, 1u);
+           tc::gemm<true, true, 3, 1>(ld, tb + C_GA0 + 16, DY64, ONES, 64, 8, 4, 1u);
+         });
 
     // ---------------------------------------------------------------- encoder backward
-    if (g0) epilogue_bwd(C_DF, 0, 0, false, DY16);
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, true>(ld, tb + C_D0, DY16, W2, 64, 64, 1, 0u);
-      if (p == 1) tc::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
-      if (p == 2) tc::gemm<true, true, 1, 3>(ld, tb + C_GB2, ONES, DY16, 64, 16, 4, 1u);
-    });
-    epilogue_bwd(C_D0, cg, mk_h2, true, DY64);
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, true>(ld, tb + C_D0, DY64, W1, 64, 64, 4, 0u);
-      if (p == 1) tc::gemm<true, true>(ld, tb + C_G1, DY64, XH1, 64, 64, 4, 1u);
-      if (p == 2) tc::gemm<true, true, 3, 1>(ld, tb + C_G1 + 64, DY64, ONES, 64, 8, 4, 1u);
-    });
-    epilogue_bwd(C_D0, cg, mk_h1, true, DY64);
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<true, true>(ld, tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
-      if (p == 1) tc::gemm<true, true, 3, 1>(ld, tb + C_G0 + 16, DY64, ONES, 64, 8, 4, 1u);
+    if (g0) epilogue_bwd(C_DF, 0, 0, false, DY16, false);         // background reads DY64 / XF only
+    step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY16, W2, 64, 64, 1, 0u); },
+         [&](bool ld) {
+           tc::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
+           tc::gemm<true, true, 1, 3>(ld, tb + C_GB2, ONES, DY16, 64, 16, 4, 1u);
+         });
+    if (worker) epilogue_bwd(C_D0, cg, mk_h2, true, DY64, false);  // background reads XH2 / DY16 only
+    step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, W1, 64, 64, 4, 0u); },
+         [&](bool ld) {
+           tc::gemm<true, true>(ld, tb + C_G1, DY64, XH1, 64, 64, 4, 1u);
+           tc::gemm<true, true, 3, 1>(ld, tb + C_G1 + 64, DY64, ONES, 64, 8, 4, 1u);
+         });
+    if (worker) epilogue_bwd(C_D0, cg, mk_h1, true, DY64, true);   // background GEMMs read DY64
+    step(none, [&](bool ld) {
+      tc::gemm<true, true>(ld, tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
+      tc::gemm<true, true, 3, 1>(ld, tb + C_G0 + 16, DY64, ONES, 64, 8, 4, 1u);
     });
 
     // hand the prefetched rows down to lanes 0-15; lanes 16-31 fetch the tile after next
-    {
+    if (worker) {
       const unsigned full = 0xffffffffu;
       const float s_actf = __shfl_down_sync(full, act_f, 16), s_lp = __shfl_down_sync(full, logp_old, 16);
       const float s_A = __shfl_down_sync(full, A, 16), s_ret = __shfl_down_sync(full, ret, 16);
@@ -548,11 +537,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       }
     }
   }
-
-  if (a.prof && blockIdx.x == 0 && (tid == 0 || tid == 128)) {
-    long long* o = a.prof + (tid ? 8 : 0);
-    o[0] = pf_epi; o[1] = pf_sync; o[2] = pf_issue; o[3] = pf_wait; o[4] = pf_ld; o[5] = pf_st; o[6] = pf_fence; o[7] = 0;
+  if (worker) {
+    wait_crit();
+    wait_bg();
   }
+
   // ------------------------------------------------------------------ flush the gradient partial
   float* part = a.partial + (size_t)blockIdx.x * a.partial_stride;
   const tc::LayerOffsets& lo = a.lo;
@@ -592,10 +581,12 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     }
   };
   // nine layers over the four column groups of warps
+  umma::tc_fence_after();
+  if (!worker) { /* issuer warp: nothing to flush */ } else
   if (g == 0) { flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0); flush_N(C_G2, C_GB2, 64, 16, 16, tc::L_ENC2); flush_N(C_GMAP, C_GBMAP, 16, a.n_out, 8, tc::L_MAP); }
-  if (g == 1) { flush_T(C_G1, 64, 64, tc::L_ENC1); flush_N(C_GV2, C_GBV2, 64, 1, 8, tc::L_V2); }
-  if (g == 2) { flush_T(C_GV1, 64, 64, tc::L_V1); flush_T(C_GV0, 16, 16, tc::L_V0); }
-  if (g == 3) { flush_T(C_GA0, 16, 16, tc::L_A0); flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1); }
+  if (worker && g == 1) { flush_T(C_G1, 64, 64, tc::L_ENC1); flush_N(C_GV2, C_GBV2, 64, 1, 8, tc::L_V2); }
+  if (worker && g == 2) { flush_T(C_GV1, 64, 64, tc::L_V1); flush_T(C_GV0, 16, 16, tc::L_V0); }
+  if (worker && g == 3) { flush_T(C_GA0, 16, 16, tc::L_A0); flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1); }
 
   // ------------------------------------------------------------------ loss statistics (fixed order)
   __syncthreads();
@@ -684,14 +675,6 @@ int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxB
   a.is_box = pol->is_box;
   a.lo = tc::layer_offsets(*pol);
   const int grid = a.n_tiles < LRX_NUM_SMS ? a.n_tiles : LRX_NUM_SMS;
-  static long long* prof_dev = nullptr;
-  static int prof_left = -1;
-  if (prof_left < 0) {
-    const char* e = getenv("LRX_FUSED_PROF");
-    prof_left = (e && e[0] == '1') ? 3 : 0;
-    if (prof_left) cudaMalloc(&prof_dev, 16 * sizeof(long long));
-  }
-  a.prof = prof_left > 0 ? prof_dev : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -702,17 +685,6 @@ int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxB
   lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid, a.lo.log_std,
                              h->entropy_loss_coefficient, (double)B_global, gradbuf, stream);
   LRX_LAUNCH_CHECK();
-  if (a.prof) {
-    long long hp[16];
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost);
-    const int tiles0 = (a.n_tiles + grid - 1) / grid;
-    for (int w = 0; w < 2; ++w)
-      fprintf(stderr, "[fused prof] tiles/CTA %d; cycles/tile warp%d: between-steps %lld (tmem-ld %lld, split+store %lld) fence %lld barrier %lld issue %lld mma-wait %lld\n",
-              tiles0, w * 4, hp[8 * w + 0] / tiles0, hp[8 * w + 4] / tiles0, hp[8 * w + 5] / tiles0, hp[8 * w + 6] / tiles0,
-              (hp[8 * w + 1] - hp[8 * w + 6]) / tiles0, hp[8 * w + 2] / tiles0, hp[8 * w + 3] / tiles0);
-    --prof_left;
-  }
   *handled = true;
   return LRX_OK;
 }
