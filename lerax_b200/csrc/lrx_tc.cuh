@@ -73,6 +73,21 @@ __device__ __forceinline__ void store_pieces(const Mat& m, int chunk, int r, con
   *reinterpret_cast<uint4*>(d + 2 * m.piece_bytes) = p2;
 }
 
+// Two adjacent columns (c, c+1; c even) of one row as the three piece words.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+  const float ra = a - trunc_bf16(a), rb = b - trunc_bf16(b);
+  const float sa = ra - trunc_bf16(ra), sb = rb - trunc_bf16(rb);
+  w0 = pack_hi16(a, b);
+  w1 = pack_hi16(ra, rb);
+  w2 = pack_hi16(sa, sb);
+}
+__device__ __forceinline__ void store2(const Mat& m, int r, int c, uint32_t w0, uint32_t w1, uint32_t w2) {
+  uint8_t* d = m.ptr + (uint32_t)(c >> 3) * (m.R * 16u) + (uint32_t)r * 16u + (uint32_t)(c & 7) * 2u;
+  *reinterpret_cast<uint32_t*>(d) = w0;
+  *reinterpret_cast<uint32_t*>(d + m.piece_bytes) = w1;
+  *reinterpret_cast<uint32_t*>(d + 2 * m.piece_bytes) = w2;
+}
+
 // Descriptor halves of an operand view.  K-major view: K runs along c (2 chunks per K = 16 MMA);
 // MN-major view: K runs along r (16 rows per MMA).  Only the start-address field (low word,
 // 16-byte units) changes between pieces and K slices, so the issue loop is integer adds.

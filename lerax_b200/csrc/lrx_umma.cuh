@@ -112,6 +112,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// tcgen05.ld 16x256b.x2: 16 TMEM lanes x 16 columns spread over all 32 threads (measured with
+// tools/tmem_shape_probe.py): thread t holds lanes r0 = t/4 and r1 = r0 + 8, columns c = 2*(t%4):
+//   v[0],v[1] = (r0, c), (r0, c+1)   v[2],v[3] = (r1, c), (r1, c+1)
+//   v[4],v[5] = (r0, c+8), (r0, c+9) v[6],v[7] = (r1, c+8), (r1, c+9)
+__device__ __forceinline__ void tmem_ld_frag16(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }

@@ -400,3 +400,40 @@ extern "C" int lrx_debug_umma_rate(int32_t M, int32_t N, int32_t dsplit, long lo
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }
+
+// ------------------------------------------------------------------ tcgen05.ld fragment-shape probe
+// TMEM[lane][col] = lane * 100 + col (written 32x32b), read back with the 16x256b.x2 shape: dump[t][r]
+// = register r of thread t, which decodes the (lane, column) each thread receives.
+__global__ void __launch_bounds__(128) tmem_shape_probe_kernel(float* __restrict__ dump) {
+  __shared__ uint32_t tmem_slot;
+  const int warp = umma::warp_idx_sync(), lane = threadIdx.x & 31;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 32);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  float v[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) v[c] = (float)((warp * 32 + lane) * 100 + c);
+  umma::tmem_st16(umma::tmem_addr(tb, warp * 32, 0), v);
+  umma::tmem_st_wait();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(umma::tmem_addr(tb, warp * 32, 0)));
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dump[threadIdx.x * 8 + i] = __uint_as_float(r[i]);
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tb, 32);
+}
+extern "C" int lrx_debug_tmem_shape_probe(float* dump, lrx_stream_t stream) {
+  LRX_REQUIRE(dump, LRX_ERR_INVALID_ARG, "lrx_debug_tmem_shape_probe: NULL pointer");
+  tmem_shape_probe_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(dump);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}

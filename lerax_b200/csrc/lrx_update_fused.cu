@@ -271,6 +271,53 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   auto nop = [](float*) {};
   const int cg = g * 16;  // first column of this thread's group in a 64-wide layer
 
+  // 64-wide layers use the 16x256b TMEM load shape so that ALL 32 lanes of the warp hold a fragment of
+  // the quadrant's 16 rows x this group's 16 columns: rows fr, fr+8 and column pairs fc, fc+8.
+  const int fr0 = q * 16 + (lane >> 2), fr1 = fr0 + 8;  // tile rows of this thread's fragment
+  const int fc = cg + (lane & 3) * 2;                   // columns fc, fc+1, fc+8, fc+9
+  // fragment order: v[0,1] = (fr0, fc..), v[2,3] = (fr1, fc..), v[4,5] = (fr0, fc+8..), v[6,7] = (fr1, fc+8..)
+  auto frag_store = [&](const tc::Mat& dst, const float* v, bool need_bg) {
+    uint32_t w[12];
+    tc::split2(v[0], v[1], w[0], w[1], w[2]);
+    tc::split2(v[2], v[3], w[3], w[4], w[5]);
+    tc::split2(v[4], v[5], w[6], w[7], w[8]);
+    tc::split2(v[6], v[7], w[9], w[10], w[11]);
+    if (need_bg) wait_bg();
+    tc::store2(dst, fr0, fc, w[0], w[1], w[2]);
+    tc::store2(dst, fr1, fc, w[3], w[4], w[5]);
+    tc::store2(dst, fr0, fc + 8, w[6], w[7], w[8]);
+    tc::store2(dst, fr1, fc + 8, w[9], w[10], w[11]);
+  };
+  // layer output -> + bias -> ReLU (8-bit mask recorded) -> operand X; fn(v) sees the fragment
+  auto frag_fwd = [&](uint32_t col, const float* bias, const tc::Mat& dst, uint32_t& mask, auto&& fn) {
+    wait_crit();
+    float v[8];
+    umma::tmem_ld_frag16(tw + col + cg, v);
+    umma::tmem_ld_wait();
+    const float2 b0 = *reinterpret_cast<const float2*>(bias + fc), b1 = *reinterpret_cast<const float2*>(bias + fc + 8);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.x; v[3] += b0.y;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.x; v[7] += b1.y;
+    mask = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (v[j] > 0.f) mask |= (1u << j);
+      v[j] = fmaxf(v[j], 0.f);
+    }
+    fn(v);
+    frag_store(dst, v, false);
+  };
+  // dX fragment masked by the ReLU of the layer that produced X -> operand dY
+  auto frag_bwd = [&](uint32_t col, uint32_t mask, const tc::Mat& dst, bool need_bg) {
+    wait_crit();
+    float v[8];
+    umma::tmem_ld_frag16(tw + col + cg, v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ((mask >> j) & 1u) ? v[j] : 0.f;
+    frag_store(dst, v, need_bg);
+  };
+  auto nopf = [](float*) {};
+
   // Row data of a tile (gather of base_buffer.py:90-103).  Lanes 0-15 own the rows of the CURRENT
   // tile; the otherwise idle lanes 16-31 load the same rows of the NEXT tile of this CTA a whole tile
   // ahead and hand them down by shuffle, so the two dependent global loads are never waited for.
@@ -319,41 +366,52 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     // ---------------------------------------------------------------- encoder forward
     uint32_t mk_h1 = 0, mk_h2 = 0, mk_b1 = 0, mk_b2 = 0, mk_none = 0;
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XOBS, W0, 64, 64, 1, 0u); }, none);
-    if (worker) epilogue_fwd(C_D0, cg, fp + tc::F_B0, true, XH1, mk_h1, false, nop);
+    if (worker) frag_fwd(C_D0, fp + tc::F_B0, XH1, mk_h1, nopf);
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH1, W1, 64, 64, 4, 0u); }, none);
-    if (worker) epilogue_fwd(C_D0, cg, fp + tc::F_B1, true, XH2, mk_h2, false, nop);
+    if (worker) frag_fwd(C_D0, fp + tc::F_B1, XH2, mk_h2, nopf);
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH2, W2, 64, 16, 4, 0u); }, none);
     if (g0) epilogue_fwd(C_D0, 0, fp + tc::F_B2, false, XF, mk_none, false, nop);
 
     // ---------------------------------------------------------------- value head forward
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XF, WV0, 64, 64, 1, 0u); },
          [&](bool ld) { tc::gemm<false, false>(ld, tb + C_D1, XF, WA0, 64, 64, 1, 0u); });  // action head layer 1, consumed later
-    if (worker) epilogue_fwd(C_D0, cg, fp + tc::F_BV0, true, XB1, mk_b1, false, nop);
+    if (worker) frag_fwd(C_D0, fp + tc::F_BV0, XB1, mk_b1, nopf);
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XB1, WV1, 64, 64, 4, 0u); }, none);
     if (worker) {
-      float part = 0.f;
-      epilogue_fwd(C_D0, cg, fp + tc::F_BV1, true, XB2, mk_b2, false, [&](float* v) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) part = fmaf(fp[tc::F_WV2 + cg + j], v[j], part);
+      float pr0 = 0.f, pr1 = 0.f;  // partial value-head dot products of rows fr0, fr1 over this thread's 4 columns
+      frag_fwd(C_D0, fp + tc::F_BV1, XB2, mk_b2, [&](float* v) {
+        const float2 w0 = *reinterpret_cast<const float2*>(fp + tc::F_WV2 + fc);
+        const float2 w1 = *reinterpret_cast<const float2*>(fp + tc::F_WV2 + fc + 8);
+        pr0 = fmaf(w1.y, v[5], fmaf(w1.x, v[4], fmaf(w0.y, v[1], w0.x * v[0])));
+        pr1 = fmaf(w1.y, v[7], fmaf(w1.x, v[6], fmaf(w0.y, v[3], w0.x * v[2])));
       });
-      if (active) vpart[g * ROWS + m] = part;
+      pr0 += __shfl_xor_sync(0xffffffffu, pr0, 1);
+      pr1 += __shfl_xor_sync(0xffffffffu, pr1, 1);
+      pr0 += __shfl_xor_sync(0xffffffffu, pr0, 2);
+      pr1 += __shfl_xor_sync(0xffffffffu, pr1, 2);
+      if ((lane & 3) == 0) {
+        vpart[g * ROWS + fr0] = pr0;
+        vpart[g * ROWS + fr1] = pr1;
+      }
     }
     __syncthreads();
-    const float value = active ? (((fp[tc::F_BV2] + vpart[m]) + vpart[ROWS + m]) + vpart[2 * ROWS + m]) + vpart[3 * ROWS + m]
-                               : 0.f;
+    auto value_of = [&](int row) {
+      return (((fp[tc::F_BV2] + vpart[row]) + vpart[ROWS + row]) + vpart[2 * ROWS + row]) + vpart[3 * ROWS + row];
+    };
+    const float value = active ? value_of(m) : 0.f;
 
     // ---------------------------------------------------------------- value loss (ppo.py:435-451)
-    float dvalue = 0.f;
-    bool bad = false;
-    if (valid && active) {
-      bad = !isfinite(value);
+    // d loss / d value of one row (0 for rows past the minibatch) and its squared-error statistic
+    auto value_grad = [&](float val, float ret_r, float vold_r, bool valid_r, float& sv) -> float {
+      sv = 0.f;
+      if (!valid_r) return 0.f;
       const float c = h.clip_coefficient;
-      const float e1 = value - ret;
-      float dvl, sv;
+      const float e1 = val - ret_r;
+      float dvl;
       if (h.clip_value_loss) {
-        const float dv = value - val_old;
-        const float clipped = val_old + lrx_clipf(dv, -c, c);
-        const float e2 = clipped - ret;
+        const float dv = val - vold_r;
+        const float clipped = vold_r + lrx_clipf(dv, -c, c);
+        const float e2 = clipped - ret_r;
         const float q1 = e1 * e1, q2 = e2 * e2;
         sv = fminf(q1, q2);
         float u1, u2;
@@ -363,20 +421,35 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
         sv = e1 * e1;
         dvl = invB * e1;
       }
-      if (g0) s_val += (double)sv;
-      dvalue = h.value_loss_coefficient * dvl;
-    }
-    // ---------------------------------------------------------------- value head backward
-    if (active) {
-      if (g0) {
+      return h.value_loss_coefficient * dvl;
+    };
+    bool bad = false;
+    if (worker) {
+      // the row scalars live in lanes 0-15 (lane = row of the quadrant); fragment rows fetch them by shuffle
+      const int l0 = lane >> 2, l1 = l0 + 8;
+      const float ret0 = __shfl_sync(0xffffffffu, ret, l0), ret1 = __shfl_sync(0xffffffffu, ret, l1);
+      const float vo0 = __shfl_sync(0xffffffffu, val_old, l0), vo1 = __shfl_sync(0xffffffffu, val_old, l1);
+      const bool va0 = __shfl_sync(0xffffffffu, (int)valid, l0) != 0, va1 = __shfl_sync(0xffffffffu, (int)valid, l1) != 0;
+      float sv_unused;
+      const float dv0 = value_grad(value_of(fr0), ret0, vo0, va0, sv_unused);
+      const float dv1 = value_grad(value_of(fr1), ret1, vo1, va1, sv_unused);
+      // ---------------------------------------------------------------- value head backward (64 -> 1 on the FMA pipe)
+      const float2 w0 = *reinterpret_cast<const float2*>(fp + tc::F_WV2 + fc);
+      const float2 w1 = *reinterpret_cast<const float2*>(fp + tc::F_WV2 + fc + 8);
+      float v[8] = {dv0 * w0.x, dv0 * w0.y, dv1 * w0.x, dv1 * w0.y, dv0 * w1.x, dv0 * w1.y, dv1 * w1.x, dv1 * w1.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ((mk_b2 >> j) & 1u) ? v[j] : 0.f;
+      frag_store(DY64, v, false);
+      if (g0 && active) {
+        float sv;
+        const float dvalue = value_grad(value, ret, val_old, valid, sv);
+        if (valid) {
+          bad = !isfinite(value);
+          s_val += (double)sv;
+        }
         float d8[8] = {dvalue, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         tc::store8(DY8, 0, m, d8);
       }
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = ((mk_b2 >> j) & 1u) ? dvalue * fp[tc::F_WV2 + cg + j] : 0.f;
-      tc::store8(DY64, (cg >> 3), m, v);
-      tc::store8(DY64, (cg >> 3) + 1, m, v + 8);
     }
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, WV1, 64, 64, 4, 0u); },        // dX = dY W
          [&](bool ld) {
@@ -385,7 +458,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
            tc::gemm<true, true>(ld, tb + C_GV2, XB2, DY8, 64, 8, 4, 1u);                          // dW_v2[in] += X^T dvalue
            tc::gemm<true, true, 1, 3>(ld, tb + C_GBV2, ONES, DY8, 64, 8, 4, 1u);                  // db_v2
          });
-    if (worker) epilogue_bwd(C_D0, cg, mk_b1, true, DY64, true);  // background GEMMs read DY64
+    if (worker) frag_bwd(C_D0, mk_b1, DY64, true);  // background GEMMs read DY64
     // all background: d(features) from the value head and the layer-0 gradients; nothing below touches
     // DY64 / XF / C_DF / C_GV0 before these are waited for at the next step
     step(none, [&](bool ld) {
@@ -395,7 +468,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     });
 
     // ---------------------------------------------------------------- action head forward
-    if (worker) epilogue_fwd(C_D1, cg, fp + tc::F_BA0, true, XB1, mk_b1, false, nop);
+    if (worker) frag_fwd(C_D1, fp + tc::F_BA0, XB1, mk_b1, nopf);
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XB1, WA1, 64, 16, 4, 0u); }, none);
     if (g0) {
       float a2[16];
@@ -491,7 +564,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
            tc::gemm<true, true>(ld, tb + C_GMAP, XA2, DY8, 64, 8, 4, 1u);                         // dW_map[in (16 valid)][out]
            tc::gemm<true, true, 1, 3>(ld, tb + C_GBMAP, ONES, DY8, 64, 8, 4, 1u);
          });
-    if (worker) epilogue_bwd(C_D0, cg, mk_b1, true, DY64, false);  // this step's background GEMMs do not read DY64
+    if (worker) frag_bwd(C_D0, mk_b1, DY64, false);  // this step's background GEMMs do not read DY64
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_DF, DY64, WA0, 64, 16, 4, 1u); },        // d(features) += action head
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_GA0, DY64, XF, 64, 16, 4, 1u);
@@ -505,13 +578,13 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
            tc::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
            tc::gemm<true, true, 1, 3>(ld, tb + C_GB2, ONES, DY16, 64, 16, 4, 1u);
          });
-    if (worker) epilogue_bwd(C_D0, cg, mk_h2, true, DY64, false);  // background reads XH2 / DY16 only
+    if (worker) frag_bwd(C_D0, mk_h2, DY64, false);  // background reads XH2 / DY16 only
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, W1, 64, 64, 4, 0u); },
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_G1, DY64, XH1, 64, 64, 4, 1u);
            tc::gemm<true, true, 3, 1>(ld, tb + C_G1 + 64, DY64, ONES, 64, 8, 4, 1u);
          });
-    if (worker) epilogue_bwd(C_D0, cg, mk_h1, true, DY64, true);   // background GEMMs read DY64
+    if (worker) frag_bwd(C_D0, mk_h1, DY64, true);   // background GEMMs read DY64
     step(none, [&](bool ld) {
       tc::gemm<true, true>(ld, tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
       tc::gemm<true, true, 3, 1>(ld, tb + C_G0 + 16, DY64, ONES, 64, 8, 4, 1u);
