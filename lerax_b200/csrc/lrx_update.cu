@@ -10,6 +10,8 @@
 // tiled fp32 SGEMM launch (forward, dX, and split-K dW with the bias gradient folded in as a
 // ones column).  The fused per-warp path for the default widths lives in
 // lrx_update_fused.cu and is tried first.
+#include <cooperative_groups.h>
+
 #include "lrx_common.cuh"
 #include "lrx_policy.cuh"
 
@@ -305,13 +307,67 @@ __global__ void __launch_bounds__(LRX_LOSS_THREADS) loss_kernel(const LossArgs a
 // =========================================================== partial-gradient reduction
 // gradbuf[p] = sum_z partial[z][p]; the last block also folds the loss partial sums into
 // the log_std gradient and the stat slots.  Fixed summation order -> deterministic.
+// clip_by_global_norm + Adam + minibatch statistics by ONE block (any size), given the global norm.
+// optax 0.2.6 chain(clip_by_global_norm, scale_by_adam, scale(-lr)); ppo.py:471-492.
+__device__ void adam_apply_block(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
+                                 int32_t* count, const float* g, int P, int log_std_off, const LrxPpoHyper& h,
+                                 float norm, float* stats_out, int32_t* nonfinite_flag) {
+  const int tid = threadIdx.x;
+  const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
+  const float nbad = __ldcg(g + P + 6);
+  const bool bad = nbad > 0.f || !isfinite(norm);
+  if (!bad) {
+    const int cnt = *count + 1;
+    const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
+    const float bc2 = 1.0f - powf(h.adam_b2, (float)cnt);
+    const bool keep = norm < h.max_grad_norm;
+    for (int p = tid; p < P; p += blockDim.x) {
+      float gp = __ldcg(g + p) + (p == log_std_off ? ls_extra : 0.f);
+      if (!keep) gp = (gp / norm) * h.max_grad_norm;
+      const float mn = h.adam_b1 * m[p] + (1.0f - h.adam_b1) * gp;
+      const float vn = h.adam_b2 * v[p] + (1.0f - h.adam_b2) * (gp * gp);
+      m[p] = mn;
+      v[p] = vn;
+      const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
+      params[p] = params[p] + (-h.learning_rate) * upd;
+    }
+    __syncthreads();
+    if (tid == 0) *count = cnt;
+  } else if (tid == 0 && nonfinite_flag) {
+    atomicOr(nonfinite_flag, 1);
+  }
+  if (tid == 0 && stats_out) {
+    const float kl = __ldcg(g + P + 0) - 1.0f;
+    const float pl = -__ldcg(g + P + 1);
+    const float vl = __ldcg(g + P + 2) / 2.0f;
+    const float el = -__ldcg(g + P + 3);
+    stats_out[0] = kl;
+    stats_out[1] = pl + vl * h.value_loss_coefficient + el * h.entropy_loss_coefficient;
+    stats_out[2] = pl;
+    stats_out[3] = vl;
+    stats_out[4] = el;
+    stats_out[5] = norm;
+    stats_out[6] = nbad;
+    stats_out[7] = 0.f;
+  }
+}
+
 // Block = 32 parameters x 8 row groups: each thread sums every 8th partial row of one parameter
-// (independent loads in flight), the 8 sub-sums are combined in a fixed order.
+// (independent loads in flight), the 8 sub-sums are combined in a fixed order.  With `ap.params`
+// set (single-GPU update) the kernel also applies the update: every block publishes the sum of
+// squares of its 32 gradient entries; after a grid barrier every block adds them in block order ->
+// global norm -> clip + Adam for its own 32 parameters.  Deterministic.
+struct LrxApplyArgs {
+  float* params; float* m; float* v; int32_t* count; LrxPpoHyper h; float* stats_out; int32_t* nonfinite_flag;
+  double* blk_ss;        // [gridDim.x]
+};
+
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, int splits, long long stride, int P,
                        const double* __restrict__ loss_partial, int loss_blocks, int log_std_off,
-                       float ent_coef, double B_global, float* gradbuf) {
+                       float ent_coef, double B_global, float* gradbuf, const LrxApplyArgs ap) {
   __shared__ float sub[8][33];
+  __shared__ double red[8];
   const int pl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + pl;
   float s = 0.f;
@@ -321,30 +377,92 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
   }
   sub[rg][pl] = s;
   __syncthreads();
+  float t = 0.f;
   if (rg == 0 && p < P && p != log_std_off) {
-    float t = sub[0][pl];
+    t = sub[0][pl];
 #pragma unroll
     for (int k = 1; k < 8; ++k) t += sub[k][pl];
     gradbuf[p] = t;
   }
   // loss statistics: warp q (< 6) of block 0 reduces quantity q; lane-strided sums then a
   // fixed-order shuffle tree
+  double lsg = 0;  // log_std gradient (block 0, warp 4, lane 0)
   if (blockIdx.x == 0 && rg < 6) {
     double d = 0;
     for (int b = pl; b < loss_blocks; b += 32) d += loss_partial[(size_t)b * 8 + rg];
     d = warp_sum(d);
     if (pl == 0) {
       if (rg < 4) gradbuf[P + rg] = (float)(d / B_global);       // kl, pol, val, ent means' share
-      else if (rg == 4) { if (log_std_off >= 0) gradbuf[log_std_off] = (float)d; }
+      else if (rg == 4) { if (log_std_off >= 0) { gradbuf[log_std_off] = (float)d; lsg = (double)(float)d; } }
       else gradbuf[P + 6] = (float)d;                              // non-finite row count
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 255) { gradbuf[P + 4] = 0.f; gradbuf[P + 5] = 0.f; gradbuf[P + 7] = 0.f; }
+  if (!ap.params) return;
+
+  // ---- fused apply (cooperative launch): per-block sum of squares (the log_std entry, owned by
+  // block 0, carries the -c_H entropy term exactly as lrx_ppo_apply adds it), grid barrier, every
+  // block rebuilds the same global norm in block order and updates ITS 32 parameters.
+  double ss = 0;
+  if (rg == 0) ss = (double)t * t;
+  if (blockIdx.x == 0 && rg == 4 && pl == 0 && log_std_off >= 0) {
+    const float gl = (float)lsg + (-ap.h.entropy_loss_coefficient);
+    ss = (double)gl * gl;
+  }
+  ss = warp_sum(ss);
+  if (pl == 0) red[rg] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) ap.blk_ss[blockIdx.x] = red[0] + red[4];
+  const int cnt = *ap.count + 1;  // read before the barrier; block 0 stores it after
+  cooperative_groups::this_grid().sync();
+  double acc = 0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) acc += __ldcg(ap.blk_ss + b);
+  acc = warp_sum(acc);
+  __syncthreads();
+  if (pl == 0) red[rg] = acc;
+  __syncthreads();
+  double tt = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tt += red[i];
+  const float norm = (float)sqrt(tt);
+  const LrxPpoHyper& h = ap.h;
+  const float nbad = __ldcg(gradbuf + P + 6);
+  const bool bad = nbad > 0.f || !isfinite(norm);
+  if (!bad && rg == 0 && p < P) {
+    const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
+    const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
+    const float bc2 = 1.0f - powf(h.adam_b2, (float)cnt);
+    float gp = __ldcg(gradbuf + p) + (p == log_std_off ? ls_extra : 0.f);
+    if (!(norm < h.max_grad_norm)) gp = (gp / norm) * h.max_grad_norm;
+    const float mn = h.adam_b1 * ap.m[p] + (1.0f - h.adam_b1) * gp;
+    const float vn = h.adam_b2 * ap.v[p] + (1.0f - h.adam_b2) * (gp * gp);
+    ap.m[p] = mn;
+    ap.v[p] = vn;
+    const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
+    ap.params[p] = ap.params[p] + (-h.learning_rate) * upd;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (!bad) *ap.count = cnt;
+    else if (ap.nonfinite_flag) atomicOr(ap.nonfinite_flag, 1);
+    if (ap.stats_out) {
+      const float kl = __ldcg(gradbuf + P + 0) - 1.0f;
+      const float plo = -__ldcg(gradbuf + P + 1);
+      const float vl = __ldcg(gradbuf + P + 2) / 2.0f;
+      const float el = -__ldcg(gradbuf + P + 3);
+      ap.stats_out[0] = kl;
+      ap.stats_out[1] = plo + vl * h.value_loss_coefficient + el * h.entropy_loss_coefficient;
+      ap.stats_out[2] = plo;
+      ap.stats_out[3] = vl;
+      ap.stats_out[4] = el;
+      ap.stats_out[5] = norm;
+      ap.stats_out[6] = nbad;
+      ap.stats_out[7] = 0.f;
+    }
+  }
 }
 
 // ===================================================================== clip + Adam
-// optax.clip_by_global_norm then scale_by_adam (bias-corrected, eps outside the sqrt) then
-// scale(-lr); one block.  Also finalises the minibatch statistics.   ppo.py:471-492.
+// One block: global norm of the (all-reduced) gradbuf, then adam_apply_block.
 __global__ void __launch_bounds__(1024)
 apply_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, int32_t* count,
              const float* __restrict__ g, int P, int log_std_off, LrxPpoHyper h, float* stats_out,
@@ -369,42 +487,7 @@ apply_kernel(float* __restrict__ params, float* __restrict__ m, float* __restric
     s_norm = (float)sqrt(t);
   }
   __syncthreads();
-  const float norm = s_norm;
-  const bool bad = g[P + 6] > 0.f || !isfinite(norm);
-  if (!bad) {
-    const int cnt = *count + 1;
-    const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
-    const float bc2 = 1.0f - powf(h.adam_b2, (float)cnt);
-    const bool keep = norm < h.max_grad_norm;
-    for (int p = tid; p < P; p += blockDim.x) {
-      float gp = g[p] + (p == log_std_off ? ls_extra : 0.f);
-      if (!keep) gp = (gp / norm) * h.max_grad_norm;
-      const float mn = h.adam_b1 * m[p] + (1.0f - h.adam_b1) * gp;
-      const float vn = h.adam_b2 * v[p] + (1.0f - h.adam_b2) * (gp * gp);
-      m[p] = mn;
-      v[p] = vn;
-      const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
-      params[p] = params[p] + (-h.learning_rate) * upd;
-    }
-    __syncthreads();
-    if (tid == 0) *count = cnt;
-  } else if (tid == 0 && nonfinite_flag) {
-    atomicOr(nonfinite_flag, 1);
-  }
-  if (tid == 0 && stats_out) {
-    const float kl = g[P + 0] - 1.0f;
-    const float pl = -g[P + 1];
-    const float vl = g[P + 2] / 2.0f;
-    const float el = -g[P + 3];
-    stats_out[0] = kl;
-    stats_out[1] = pl + vl * h.value_loss_coefficient + el * h.entropy_loss_coefficient;
-    stats_out[2] = pl;
-    stats_out[3] = vl;
-    stats_out[4] = el;
-    stats_out[5] = norm;
-    stats_out[6] = g[P + 6];
-    stats_out[7] = 0.f;
-  }
+  adam_apply_block(params, m, v, count, g, P, log_std_off, h, s_norm, stats_out, nonfinite_flag);
 }
 
 // ========================================================================= workspace
@@ -467,8 +550,9 @@ size_t lrx_fused_workspace_bytes(const LrxPolicyDesc* pol, int64_t B);
 
 // Workspace = [max(generic scratch, fused scratch)] [adv_sums of lrx_ppo_update] [gradbuf of lrx_ppo_update].
 struct WorkspaceTail {
-  size_t adv_sums_off, gradbuf_off, total;
+  size_t adv_sums_off, gradbuf_off, scratch_off, total;
 };
+constexpr size_t LRX_APPLY_SCRATCH = 8192;  // per-block sums of squares (<= 1000 blocks) + ticket
 static WorkspaceTail workspace_tail(const LrxPolicyDesc* pol, int64_t B) {
   Workspace w = carve(*pol, B, nullptr);
   size_t a = w.total;
@@ -476,7 +560,8 @@ static WorkspaceTail workspace_tail(const LrxPolicyDesc* pol, int64_t B) {
   WorkspaceTail t{};
   t.adv_sums_off = a > f ? a : f;
   t.gradbuf_off = t.adv_sums_off + align_up((size_t)LRX_MAX_BATCHES * 2 * sizeof(double), 256);
-  t.total = t.gradbuf_off + align_up(w.P_pad * 4, 256);
+  t.scratch_off = t.gradbuf_off + align_up(w.P_pad * 4, 256);
+  t.total = t.scratch_off + LRX_APPLY_SCRATCH;
   return t;
 }
 
@@ -487,9 +572,24 @@ extern "C" size_t lrx_ppo_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) {
 
 void lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
                                 int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
-                                cudaStream_t s) {
-  reduce_partials_kernel<<<(P + 31) / 32, 256, 0, s>>>(partial, splits, stride, P, loss_partial, loss_blocks,
-                                                       log_std_off, ent_coef, B_global, gradbuf);
+                                const LrxApplyArgs* apply, cudaStream_t s) {
+  LrxApplyArgs ap{};
+  const int grid = (P + 31) / 32;
+  if (apply && grid <= 900) {
+    // fused reduce + clip + Adam: needs every block resident at once (grid barrier) -> cooperative launch
+    ap = *apply;
+    void* args[] = {(void*)&partial, (void*)&splits, (void*)&stride, (void*)&P, (void*)&loss_partial,
+                    (void*)&loss_blocks, (void*)&log_std_off, (void*)&ent_coef, (void*)&B_global, (void*)&gradbuf,
+                    (void*)&ap};
+    cudaLaunchCooperativeKernel((const void*)reduce_partials_kernel, dim3(grid), dim3(256), args, 0, s);
+    return;
+  }
+  reduce_partials_kernel<<<grid, 256, 0, s>>>(partial, splits, stride, P, loss_partial, loss_blocks, log_std_off,
+                                              ent_coef, B_global, gradbuf, ap);
+  if (apply) {  // too many blocks for one resident wave: separate apply launch
+    apply_kernel<<<1, 1024, 0, s>>>(apply->params, apply->m, apply->v, apply->count, gradbuf, P, log_std_off, apply->h,
+                                    apply->stats_out, apply->nonfinite_flag);
+  }
 }
 
 // ======================================================================== host driver
@@ -522,7 +622,7 @@ static int validate_update_args(const LrxPolicyDesc* pol, const LrxBatchView* bu
 int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf,
                        const int32_t* idx, int64_t B, int64_t B_global, const double* adv_sums,
                        const LrxPpoHyper* h, float* gradbuf, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream, bool* handled);
+                       cudaStream_t stream, bool* handled, const LrxApplyArgs* apply);
 
 extern "C" int lrx_ppo_grad(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf,
                             const int32_t* idx, int64_t B, int64_t B_global, const double* adv_sums,
@@ -539,7 +639,7 @@ extern "C" int lrx_ppo_grad(const LrxPolicyDesc* pol, const float* params, const
   cudaStream_t s = (cudaStream_t)stream;
 
   bool handled = false;
-  rc = lrx_ppo_grad_fused(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, s, &handled);
+  rc = lrx_ppo_grad_fused(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, s, &handled, nullptr);
   if (rc) return rc;
   if (handled) return LRX_OK;
 
@@ -638,7 +738,8 @@ extern "C" int lrx_ppo_grad(const LrxPolicyDesc* pol, const float* params, const
 
   reduce_partials_kernel<<<(P + 31) / 32, 256, 0, s>>>(w.partial, w.splits, (long long)w.P_pad, P, w.loss_partial,
                                                         nchunks * w.loss_blocks, tab.log_std_off,
-                                                        h->entropy_loss_coefficient, (double)B_global, gradbuf);
+                                                        h->entropy_loss_coefficient, (double)B_global, gradbuf,
+                                                        LrxApplyArgs{});
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }
@@ -676,7 +777,19 @@ extern "C" int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* ad
   float* gradbuf = (float*)((char*)workspace + tail.gradbuf_off);
   rc = lrx_ppo_adv_sums(buf->adv, buf->N, buf->T, idx, num_batches, B, adv_sums, stream);
   if (rc) return rc;
+  LrxApplyArgs ap{};
+  ap.params = params; ap.m = adam_m; ap.v = adam_v; ap.count = adam_count; ap.h = *h;
+  ap.nonfinite_flag = nonfinite_flag;
+  ap.blk_ss = (double*)((char*)workspace + tail.scratch_off);
   for (int b = 0; b < num_batches; ++b) {
+    // default widths: one fused gradient launch + one reduce/clip/Adam launch per minibatch
+    bool handled = false;
+    ap.stats_out = stats_out + (size_t)b * LRX_PPO_NSTATS;
+    LRX_REQUIRE(!h->normalize_advantages || adv_sums, LRX_ERR_INVALID_ARG, "adv_sums missing");
+    rc = lrx_ppo_grad_fused(pol, params, buf, idx + (size_t)b * B, B, B, adv_sums + 2 * b, h, gradbuf, workspace,
+                            tail.adv_sums_off, (cudaStream_t)stream, &handled, &ap);
+    if (rc) return rc;
+    if (handled) continue;
     rc = lrx_ppo_grad(pol, params, buf, idx + (size_t)b * B, B, B, adv_sums + 2 * b, h, gradbuf, workspace,
                       tail.adv_sums_off, stream);
     if (rc) return rc;

@@ -705,9 +705,10 @@ FusedWorkspace carve_fused(const LrxPolicyDesc& pol, void* base) {
 }  // namespace
 
 // defined in lrx_update.cu
+struct LrxApplyArgs;
 void lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
                                 int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
-                                cudaStream_t s);
+                                const LrxApplyArgs* apply, cudaStream_t s);
 
 size_t lrx_fused_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) {
   if (!tc::is_default_policy(*pol)) return 0;
@@ -726,7 +727,7 @@ static int fused_disabled() {
 int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf,
                        const int32_t* idx, int64_t B, int64_t B_global, const double* adv_sums,
                        const LrxPpoHyper* h, float* gradbuf, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream, bool* handled) {
+                       cudaStream_t stream, bool* handled, const LrxApplyArgs* apply) {
   *handled = false;
   if (!tc::is_default_policy(*pol) || fused_disabled()) return LRX_OK;
   FusedWorkspace w = carve_fused(*pol, workspace);
@@ -756,7 +757,7 @@ int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxB
   ppo_grad_fused_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(a);
   LRX_LAUNCH_CHECK();
   lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid, a.lo.log_std,
-                             h->entropy_loss_coefficient, (double)B_global, gradbuf, stream);
+                             h->entropy_loss_coefficient, (double)B_global, gradbuf, apply, stream);
   LRX_LAUNCH_CHECK();
   *handled = true;
   return LRX_OK;
