@@ -39,7 +39,7 @@ constexpr uint32_t OFF_XH1 = OFF_XOBS + 3 * PX16;   // encoder layer 1, then val
 constexpr uint32_t OFF_XH2 = OFF_XH1 + 3 * PX64;    // encoder layer 2, then action head layer 1
 constexpr uint32_t OFF_XF = OFF_XH2 + 3 * PX64;
 constexpr uint32_t OFF_F32 = OFF_XF + 3 * PX16;
-constexpr uint32_t OFF_VPART = OFF_F32 + 640 * 4;   // [4][128] partial value dot products
+constexpr uint32_t OFF_VPART = OFF_F32 + tc::F_RESERVE * 4;   // [4][128] partial value dot products
 constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ENVS * 4;
 constexpr uint32_t SMEM_BYTES = OFF_MISC + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "fused rollout kernel exceeds shared memory");
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_tc_kernel(const __grid_con
   tc::stage_weight(a.params + a.lo.w[tc::L_V1], 64, 64, 64, WV1, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_A0], 64, 16, 16, WA0, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_A1], 16, 64, 64, WA1, tid, THREADS);
-  tc::stage_f32(a.params, a.lo, a.n_out, fp, tid, THREADS);
+  tc::stage_f32(a.params, a.lo, a.n_out, OD, fp, tid, THREADS);
   if (tid == 0) {
     umma::mbar_init(bar, ISSUERS);
     umma::fence_mbar_init();

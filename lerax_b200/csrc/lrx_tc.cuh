@@ -176,7 +176,9 @@ __host__ inline bool is_default_policy(const LrxPolicyDesc& p) {
 // Offsets into the block of fp32 parameters kept in shared memory next to the bf16 weights.
 enum : int {
   F_B0 = 0, F_B1 = 64, F_B2 = 128, F_BV0 = 144, F_BV1 = 208, F_BV2 = 272, F_BA0 = 276, F_BA1 = 340,
-  F_BMAP = 356, F_WV2 = 364, F_WMAP = 428, F_COUNT = 556
+  F_BMAP = 356, F_WV2 = 364, F_WMAP = 428,
+  F_W0 = 556,  // encoder layer 0 weight [64][8] (inputs zero-padded): that layer runs on the FMA pipe
+  F_COUNT = 1068, F_RESERVE = 1088
 };
 // Layer order in the flat (Equinox leaf order) parameter vector.
 enum : int { L_ENC0 = 0, L_ENC1, L_ENC2, L_V0, L_V1, L_V2, L_A0, L_A1, L_MAP, L_COUNT };
@@ -201,8 +203,8 @@ __host__ inline LayerOffsets layer_offsets(const LrxPolicyDesc& p) {
 }
 
 // Copy biases, the scalar value-head output row and the action mapping to shared fp32.
-__device__ __forceinline__ void stage_f32(const float* __restrict__ params, const LayerOffsets& lo, int n_out, float* fp,
-                                          int tid, int nthreads) {
+__device__ __forceinline__ void stage_f32(const float* __restrict__ params, const LayerOffsets& lo, int n_out, int obs_dim,
+                                          float* fp, int tid, int nthreads) {
   for (int i = tid; i < F_COUNT; i += nthreads) {
     float v = 0.f;
     if (i < F_B1) v = params[lo.b[L_ENC0] + i];
@@ -215,7 +217,11 @@ __device__ __forceinline__ void stage_f32(const float* __restrict__ params, cons
     else if (i < F_BMAP) v = params[lo.b[L_A1] + (i - F_BA1)];
     else if (i < F_WV2) v = (i - F_BMAP) < n_out ? params[lo.b[L_MAP] + (i - F_BMAP)] : 0.f;
     else if (i < F_WMAP) v = params[lo.w[L_V2] + (i - F_WV2)];
-    else v = (i - F_WMAP) < n_out * 16 ? params[lo.w[L_MAP] + (i - F_WMAP)] : 0.f;
+    else if (i < F_W0) v = (i - F_WMAP) < n_out * 16 ? params[lo.w[L_MAP] + (i - F_WMAP)] : 0.f;
+    else {
+      const int o = (i - F_W0) >> 3, k = (i - F_W0) & 7;
+      v = k < obs_dim ? params[lo.w[L_ENC0] + o * obs_dim + k] : 0.f;
+    }
     fp[i] = v;
   }
 }

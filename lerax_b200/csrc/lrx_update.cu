@@ -307,51 +307,6 @@ __global__ void __launch_bounds__(LRX_LOSS_THREADS) loss_kernel(const LossArgs a
 // =========================================================== partial-gradient reduction
 // gradbuf[p] = sum_z partial[z][p]; the last block also folds the loss partial sums into
 // the log_std gradient and the stat slots.  Fixed summation order -> deterministic.
-// clip_by_global_norm + Adam + minibatch statistics by ONE block (any size), given the global norm.
-// optax 0.2.6 chain(clip_by_global_norm, scale_by_adam, scale(-lr)); ppo.py:471-492.
-__device__ void adam_apply_block(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
-                                 int32_t* count, const float* g, int P, int log_std_off, const LrxPpoHyper& h,
-                                 float norm, float* stats_out, int32_t* nonfinite_flag) {
-  const int tid = threadIdx.x;
-  const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
-  const float nbad = __ldcg(g + P + 6);
-  const bool bad = nbad > 0.f || !isfinite(norm);
-  if (!bad) {
-    const int cnt = *count + 1;
-    const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
-    const float bc2 = 1.0f - powf(h.adam_b2, (float)cnt);
-    const bool keep = norm < h.max_grad_norm;
-    for (int p = tid; p < P; p += blockDim.x) {
-      float gp = __ldcg(g + p) + (p == log_std_off ? ls_extra : 0.f);
-      if (!keep) gp = (gp / norm) * h.max_grad_norm;
-      const float mn = h.adam_b1 * m[p] + (1.0f - h.adam_b1) * gp;
-      const float vn = h.adam_b2 * v[p] + (1.0f - h.adam_b2) * (gp * gp);
-      m[p] = mn;
-      v[p] = vn;
-      const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
-      params[p] = params[p] + (-h.learning_rate) * upd;
-    }
-    __syncthreads();
-    if (tid == 0) *count = cnt;
-  } else if (tid == 0 && nonfinite_flag) {
-    atomicOr(nonfinite_flag, 1);
-  }
-  if (tid == 0 && stats_out) {
-    const float kl = __ldcg(g + P + 0) - 1.0f;
-    const float pl = -__ldcg(g + P + 1);
-    const float vl = __ldcg(g + P + 2) / 2.0f;
-    const float el = -__ldcg(g + P + 3);
-    stats_out[0] = kl;
-    stats_out[1] = pl + vl * h.value_loss_coefficient + el * h.entropy_loss_coefficient;
-    stats_out[2] = pl;
-    stats_out[3] = vl;
-    stats_out[4] = el;
-    stats_out[5] = norm;
-    stats_out[6] = nbad;
-    stats_out[7] = 0.f;
-  }
-}
-
 // Block = 32 parameters x 8 row groups: each thread sums every 8th partial row of one parameter
 // (independent loads in flight), the 8 sub-sums are combined in a fixed order.  With `ap.params`
 // set (single-GPU update) the kernel also applies the update: every block publishes the sum of
@@ -462,17 +417,20 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
 }
 
 // ===================================================================== clip + Adam
-// One block: global norm of the (all-reduced) gradbuf, then adam_apply_block.
-__global__ void __launch_bounds__(1024)
+// lrx_ppo_apply: every block rebuilds the global norm of the (all-reduced) gradbuf by itself, in the
+// same order (deterministic, no scratch memory, L2-resident reads), then updates its own 256
+// parameters.  Cooperative launch: the grid barrier orders block 0's store to *count after every
+// block has read it.
+__global__ void __launch_bounds__(256)
 apply_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, int32_t* count,
              const float* __restrict__ g, int P, int log_std_off, LrxPpoHyper h, float* stats_out,
              int32_t* nonfinite_flag) {
-  __shared__ double red[32];
-  __shared__ float s_norm;
+  __shared__ double red[8];
   const int tid = threadIdx.x;
   // d entropy_loss / d log_std = -1 per row mean -> -c_H, contributed once (not per rank):
   // callers all-reduce gradbuf, so it is added here, after the reduction.
   const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
+  const int cnt = *count + 1;
   double ss = 0;
   for (int p = tid; p < P; p += blockDim.x) {
     float gp = g[p] + (p == log_std_off ? ls_extra : 0.f);
@@ -481,13 +439,53 @@ apply_kernel(float* __restrict__ params, float* __restrict__ m, float* __restric
   ss = warp_sum(ss);  // fixed order -> deterministic
   if ((tid & 31) == 0) red[tid >> 5] = ss;
   __syncthreads();
-  if (tid == 0) {
-    double t = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-    s_norm = (float)sqrt(t);
+  double t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i];
+  const float norm = (float)sqrt(t);
+  const float nbad = g[P + 6];
+  const bool bad = nbad > 0.f || !isfinite(norm);
+  cooperative_groups::this_grid().sync();
+  const int p = blockIdx.x * blockDim.x + tid;
+  if (!bad && p < P) {
+    const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
+    const float bc2 = 1.0f - powf(h.adam_b2, (float)cnt);
+    float gp = g[p] + (p == log_std_off ? ls_extra : 0.f);
+    if (!(norm < h.max_grad_norm)) gp = (gp / norm) * h.max_grad_norm;
+    const float mn = h.adam_b1 * m[p] + (1.0f - h.adam_b1) * gp;
+    const float vn = h.adam_b2 * v[p] + (1.0f - h.adam_b2) * (gp * gp);
+    m[p] = mn;
+    v[p] = vn;
+    const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
+    params[p] = params[p] + (-h.learning_rate) * upd;
   }
-  __syncthreads();
-  adam_apply_block(params, m, v, count, g, P, log_std_off, h, s_norm, stats_out, nonfinite_flag);
+  if (blockIdx.x == 0 && tid == 0) {
+    if (!bad) *count = cnt;
+    else if (nonfinite_flag) atomicOr(nonfinite_flag, 1);
+    if (stats_out) {
+      const float kl = g[P + 0] - 1.0f;
+      const float pl = -g[P + 1];
+      const float vl = g[P + 2] / 2.0f;
+      const float el = -g[P + 3];
+      stats_out[0] = kl;
+      stats_out[1] = pl + vl * h.value_loss_coefficient + el * h.entropy_loss_coefficient;
+      stats_out[2] = pl;
+      stats_out[3] = vl;
+      stats_out[4] = el;
+      stats_out[5] = norm;
+      stats_out[6] = nbad;
+      stats_out[7] = 0.f;
+    }
+  }
+}
+
+static int launch_apply(float* params, float* m, float* v, int32_t* count, const float* g, int P, int log_std_off,
+                        const LrxPpoHyper& h, float* stats_out, int32_t* nonfinite_flag, cudaStream_t s) {
+  LrxPpoHyper hh = h;
+  void* args[] = {(void*)&params, (void*)&m, (void*)&v, (void*)&count, (void*)&g, (void*)&P, (void*)&log_std_off,
+                  (void*)&hh, (void*)&stats_out, (void*)&nonfinite_flag};
+  LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)apply_kernel, dim3((P + 255) / 256), dim3(256), args, 0, s));
+  return LRX_OK;
 }
 
 // ========================================================================= workspace
@@ -586,10 +584,9 @@ void lrx_launch_reduce_partials(const float* partial, int splits, long long stri
   }
   reduce_partials_kernel<<<grid, 256, 0, s>>>(partial, splits, stride, P, loss_partial, loss_blocks, log_std_off,
                                               ent_coef, B_global, gradbuf, ap);
-  if (apply) {  // too many blocks for one resident wave: separate apply launch
-    apply_kernel<<<1, 1024, 0, s>>>(apply->params, apply->m, apply->v, apply->count, gradbuf, P, log_std_off, apply->h,
-                                    apply->stats_out, apply->nonfinite_flag);
-  }
+  if (apply)  // too many blocks for one resident wave of the fused kernel: separate apply launch
+    launch_apply(apply->params, apply->m, apply->v, apply->count, gradbuf, P, log_std_off, apply->h, apply->stats_out,
+                 apply->nonfinite_flag, s);
 }
 
 // ======================================================================== host driver
@@ -752,8 +749,9 @@ extern "C" int lrx_ppo_apply(const LrxPolicyDesc* pol, float* params, float* ada
   LRX_REQUIRE(params && adam_m && adam_v && adam_count && gradbuf && h, LRX_ERR_INVALID_ARG,
               "lrx_ppo_apply: NULL pointer");
   PolicyTable tab = lrx_make_table(*pol);
-  apply_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, adam_m, adam_v, adam_count, gradbuf, pol->n_params,
-                                                    tab.log_std_off, *h, stats_out, nonfinite_flag);
+  int rc2 = launch_apply(params, adam_m, adam_v, adam_count, gradbuf, pol->n_params, tab.log_std_off, *h, stats_out,
+                         nonfinite_flag, (cudaStream_t)stream);
+  if (rc2) return rc2;
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }

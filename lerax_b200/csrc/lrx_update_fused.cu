@@ -51,11 +51,11 @@ constexpr uint32_t OFF_DY16 = OFF_DY64 + 3 * PS64;     // [64][16]
 constexpr uint32_t OFF_DY8 = OFF_DY16 + 3 * PS16;      // [64][8]  dvalue / dlogits
 constexpr uint32_t OFF_ONES = OFF_DY8 + 3 * PS8;       // [64][8]  all ones (one piece)
 constexpr uint32_t OFF_F32 = OFF_ONES + PS8;           // fp32 biases etc. (tc::F_COUNT floats)
-constexpr uint32_t OFF_VPART = OFF_F32 + 640 * 4;      // [4 column groups][64 rows] partial value dot products
+constexpr uint32_t OFF_VPART = OFF_F32 + tc::F_RESERVE * 4;      // [4 column groups][64 rows] partial value dot products
 constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ROWS * 4;  // 2 mbarriers, TMEM slot
 constexpr uint32_t SMEM_BYTES = OFF_MISC + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "fused update kernel exceeds shared memory");
-static_assert(tc::F_COUNT <= 640, "fp32 parameter block too small");
+static_assert(tc::F_COUNT <= tc::F_RESERVE, "fp32 parameter block too small");
 
 // ---- TMEM columns (fp32; M = 64 accumulators use lanes 0-15 of every 32-lane quadrant)
 constexpr uint32_t C_D0 = 0;       // 64: layer outputs
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   tc::stage_weight(a.params + a.lo.w[tc::L_V1], 64, 64, 64, WV1, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_A0], 64, 16, 16, WA0, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_A1], 16, 64, 64, WA1, tid, THREADS);
-  tc::stage_f32(a.params, a.lo, a.n_out, fp, tid, THREADS);
+  tc::stage_f32(a.params, a.lo, a.n_out, a.obs_dim, fp, tid, THREADS);
   for (int i = tid; i < (int)(PS8 / 4); i += THREADS)
     reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;  // two bf16 1.0
   // XB2 is read past the 16 action columns by the mapping-gradient GEMM: keep it finite
@@ -337,11 +337,13 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       const size_t src = (size_t)t * a.buf.N + n;
       ret = __ldg(a.buf.ret + src);
       if (h.clip_value_loss) val_old = __ldg(a.buf.val + src);
-      if (g0) {
+      {
         const float* op = a.buf.obs + src * a.obs_dim;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           if (k < a.obs_dim) o[k] = __ldg(op + k);
+      }
+      if (g0) {
         if (a.is_box) act_f = __ldg((const float*)a.buf.act + src);
         else act_i = __ldg((const int32_t*)a.buf.act + src);
         logp_old = __ldg(a.buf.logp + src);
@@ -365,8 +367,34 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
 
     // ---------------------------------------------------------------- encoder forward
     uint32_t mk_h1 = 0, mk_h2 = 0, mk_b1 = 0, mk_b2 = 0, mk_none = 0;
-    step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XOBS, W0, 64, 64, 1, 0u); }, none);
-    if (worker) frag_fwd(C_D0, fp + tc::F_B0, XH1, mk_h1, nopf);
+    // encoder layer 0 (d <= 8 inputs) on the FMA pipe, straight from the gathered observation: no MMA round
+    // trip.  The fragment rows' observations come from the row-owner lanes by shuffle.
+    if (worker) {
+      const int l0 = lane >> 2, l1 = l0 + 8;
+      float v[8];
+      {
+        const float2 b0 = *reinterpret_cast<const float2*>(fp + tc::F_B0 + fc);
+        const float2 b1 = *reinterpret_cast<const float2*>(fp + tc::F_B0 + fc + 8);
+        v[0] = b0.x; v[1] = b0.y; v[2] = b0.x; v[3] = b0.y; v[4] = b1.x; v[5] = b1.y; v[6] = b1.x; v[7] = b1.y;
+      }
+      const float* w0p = fp + tc::F_W0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < a.obs_dim) {
+          const float x0 = __shfl_sync(0xffffffffu, o[k], l0), x1 = __shfl_sync(0xffffffffu, o[k], l1);
+          const float wa = w0p[fc * 8 + k], wb = w0p[(fc + 1) * 8 + k], wc = w0p[(fc + 8) * 8 + k], wd = w0p[(fc + 9) * 8 + k];
+          v[0] = fmaf(wa, x0, v[0]); v[1] = fmaf(wb, x0, v[1]); v[2] = fmaf(wa, x1, v[2]); v[3] = fmaf(wb, x1, v[3]);
+          v[4] = fmaf(wc, x0, v[4]); v[5] = fmaf(wd, x0, v[5]); v[6] = fmaf(wc, x1, v[6]); v[7] = fmaf(wd, x1, v[7]);
+        }
+      }
+      mk_h1 = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (v[j] > 0.f) mk_h1 |= (1u << j);
+        v[j] = fmaxf(v[j], 0.f);
+      }
+      frag_store(XH1, v, false);
+    }
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH1, W1, 64, 64, 4, 0u); }, none);
     if (worker) frag_fwd(C_D0, fp + tc::F_B1, XH2, mk_h2, nopf);
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH2, W2, 64, 16, 4, 0u); }, none);
