@@ -265,6 +265,10 @@ int lrx_debug_umma_rate(int32_t M, int32_t N, int32_t dsplit, long long* cycles,
 /* Decode of the tcgen05.ld 16x256b.x2 fragment shape: dump [128 threads][8 registers]. */
 int lrx_debug_tmem_shape_probe(float* dump, lrx_stream_t stream);
 
+/* 1 (default): default-width policies run the specialised tensor-core kernels; 0: everything runs
+ * the generic-width kernels (also selectable with the environment variable LRX_DISABLE_FUSED=1). */
+void lrx_debug_set_fused(int enabled);
+
 /* ------------------------------------------------------------------------- misc */
 const char* lrx_last_error(void);
 int lrx_version(void);

@@ -1,5 +1,6 @@
 // Error reporting, descriptor validation and misc C-ABI entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "lrx_common.cuh"
@@ -23,6 +24,19 @@ extern "C" int64_t lrx_launch_count(int reset) {
   if (reset) g_launches = 0;
   return v;
 }
+
+// Specialised tensor-core kernels on (default) / off: with 0 every call takes the generic-width
+// kernels.  Initial value from the environment variable LRX_DISABLE_FUSED=1.  Used by the tests to
+// check both implementations against each other.
+static int g_fused = -1;
+int lrx_fused_enabled() {
+  if (g_fused < 0) {
+    const char* e = getenv("LRX_DISABLE_FUSED");
+    g_fused = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_fused;
+}
+extern "C" void lrx_debug_set_fused(int enabled) { g_fused = enabled ? 1 : 0; }
 
 int lrx_env_state_dim(int kind) { return kind == LRX_ENV_PENDULUM ? 2 : 4; }
 int lrx_env_obs_dim(int kind) { return kind == LRX_ENV_CARTPOLE ? 4 : kind == LRX_ENV_PENDULUM ? 3 : 6; }

@@ -377,14 +377,6 @@ int launch_tc(const RolloutArgs& a, cudaStream_t stream) {
   return LRX_OK;
 }
 
-int fast_disabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LRX_DISABLE_FUSED");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v;
-}
 
 }  // namespace
 
@@ -392,7 +384,7 @@ int lrx_rollout_fast(const LrxEnvDesc* env, const LrxPolicyDesc* pol, const floa
                      LrxEnvState state, LrxRng rng, const LrxReplay* replay, LrxRolloutOut out,
                      int32_t N, int32_t T, float gamma, cudaStream_t stream, bool* handled) {
   *handled = false;
-  if (!tc::is_default_policy(*pol) || fast_disabled()) return LRX_OK;
+  if (!tc::is_default_policy(*pol) || !lrx_fused_enabled()) return LRX_OK;
   RolloutArgs a{};
   a.env = *env;
   a.params = params;

@@ -743,21 +743,13 @@ size_t lrx_fused_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) {
   return carve_fused(*pol, nullptr).total;
 }
 
-static int fused_disabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LRX_DISABLE_FUSED");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v;
-}
 
 int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf,
                        const int32_t* idx, int64_t B, int64_t B_global, const double* adv_sums,
                        const LrxPpoHyper* h, float* gradbuf, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream, bool* handled, const LrxApplyArgs* apply) {
   *handled = false;
-  if (!tc::is_default_policy(*pol) || fused_disabled()) return LRX_OK;
+  if (!tc::is_default_policy(*pol) || !lrx_fused_enabled()) return LRX_OK;
   FusedWorkspace w = carve_fused(*pol, workspace);
   LRX_REQUIRE(workspace_bytes >= w.total, LRX_ERR_INVALID_ARG, "lrx_ppo_grad: workspace too small for the fused path");
   FusedArgs a{};

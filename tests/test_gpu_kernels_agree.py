@@ -1,0 +1,104 @@
+"""The specialised tensor-core kernels (default policy widths) against the generic-width kernels of the
+same library, and size-independent properties at BASELINE.json's full sizes (65 536 envs x 128 steps):
+determinism, GAE returns = advantages + values, the update's gradient linearity over disjoint row sets."""
+
+import numpy as np
+import pytest
+
+from oracle import gae as OG
+from oracle import ppo as OU
+
+import helpers as H
+from test_gpu_parity import noise_for, setup, synthetic_buffer
+
+pytestmark = pytest.mark.gpu
+KINDS = ["cartpole", "pendulum", "acrobot"]
+
+
+@pytest.fixture
+def fused_toggle():
+    from lerax_b200 import _lib as L
+
+    yield L.lib.lrx_debug_set_fused
+    L.lib.lrx_debug_set_fused(1)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("mes", [0, 9])
+def test_rollout_tensor_core_vs_generic(kind, mes, fused_toggle):
+    N, T = 200, 48  # two CTAs of the 128-env kernel, the second one ragged
+    oenv, spec, params, env, pol, rng, y0 = setup(kind, N=N, mes=mes)
+    na, ru = noise_for(spec, rng, T, N, oenv.state_dim)
+    t0, sc0 = np.zeros(N, np.float32), np.zeros(N, np.int32)
+    fused_toggle(1)
+    a = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, na, ru)
+    fused_toggle(0)
+    b = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, na, ru)
+    assert (a["done"] != b["done"]).mean() == 0
+    if not spec.is_box:
+        assert (a["act"] != b["act"]).mean() == 0
+    # per step from identical states: value / log-prob of the two implementations at 1e-5
+    same = np.isclose(a["y_trace"], b["y_trace"], rtol=0, atol=0).all(axis=1)  # [T, N] bit-identical inputs
+    assert same[0].all()
+    for name in ("val", "logp", "rew"):
+        H.assert_close(a[name][same], b[name][same], 1e-5, 2e-6, name + " (identical states)")
+    drift = 1e-5 if kind == "cartpole" else 3e-4
+    for name in ("obs", "val", "logp", "last_value"):
+        H.assert_close(a[name], b[name], 1e-4, drift, name)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_gradient_tensor_core_vs_generic(kind, fused_toggle):
+    T, N, B = 40, 33, 1000  # 15 full 64-row tiles + a ragged one
+    spec, params, pol, rng, flat, buf = synthetic_buffer(kind, T, N, seed=21)
+    hp = OU.Hyper(clip_value_loss=True, entropy_loss_coefficient=0.01)
+    idx = rng.permutation(T * N)[:B].astype(np.int32)
+    fused_toggle(1)
+    ga, _ = H.run_grad(pol, buf, idx, hp)
+    ga2, _ = H.run_grad(pol, buf, idx, hp)
+    np.testing.assert_array_equal(ga, ga2)  # deterministic (fixed-order reductions)
+    fused_toggle(0)
+    gb, _ = H.run_grad(pol, buf, idx, hp)
+    P = spec.n_params
+    scale = np.abs(gb[:P]).max()
+    H.assert_close(ga[:P], gb[:P], 1e-4, 1e-5 * scale, "gradient")
+    H.assert_close(ga[P:P + 4], gb[P:P + 4], 1e-5, 1e-6, "stat sums")
+
+
+def test_full_size_properties():
+    """BASELINE configs[1]: 65 536 envs x 128 steps.  Too large for the oracle; checked through
+    size-independent properties."""
+    import torch
+
+    from lerax_b200 import _lib as L
+
+    N, T = 65536, 128
+    oenv, spec, params, env, pol, rng, _ = setup("cartpole", N=8)
+    y0 = rng.uniform(-0.05, 0.05, (4, N)).astype(np.float32)
+    t0, sc0 = np.zeros(N, np.float32), np.zeros(N, np.int32)
+    a = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, seed=11, trace=False)
+    b = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, seed=11, trace=False)
+    for k in ("obs", "act", "rew", "done", "logp", "val", "last_value"):
+        np.testing.assert_array_equal(a[k], b[k])  # bit-reproducible
+    assert np.isfinite(a["val"]).all() and np.isfinite(a["logp"]).all() and (a["logp"] <= 0).all()
+    assert set(np.unique(a["act"])) <= {0, 1} and (a["rew"] == 1.0).all()
+    ep_len = T * N / max(a["done"].sum(), 1)
+    assert 8 < ep_len < 60  # a random CartPole policy falls after ~10-40 steps
+    # the first 512 envs reproduce the oracle's GAE; everywhere returns = advantages + values
+    adv, ret = H.run_gae(a["rew"], a["val"], a["done"], a["last_value"], 0.99, 0.95)
+    oadv, oret = OG.gae(a["rew"][:, :512], a["val"][:, :512], a["done"][:, :512], a["last_value"][:512], 0.99, 0.95)
+    H.assert_close(adv[:, :512], oadv, 1e-5, 1e-5, "adv")
+    np.testing.assert_allclose(ret, adv + a["val"], rtol=0, atol=1e-5)
+    # gradient of a 262 144-row minibatch = sum of the gradients of its two halves (each scaled by
+    # B_global): linearity of the mean loss over disjoint row sets
+    planes = dict(obs=a["obs"], act=a["act"], logp=a["logp"], val=a["val"], ret=ret, adv=adv)
+    buf = H.DeviceBuffer(**planes)
+    hp = OU.Hyper(normalize_advantages=False)
+    idx = rng.permutation(T * N)[:262144].astype(np.int32)
+    g_all, _ = H.run_grad(pol, buf, idx, hp)
+    g_1, _ = H.run_grad(pol, buf, idx[:131072], hp, B_global=262144)
+    g_2, _ = H.run_grad(pol, buf, idx[131072:], hp, B_global=262144)
+    P = spec.n_params
+    scale = np.abs(g_all[:P]).max()
+    H.assert_close(g_1[:P] + g_2[:P], g_all[:P], 1e-4, 2e-6 * scale, "gradient linearity")
+    torch.cuda.synchronize()
