@@ -177,6 +177,12 @@ int lrx_gae(const float* rew, const float* val, const uint8_t* done, const float
             float* adv, float* ret, int32_t N, int32_t T, float gamma, float lam, int32_t layout,
             double* ev_sums, lrx_stream_t stream);
 
+/* ------------------------------------------------------------------- permutation
+ * buffer/base_buffer.py:85-88: jr.permutation(key, N*T).  out[n] receives a pseudo-random
+ * permutation of [0, n) keyed by `seed` (keyed Feistel bijection with cycle walking, one pass;
+ * the RNG stream is not part of the parity contract). */
+int lrx_permutation(int32_t* out, int64_t n, uint64_t seed, lrx_stream_t stream);
+
 /* --------------------------------------------------------------------- PPO update
  * algorithm/ppo.py:396-561 + optax chain(clip_by_global_norm, adam) (ppo.py:192-194). */
 typedef struct LrxPpoHyper {

@@ -77,6 +77,7 @@ PROTOTYPES = {
                               LrxRolloutOut, C.c_int32, C.c_int32, C.c_float, _vp]),
     "lrx_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,
                           _vp, _vp]),
+    "lrx_permutation": (C.c_int, [_vp, C.c_int64, C.c_uint64, _vp]),
     "lrx_ppo_workspace_bytes": (C.c_size_t, [_P(LrxPolicyDesc), C.c_int64]),
     "lrx_ppo_adv_sums": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int64, _vp, _vp]),
     "lrx_ppo_grad": (C.c_int, [_P(LrxPolicyDesc), _vp, _P(LrxBatchView), _vp, C.c_int64, C.c_int64, _vp,

@@ -78,8 +78,9 @@ class RolloutBuffer(AbstractBuffer):
         if key is None:
             idx = torch.arange(total, device=dev, dtype=torch.int32)
         else:
-            g = torch.Generator(device=dev).manual_seed(int(key) & ((1 << 63) - 1))
-            idx = torch.randperm(total, generator=g, device=dev).to(torch.int32)
+            idx = torch.empty(total, device=dev, dtype=torch.int32)
+            L.check(L.lib.lrx_permutation(L.ptr(idx), total, int(key) & ((1 << 64) - 1), L.stream_ptr()),
+                    "lrx_permutation")
         trim = total - (total % batch_size)
         return idx[:trim].reshape(-1, batch_size).contiguous()
 

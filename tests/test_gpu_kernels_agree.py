@@ -102,3 +102,22 @@ def test_full_size_properties():
     scale = np.abs(g_all[:P]).max()
     H.assert_close(g_1[:P] + g_2[:P], g_all[:P], 1e-4, 2e-6 * scale, "gradient linearity")
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 256, 1000, 65536, 8388608])
+def test_permutation_is_a_bijection(n):
+    import torch
+
+    from lerax_b200 import _lib as L
+
+    out = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    L.check(L.lib.lrx_permutation(L.ptr(out), n, 0x1234567890ABCDEF, L.stream_ptr()), "lrx_permutation")
+    assert torch.equal(torch.sort(out).values, torch.arange(n, dtype=torch.int32, device="cuda"))
+    if n >= 256:
+        out2 = torch.empty_like(out)
+        L.check(L.lib.lrx_permutation(L.ptr(out2), n, 0x1234567890ABCDF0, L.stream_ptr()), "lrx_permutation")
+        assert (out != out2).float().mean() > 0.9  # another key, another permutation
+        assert (out == torch.arange(n, dtype=torch.int32, device="cuda")).float().mean() < 0.05
+        # no structure a minibatch would notice: first-quarter mean index close to n/2
+        q = out[: n // 4].double().mean().item()
+        assert abs(q - (n - 1) / 2) < 0.05 * n
