@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--horizon", type=int, default=T_STEPS)
     ap.add_argument("--epochs", type=int, default=N_EPOCHS)
     ap.add_argument("--batches", type=int, default=N_BATCHES)
-    ap.add_argument("--cpu-envs", type=int, default=2048, help="env count of the bounded CPU sample")
+    ap.add_argument("--cpu-envs", type=int, default=4096, help="env count of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -339,11 +339,11 @@ def run_ours(args):
                   "per row-epoch) / update-stage time; the kernel executes 6 bf16 MMAs per fp32 product on top of that. "
                   "traffic = dram bytes per fused launch (one minibatch of envs*horizon/minibatches rows) from the "
                   "ncu --set full capture in profiles/r1_ppo_grad_fused.md",
-        "rollout": "rollout_generic_kernel: fp32 FMA (the binding pipe is the ~74 TFLOP/s FMA pipe), reported against "
-                   "the measured bf16 tensor peak as the contract asks",
+        "rollout": "rollout_tc_kernel (tcgen05, bf16x3 fp32 emulation): algorithmic fp32 FLOPs / rollout time against the "
+                   "measured bf16 tensor peak",
         "gae": "gae_tn2_kernel: 17 algorithmic bytes per element",
     }
-    traffic = {"update": 129.9e6 if (args.envs, args.horizon, args.batches) == (N_ENVS, T_STEPS, N_BATCHES) else None}
+    traffic = {"update": 128.0e6 if (args.envs, args.horizon, args.batches) == (N_ENVS, T_STEPS, N_BATCHES) else None}
     roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": traffic.get(dominant), "kernel": dominant,
                  "peak_source": peaks["source"], "note": notes[dominant]})
 

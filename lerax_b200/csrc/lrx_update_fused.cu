@@ -33,7 +33,7 @@ constexpr int THREADS = WORKERS + 32;  // + warp 16: issues every tcgen05.mma (c
 constexpr uint32_t PS16 = ROWS * 16 * 2;  // [64][16] piece
 constexpr uint32_t PS64 = ROWS * 64 * 2;  // [64][64] piece
 constexpr uint32_t PS8 = ROWS * 8 * 2;    // [64][8] piece
-constexpr uint32_t OFF_W0 = 0;                         // [64][16]
+constexpr uint32_t OFF_W0 = 0;                         // (reserved; encoder layer 0 runs on the FMA pipe from fp32 weights)
 constexpr uint32_t OFF_W1 = OFF_W0 + 3 * PS16;         // [64][64]
 constexpr uint32_t OFF_W2 = OFF_W1 + 3 * PS64;         // [16][64]  (piece = 16*64*2 = PS16)
 constexpr uint32_t OFF_WV0 = OFF_W2 + 3 * PS16;        // [64][16]
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   uint64_t* barB = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 8);  // background GEMMs of a step done
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 16);
 
-  const tc::Mat W0{smem + OFF_W0, 64, PS16}, W1{smem + OFF_W1, 64, PS64}, W2{smem + OFF_W2, 16, PS16};
+  const tc::Mat W1{smem + OFF_W1, 64, PS64}, W2{smem + OFF_W2, 16, PS16};
   const tc::Mat WV0{smem + OFF_WV0, 64, PS16}, WV1{smem + OFF_WV1, 64, PS64};
   const tc::Mat WA0{smem + OFF_WA0, 64, PS16}, WA1{smem + OFF_WA1, 16, PS16};
   const tc::Mat XOBS{smem + OFF_XOBS, ROWS, PS16}, XH1{smem + OFF_XH1, ROWS, PS64}, XH2{smem + OFF_XH2, ROWS, PS64};
@@ -124,7 +124,6 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   const tc::Mat ONES{smem + OFF_ONES, 0, PS8};  // R = 0: as an MN-major A operand every MN group aliases the same ones
 
   // ------------------------------------------------------------------ one-time staging
-  tc::stage_weight(a.params + a.lo.w[tc::L_ENC0], 64, a.obs_dim, 16, W0, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_ENC1], 64, 64, 64, W1, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_ENC2], 16, 64, 64, W2, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_V0], 64, 16, 16, WV0, tid, THREADS);
