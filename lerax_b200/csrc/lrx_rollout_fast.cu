@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_tc_kernel(const __grid_con
 #pragma unroll
       for (int o2 = 0; o2 < LRX_MAX_NOUT; ++o2) {
         float s = fp[tc::F_BMAP + o2];
-        if (o2 < a.n_out) {
+        if (o2 < EnvDims<KIND>::NA) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) s = fmaf(fp[tc::F_WMAP + o2 * 16 + i], a2[i], s);
         }
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_tc_kernel(const __grid_con
   const LrxRolloutOut& out = a.out;
   const LrxReplay& rp = a.rp;
   const LrxRng& rng = a.rng;
-  const int n_out = a.n_out;
+  constexpr int n_out = EnvDims<KIND>::NA;  // lrx_rollout validated pol->n_out against the env
 
   for (int s = 0; s < T; ++s) {
     const size_t row = (size_t)s * N + nl;

@@ -161,7 +161,16 @@ extern "C" int lrx_debug_umma_gemm(const float* A, const float* B, float* dump, 
 // p_i * q_j kept for i + j <= 2 (6 MMAs, kind::f16, fp32 accumulation).  Element size 2 bytes:
 // a 16-byte chunk holds 8 consecutive k (K-major) or 8 consecutive mn (MN-major); K = 16 per MMA.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
+// fp16x2 probe: x = h0 + h1 with h0 = fp16_rn(x), h1 = fp16_rn(x - h0); stored in the same 2-byte slots
+__device__ __forceinline__ void fp16_split2(float x, __nv_bfloat16 (&p)[3]) {
+  const __half h0 = __float2half_rn(x);
+  const __half h1 = __float2half_rn(x - __half2float(h0));
+  p[0] = *reinterpret_cast<const __nv_bfloat16*>(&h0);
+  p[1] = *reinterpret_cast<const __nv_bfloat16*>(&h1);
+  p[2] = __float2bfloat16_rn(0.f);
+}
 __device__ __forceinline__ void bf16_split3(float x, __nv_bfloat16 (&p)[3]) {
   float r = x;
 #pragma unroll
@@ -194,6 +203,7 @@ umma_selftest_bf16_kernel(const float* __restrict__ A, const float* __restrict__
   uint8_t* a_p[3] = {smem, smem + bytesA, smem + 2 * bytesA};
   uint8_t* b_p[3] = {smem + 3 * bytesA, smem + 3 * bytesA + bytesB, smem + 3 * bytesA + 2 * bytesB};
   __nv_bfloat16 pc[3];
+  const bool fp16_mode = (nprod & 0x10000) != 0;
   if (raw_a) {
     for (uint32_t w = tid; w < bytesA / 2; w += blockDim.x) {
       bf16_split3((float)w, pc);
@@ -201,7 +211,7 @@ umma_selftest_bf16_kernel(const float* __restrict__ A, const float* __restrict__
     }
   } else {
     for (int i = tid; i < M * K; i += blockDim.x) {
-      bf16_split3(A[i], pc);
+      if (fp16_mode) fp16_split2(A[i], pc); else bf16_split3(A[i], pc);
       const uint32_t off = selftest_off16(cfg.a, i / K, i % K);
       for (int q = 0; q < 3; ++q) *(__nv_bfloat16*)(a_p[q] + off) = pc[q];
     }
@@ -213,7 +223,7 @@ umma_selftest_bf16_kernel(const float* __restrict__ A, const float* __restrict__
     }
   } else {
     for (int i = tid; i < N * K; i += blockDim.x) {
-      bf16_split3(B[i], pc);
+      if (fp16_mode) fp16_split2(B[i], pc); else bf16_split3(B[i], pc);
       const uint32_t off = selftest_off16(cfg.b, i / K, i % K);
       for (int q = 0; q < 3; ++q) *(__nv_bfloat16*)(b_p[q] + off) = pc[q];
     }
@@ -241,14 +251,15 @@ umma_selftest_bf16_kernel(const float* __restrict__ A, const float* __restrict__
   if (umma::warp_idx_sync() == 0) {
     umma::tc_fence_after();
     const bool leader = umma::elect_one();
-    const uint32_t idesc = umma::idesc_bf16(M, N, cfg.a.mn, cfg.b.mn);
+    uint32_t idesc = umma::idesc_bf16(M, N, cfg.a.mn, cfg.b.mn);
+    if (fp16_mode) idesc &= ~((7u << 7) | (7u << 10));  // a_format = b_format = F16
     const uint32_t ahi = ((uint32_t)cfg.a.sbo >> 4) | (1u << 14) | (lt_a << 29);
     const uint32_t bhi = ((uint32_t)cfg.b.sbo >> 4) | (1u << 14) | (lt_b << 29);
     const uint32_t alo0 = ((umma::smem_u32(a_p[0]) >> 4) & 0x3FFFu) | (((uint32_t)cfg.a.lbo >> 4) << 16);
     const uint32_t blo0 = ((umma::smem_u32(b_p[0]) >> 4) & 0x3FFFu) | (((uint32_t)cfg.b.lbo >> 4) << 16);
     const uint32_t aps = bytesA >> 4, bps = bytesB >> 4, aks = (uint32_t)cfg.a.kstep >> 4, bks = (uint32_t)cfg.b.kstep >> 4;
     uint32_t acc = 0;
-    const int dsplit = (nprod >> 8) ? (nprod >> 8) : 1;  // timing: rotate over independent accumulators
+    const int dsplit = ((nprod >> 8) & 0xFF) ? ((nprod >> 8) & 0xFF) : 1;  // timing: rotate over independent accumulators
     nprod &= 0xFF;
     uint32_t dn = 0;
     const long long t0 = clock64();
@@ -318,7 +329,7 @@ extern "C" int lrx_debug_umma_gemm_bf16(const float* A, const float* B, float* d
   const size_t smem = (size_t)3 * (bytesA + bytesB);
   LRX_REQUIRE(smem <= 200 * 1024, LRX_ERR_INVALID_ARG, "lrx_debug_umma_gemm_bf16: operands exceed shared memory");
   LRX_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  umma_selftest_bf16_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, dump, M, N, K, cfg, nprod & 0xFF, bytesA,
+  umma_selftest_bf16_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, dump, M, N, K, cfg, nprod & 0x100FF, bytesA,
                                                                       bytesB, 1, nullptr);
   LRX_LAUNCH_CHECK();
   return LRX_OK;

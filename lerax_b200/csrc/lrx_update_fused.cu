@@ -100,7 +100,12 @@ __device__ __forceinline__ float clip_grad_f(float x, float lo, float hi) {
   return (x > lo && x < hi) ? 1.f : ((x == lo || x == hi) ? 0.5f : 0.f);
 }
 
+// NOUT: number of action-head outputs when known at compile time (1 = scalar Box, 2 = CartPole, 3 = Acrobot), so the
+// per-row loss code of the row-owner threads -- the longest serial section of a tile -- unrolls without dead
+// predicated iterations; 0 = read it from the arguments (up to LRX_MAX_NOUT).
+template <int NOUT>
 __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid_constant__ FusedArgs a) {
+  const int n_out = NOUT ? NOUT : a.n_out;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
   const bool worker = warp < WORKERS / 32;  // warp-uniform
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   tc::stage_weight(a.params + a.lo.w[tc::L_V1], 64, 64, 64, WV1, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_A0], 64, 16, 16, WA0, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_A1], 16, 64, 64, WA1, tid, THREADS);
-  tc::stage_f32(a.params, a.lo, a.n_out, a.obs_dim, fp, tid, THREADS);
+  tc::stage_f32(a.params, a.lo, n_out, a.obs_dim, fp, tid, THREADS);
   for (int i = tid; i < (int)(PS8 / 4); i += THREADS)
     reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;  // two bf16 1.0
   // XB2 is read past the 16 action columns by the mapping-gradient GEMM: keep it finite
@@ -508,7 +513,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
 #pragma unroll
       for (int o2 = 0; o2 < LRX_MAX_NOUT; ++o2) {
         float sacc = fp[tc::F_BMAP + o2];
-        if (o2 < a.n_out) {
+        if (o2 < n_out) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) sacc = fmaf(fp[tc::F_WMAP + o2 * 16 + i], a2[i], sacc);
         }
@@ -529,13 +534,13 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
           entropy = 0.5f + LRX_HALF_LOG_2PI + log_scale;
         } else {
 #pragma unroll
-          for (int j = 0; j < LRX_MAX_NOUT; ++j) lp[j] = j < a.n_out ? head[j] : 0.f;
-          log_softmax_n<LRX_MAX_NOUT>(lp, a.n_out);
+          for (int j = 0; j < LRX_MAX_NOUT; ++j) lp[j] = j < n_out ? head[j] : 0.f;
+          log_softmax_n<LRX_MAX_NOUT>(lp, n_out);
           logp = 0.f;
           entropy = 0.f;
 #pragma unroll
           for (int j = 0; j < LRX_MAX_NOUT; ++j) {
-            if (j < a.n_out) {
+            if (j < n_out) {
               pr[j] = expf(lp[j]);
               entropy -= pr[j] * lp[j];
               if (j == act_i) logp = lp[j];
@@ -561,7 +566,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
         } else {
 #pragma unroll
           for (int j = 0; j < LRX_MAX_NOUT; ++j) {
-            if (j < a.n_out) {
+            if (j < n_out) {
               const float dH = -pr[j] * (lp[j] + entropy);
               dhead[j] = dlogp * ((j == act_i ? 1.f : 0.f) - pr[j]) + (-ch * invB) * dH;
             }
@@ -577,7 +582,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
           float sacc = 0.f;
 #pragma unroll
           for (int o2 = 0; o2 < LRX_MAX_NOUT; ++o2)
-            if (o2 < a.n_out) sacc = fmaf(dhead[o2], fp[tc::F_WMAP + o2 * 16 + i], sacc);
+            if (o2 < n_out) sacc = fmaf(dhead[o2], fp[tc::F_WMAP + o2 * 16 + i], sacc);
           d16[i] = sacc;
         }
         tc::store8(DY16, 0, m, d16);
@@ -683,7 +688,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   // nine layers over the four column groups of warps
   umma::tc_fence_after();
   if (!worker) { /* issuer warp: nothing to flush */ } else
-  if (g == 0) { flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0); flush_N(C_G2, C_GB2, 64, 16, 16, tc::L_ENC2); flush_N(C_GMAP, C_GBMAP, 16, a.n_out, 8, tc::L_MAP); }
+  if (g == 0) { flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0); flush_N(C_G2, C_GB2, 64, 16, 16, tc::L_ENC2); flush_N(C_GMAP, C_GBMAP, 16, n_out, 8, tc::L_MAP); }
   if (worker && g == 1) { flush_T(C_G1, 64, 64, tc::L_ENC1); flush_N(C_GV2, C_GBV2, 64, 1, 8, tc::L_V2); }
   if (worker && g == 2) { flush_T(C_GV1, 64, 64, tc::L_V1); flush_T(C_GV0, 16, 16, tc::L_V0); }
   if (worker && g == 3) { flush_T(C_GA0, 16, 16, tc::L_A0); flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1); }
@@ -770,10 +775,18 @@ int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxB
   const int grid = a.n_tiles < LRX_NUM_SMS ? a.n_tiles : LRX_NUM_SMS;
   static bool attr_set = false;
   if (!attr_set) {
-    LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_set = true;
   }
-  ppo_grad_fused_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(a);
+  switch (pol->n_out) {
+    case 1: ppo_grad_fused_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
+    case 2: ppo_grad_fused_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
+    case 3: ppo_grad_fused_kernel<3><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
+    default: ppo_grad_fused_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
+  }
   LRX_LAUNCH_CHECK();
   lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid, a.lo.log_std,
                              h->entropy_loss_coefficient, (double)B_global, gradbuf, apply, stream);
