@@ -502,12 +502,16 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     // ---------------------------------------------------------------- action head forward
     if (worker) frag_fwd(C_D1, fp + tc::F_BA0, XB1, mk_b1, nopf);
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XB1, WA1, 64, 16, 4, 0u); }, none);
+    if (worker && g == 1) epilogue_fwd(C_D0, 0, fp + tc::F_BA1, false, XA2, mk_none, false, nop);
     if (g0) {
+      // column group 1 (idle otherwise) writes the layer output back as the mapping-gradient operand while the
+      // row-owner threads here go straight on with the loss
       float a2[16];
-      epilogue_fwd(C_D0, 0, fp + tc::F_BA1, false, XA2, mk_none, false, [&](float* v) {
+      wait_crit();
+      umma::tmem_ld16(tw + C_D0, a2);
+      umma::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) a2[j] = v[j];
-      });
+      for (int j = 0; j < 16; ++j) a2[j] += fp[tc::F_BA1 + j];
       // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261) on the FMA pipe
       float head[LRX_MAX_NOUT];
 #pragma unroll
