@@ -275,6 +275,10 @@ int lrx_debug_tmem_shape_probe(float* dump, lrx_stream_t stream);
  * the generic-width kernels (also selectable with the environment variable LRX_DISABLE_FUSED=1). */
 void lrx_debug_set_fused(int enabled);
 
+/* Probes of the A-operand-in-TMEM layout (mode 0) and of an M = 64 accumulator at TMEM lane 16 (mode 1):
+ * dump [128 threads][16 columns] of the accumulator. */
+int lrx_debug_tmem_operand_probe(float* dump, int32_t mode, int32_t variant, int32_t M, lrx_stream_t stream);
+
 /* ------------------------------------------------------------------------- misc */
 const char* lrx_last_error(void);
 int lrx_version(void);

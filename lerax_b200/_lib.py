@@ -94,6 +94,7 @@ PROTOTYPES = {
     "lrx_debug_umma_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "lrx_debug_tmem_shape_probe": (C.c_int, [_vp, _vp]),
     "lrx_debug_set_fused": (None, [C.c_int]),
+    "lrx_debug_tmem_operand_probe": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "lrx_last_error": (C.c_char_p, []),
     "lrx_version": (C.c_int, []),
     "lrx_launch_count": (C.c_int64, [C.c_int]),

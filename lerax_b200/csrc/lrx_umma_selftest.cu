@@ -448,3 +448,92 @@ extern "C" int lrx_debug_tmem_shape_probe(float* dump, lrx_stream_t stream) {
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }
+
+// ------------------------------------------------------------------ A-from-TMEM / accumulator-lane probes
+// mode 0: D = A_tmem * I  with A written to TMEM by tcgen05.st 32x32b as bf16 pairs: word(lane L, col c) =
+//         (bf16(f(L, 2c)) | bf16(f(L, 2c+1)) << 16), f = lane id (variant 0) or k index (variant 1); B = identity
+//         [16][16] in shared memory.  The accumulator dump shows which TMEM lane / half-word feeds row m, column k.
+// mode 1: SS-mode M = 64 MMA (A = row id, B = identity) with the accumulator address at TMEM lane 16: does an
+//         M = 64 accumulator live in the upper half of each 32-lane quadrant?
+__global__ void __launch_bounds__(128) tmem_operand_probe_kernel(float* __restrict__ dump, int mode, int variant, int M) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = umma::warp_idx_sync(), lane = threadIdx.x & 31, tid = threadIdx.x;
+  __nv_bfloat16* Bm = reinterpret_cast<__nv_bfloat16*>(smem);            // identity [16][16], canonical K-major
+  __nv_bfloat16* Am = reinterpret_cast<__nv_bfloat16*>(smem + 1024);     // [M][16] row id, canonical K-major (mode 1)
+  for (int i = tid; i < 16 * 16; i += 128) {
+    const int n = i / 16, k = i % 16;
+    Bm[((k >> 3) * (16 * 16) + n * 16 + (k & 7) * 2) / 2] = __float2bfloat16_rn(n == k ? 1.f : 0.f);
+  }
+  for (int i = tid; i < 128 * 16; i += 128) {
+    const int m = i / 16, k = i % 16;
+    Am[((k >> 3) * (128 * 16) + m * 16 + (k & 7) * 2) / 2] = __float2bfloat16_rn(k == 0 ? (float)m : 0.f);
+  }
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 64);
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  {
+    float z[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) z[c] = 0.f;
+    for (int c = 0; c < 64; c += 16) umma::tmem_st16(umma::tmem_addr(tb, warp * 32, c), z);
+    // A operand at columns 32..39: 8 packed words per lane
+    float w[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float lo = variant ? (float)(2 * c) : (float)tid, hi = variant ? (float)(2 * c + 1) : (float)tid;
+      const uint32_t word = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) |
+                            ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
+      w[c] = __uint_as_float(word);
+    }
+    umma::tmem_st16(umma::tmem_addr(tb, warp * 32, 32), w);
+    umma::tmem_st_wait();
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    umma::tc_fence_after();
+    const bool leader = umma::elect_one();
+    const uint32_t idesc = umma::idesc_bf16(M, 16, 0, 0);
+    const uint64_t bd = umma::smem_desc(umma::smem_u32(Bm), 16u * 16u, 128u);
+    if (leader) {
+      if (mode == 0) {
+        const uint32_t a_t = tb + 32;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tb),
+            "r"(a_t), "l"(bd), "r"(idesc), "r"(0u)
+            : "memory");
+      } else {
+        const uint64_t ad = umma::smem_desc(umma::smem_u32(Am), 128u * 16u, 128u);
+        umma::mma_f16(tb + (16u << 16), ad, bd, idesc, 0u);
+      }
+      umma::mma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::tc_fence_after();
+  float v[16];
+  umma::tmem_ld16(umma::tmem_addr(tb, warp * 32, 0), v);
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dump[tid * 16 + i] = v[i];
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tb, 64);
+}
+extern "C" int lrx_debug_tmem_operand_probe(float* dump, int32_t mode, int32_t variant, int32_t M, lrx_stream_t stream) {
+  LRX_REQUIRE(dump && (M == 64 || M == 128), LRX_ERR_INVALID_ARG, "lrx_debug_tmem_operand_probe: bad argument");
+  tmem_operand_probe_kernel<<<1, 128, 8192, (cudaStream_t)stream>>>(dump, mode, variant, M);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
