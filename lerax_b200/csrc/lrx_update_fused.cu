@@ -33,7 +33,7 @@ constexpr int THREADS = WORKERS + 32;  // + warp 16: issues every tcgen05.mma (c
 constexpr uint32_t PS16 = ROWS * 16 * 2;  // [64][16] piece
 constexpr uint32_t PS64 = ROWS * 64 * 2;  // [64][64] piece
 constexpr uint32_t PS8 = ROWS * 8 * 2;    // [64][8] piece
-constexpr uint32_t OFF_W0 = 0;                         // (reserved; encoder layer 0 runs on the FMA pipe from fp32 weights)
+constexpr uint32_t OFF_W0 = 0;                         // second observation buffer [64][16] (encoder layer 0 itself runs on the FMA pipe)
 constexpr uint32_t OFF_W1 = OFF_W0 + 3 * PS16;         // [64][64]
 constexpr uint32_t OFF_W2 = OFF_W1 + 3 * PS64;         // [16][64]  (piece = 16*64*2 = PS16)
 constexpr uint32_t OFF_WV0 = OFF_W2 + 3 * PS16;        // [64][16]
@@ -122,7 +122,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   const tc::Mat W1{smem + OFF_W1, 64, PS64}, W2{smem + OFF_W2, 16, PS16};
   const tc::Mat WV0{smem + OFF_WV0, 64, PS16}, WV1{smem + OFF_WV1, 64, PS64};
   const tc::Mat WA0{smem + OFF_WA0, 64, PS16}, WA1{smem + OFF_WA1, 16, PS16};
-  const tc::Mat XOBS{smem + OFF_XOBS, ROWS, PS16}, XH1{smem + OFF_XH1, ROWS, PS64}, XH2{smem + OFF_XH2, ROWS, PS64};
+  // observations are double-buffered: the last GEMM of a tile (layer-0 weight gradient) still reads them while
+  // the next tile's are written
+  const tc::Mat XOBS2[2] = {tc::Mat{smem + OFF_XOBS, ROWS, PS16}, tc::Mat{smem + OFF_W0, ROWS, PS16}};
+  const tc::Mat XH1{smem + OFF_XH1, ROWS, PS64}, XH2{smem + OFF_XH2, ROWS, PS64};
   const tc::Mat XF{smem + OFF_XF, ROWS, PS16}, XB1{smem + OFF_XB1, ROWS, PS64}, XB2{smem + OFF_XB2, ROWS, PS64};
   const tc::Mat XA2{smem + OFF_XB2, ROWS, PS64};  // [64][16] action layer-2 output; reads past col 16 stay inside XB2
   const tc::Mat DY64{smem + OFF_DY64, ROWS, PS64}, DY16{smem + OFF_DY16, ROWS, PS16}, DY8{smem + OFF_DY8, ROWS, PS8};
@@ -358,10 +361,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   };
   if (worker) load_row(lane < 16 ? (int)blockIdx.x : (int)(blockIdx.x + gridDim.x));
 
+  int tile_parity = 0;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const tc::Mat& XOBS = XOBS2[tile_parity];
+    tile_parity ^= 1;
     if (g0) {
-      wait_crit();
-      wait_bg();  // the previous tile's layer-0 gradient GEMM still reads XOBS
       if (active) {
         float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         tc::store8(XOBS, 0, m, o);
