@@ -324,22 +324,50 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     frag_store(dst, v, need_bg);
   };
   auto nopf = [](float*) {};
+  // 16-wide layer outputs (features, d(features)): every column group takes 4 of the 16 columns of its
+  // quadrant's rows (lane = row), so the step is not left to one group while twelve warps wait.
+  auto quarter16 = [&](uint32_t col, const float* bias, const tc::Mat& dst) {
+    wait_crit();
+    float v[4];
+    umma::tmem_ld4(tw + col + 4 * g, v);
+    umma::tmem_ld_wait();
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += bias[4 * g + j];
+    }
+    uint32_t w[6];
+    tc::split2(v[0], v[1], w[0], w[1], w[2]);
+    tc::split2(v[2], v[3], w[3], w[4], w[5]);
+    if (active) {
+      uint8_t* d = dst.ptr + (uint32_t)((4 * g) >> 3) * (dst.R * 16u) + (uint32_t)m * 16u + (uint32_t)((4 * g) & 7) * 2u;
+      *reinterpret_cast<uint2*>(d) = make_uint2(w[0], w[3]);
+      *reinterpret_cast<uint2*>(d + dst.piece_bytes) = make_uint2(w[1], w[4]);
+      *reinterpret_cast<uint2*>(d + 2 * dst.piece_bytes) = make_uint2(w[2], w[5]);
+    }
+  };
 
-  // Row data of a tile (gather of base_buffer.py:90-103).  Lanes 0-15 own the rows of the CURRENT
-  // tile; the otherwise idle lanes 16-31 load the same rows of the NEXT tile of this CTA a whole tile
-  // ahead and hand them down by shuffle, so the two dependent global loads are never waited for.
+  // Row data of a tile (gather of base_buffer.py:90-103).  Lanes 0-15 own the rows of the CURRENT tile; the
+  // otherwise idle lanes 16-31 prefetch the same rows of the NEXT tiles of this CTA and hand them down by shuffle.
+  // The two dependent global loads (minibatch index, then the row's planes) are issued ONE TILE APART -- the index
+  // two tiles ahead, the data one tile ahead -- so no thread ever waits on a load it has just issued.
   float act_f = 0.f, logp_old = 0.f, A = 0.f, ret = 0.f, val_old = 0.f, o[8];
   int act_i = 0;
   bool valid = false;
-  auto load_row = [&](int tile_of_lane) {
+  int idx_pf = 0;        // minibatch index of this lane's row in the tile whose data is loaded next
+  bool idx_ok = false;
+  auto load_idx = [&](int tile_of_lane) {
     const long long row = (long long)tile_of_lane * ROWS + m;
-    valid = tile_of_lane < a.n_tiles && row < a.B;
+    idx_ok = tile_of_lane < a.n_tiles && row < a.B;
+    idx_pf = idx_ok ? __ldg(a.idx + row) : 0;
+  };
+  auto load_data = [&]() {  // consumes idx_pf / idx_ok
+    valid = idx_ok;
     act_f = logp_old = A = ret = val_old = 0.f;
     act_i = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = 0.f;
     if (valid) {
-      const int i = a.idx[row];
+      const int i = idx_pf;
       const int n = i / a.buf.T, t = i - n * a.buf.T;
       const size_t src = (size_t)t * a.buf.N + n;
       ret = __ldg(a.buf.ret + src);
@@ -354,12 +382,15 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
         if (a.is_box) act_f = __ldg((const float*)a.buf.act + src);
         else act_i = __ldg((const int32_t*)a.buf.act + src);
         logp_old = __ldg(a.buf.logp + src);
-        A = __ldg(a.buf.adv + src);
-        if (h.normalize_advantages) A = (A - adv_mean) / adv_den;
+        A = __ldg(a.buf.adv + src);  // raw; normalised where it is used
       }
     }
   };
-  if (worker) load_row(lane < 16 ? (int)blockIdx.x : (int)(blockIdx.x + gridDim.x));
+  if (worker) {
+    load_idx(lane < 16 ? (int)blockIdx.x : (int)(blockIdx.x + gridDim.x));
+    load_data();
+    if (lane >= 16) load_idx((int)(blockIdx.x + 2 * gridDim.x));
+  }
 
   int tile_parity = 0;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -406,7 +437,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH1, W1, 64, 64, 4, 0u); }, none);
     if (worker) frag_fwd(C_D0, fp + tc::F_B1, XH2, mk_h2, nopf);
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH2, W2, 64, 16, 4, 0u); }, none);
-    if (g0) epilogue_fwd(C_D0, 0, fp + tc::F_B2, false, XF, mk_none, false, nop);
+    if (worker) quarter16(C_D0, fp + tc::F_B2, XF);
 
     // ---------------------------------------------------------------- value head forward
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XF, WV0, 64, 64, 1, 0u); },
@@ -561,11 +592,12 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
         const float ratio = expf(log_ratio);
         s_kl += (double)(ratio - log_ratio);
         const float c = h.clip_coefficient, lo = 1.f - c, hi = 1.f + c;
-        const float s1 = A * ratio, s2 = A * lrx_clipf(ratio, lo, hi);
+        const float An = h.normalize_advantages ? (A - adv_mean) / adv_den : A;  // ppo.py:424-427
+        const float s1 = An * ratio, s2 = An * lrx_clipf(ratio, lo, hi);
         s_pol += (double)fminf(s1, s2);
         float w1, w2;
         tie_weights_f(s1, s2, w1, w2);
-        const float dlogp = -invB * (w1 * A * ratio + w2 * A * clip_grad_f(ratio, lo, hi) * ratio);
+        const float dlogp = -invB * (w1 * An * ratio + w2 * An * clip_grad_f(ratio, lo, hi) * ratio);
         s_ent += (double)entropy;
         const float ch = h.entropy_loss_coefficient;
         if (a.is_box) {
@@ -612,7 +644,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
          });
 
     // ---------------------------------------------------------------- encoder backward
-    if (g0) epilogue_bwd(C_DF, 0, 0, false, DY16, false);         // background reads DY64 / XF only
+    if (worker) quarter16(C_DF, nullptr, DY16);                   // background reads DY64 / XF only
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY16, W2, 64, 64, 1, 0u); },
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
@@ -646,7 +678,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = so[k];
       } else {
-        load_row(tile + 2 * (int)gridDim.x);
+        load_data();                               // tile + 2 * grid: its index was fetched one tile ago
+        load_idx(tile + 3 * (int)gridDim.x);
       }
     }
   }

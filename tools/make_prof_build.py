@@ -1,0 +1,62 @@
+"""Builds tools/_liblerax_prof.so: the library with per-step cycle counters compiled into the fused PPO gradient
+kernel (-DLRX_FUSED_PROFILE; never part of the product build).  Usage on the GPU box:
+    cp tools/_liblerax_prof.so lerax_b200/_C/liblerax_b200.so && python bench.py --steps 1 --warmup 1 --epochs 1 ..."""
+import os, re, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CS = os.path.join(ROOT, "lerax_b200", "csrc")
+s = open(os.path.join(CS, "lrx_update_fused.cu")).read()
+s = s.replace('''  auto step = [&](auto&& crit, auto&& bg) {
+    if (worker) {''', '''  long long pf_t[20] = {0};
+  long long pf_last = clock64();
+  int pf_i = 0;
+  auto step = [&](auto&& crit, auto&& bg) {
+    {
+      const long long now = clock64();
+      pf_t[pf_i] += now - pf_last;
+      pf_last = now;
+      pf_i = pf_i + 1;
+    }
+    if (worker) {''')
+s = s.replace('''    // hand the prefetched rows down to lanes 0-15; lanes 16-31 fetch the tile after next''', '''    pf_i = 0;
+    // hand the prefetched rows down to lanes 0-15; lanes 16-31 fetch the tile after next''')
+s = s.replace('''  // ------------------------------------------------------------------ flush the gradient partial''', '''  if (blockIdx.x == 0 && (tid == 128 || tid == 0 || tid == 512) && a.prof) {
+    long long* o = a.prof + (tid == 0 ? 0 : tid == 128 ? 20 : 40);
+    for (int i = 0; i < 20; ++i) o[i] = pf_t[i];
+  }
+  // ------------------------------------------------------------------ flush the gradient partial''')
+s = s.replace('''  int obs_dim, n_out, is_box;
+  tc::LayerOffsets lo;
+};''', '''  int obs_dim, n_out, is_box;
+  tc::LayerOffsets lo;
+  long long* prof;
+};''')
+s = s.replace('''  switch (pol->n_out) {''', '''  static long long* prof_dev = nullptr;
+  static int prof_left = 2;
+  if (!prof_dev) cudaMalloc(&prof_dev, 60 * sizeof(long long));
+  a.prof = prof_dev;
+  switch (pol->n_out) {''')
+s = s.replace('''  LRX_LAUNCH_CHECK();
+  lrx_launch_reduce_partials(''', '''  LRX_LAUNCH_CHECK();
+  if (prof_left > 0 && a.n_tiles > 1000) {
+    long long hp[60];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost);
+    const int tiles0 = (a.n_tiles + grid - 1) / grid;
+    const char* names[3] = {"warp0(g0)", "warp4(g1)", "issuer"};
+    for (int w = 0; w < 3; ++w) {
+      fprintf(stderr, "[fused prof] %s cycles/tile before step k:", names[w]);
+      long long tot = 0;
+      for (int i = 0; i < 14; ++i) { fprintf(stderr, " %lld", hp[20 * w + i] / tiles0); tot += hp[20 * w + i] / tiles0; }
+      fprintf(stderr, "  | total %lld\\n", tot);
+    }
+    --prof_left;
+  }
+  lrx_launch_reduce_partials(''', 1)
+tmp = "/tmp/lrx_update_fused_prof.cu"
+open(tmp, "w").write(s)
+nv = "/usr/local/cuda/bin/nvcc"
+flags = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", CS]
+subprocess.check_call([nv] + flags + ["-c", tmp, "-o", "/tmp/lrx_update_fused_prof.o"])
+objs = [os.path.join(CS, "build", f) for f in os.listdir(os.path.join(CS, "build")) if f.endswith(".o") and f != "lrx_update_fused.o"]
+subprocess.check_call([nv, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", os.path.join(ROOT, "tools", "_liblerax_prof.so"), "/tmp/lrx_update_fused_prof.o"] + objs + ["-lcudart"])
+print("built tools/_liblerax_prof.so")
