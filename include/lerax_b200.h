@@ -194,6 +194,8 @@ typedef struct LrxPpoHyper {
   float adam_b1, adam_b2, adam_eps;
   int32_t clip_value_loss;
   int32_t normalize_advantages;
+  int32_t surrogate; /* 0: PPO clipped ratio (algorithm/ppo.py:429-434); 1: -mean(log_prob * advantage), the
+                        policy loss of A2C and REINFORCE (algorithm/a2c.py:401, algorithm/reinforce.py:391) */
 } LrxPpoHyper;
 
 /* Flat view of the rollout buffer the update gathers from; planes are [T][N]. */

@@ -55,7 +55,8 @@ class LrxPpoHyper(C.Structure):
     _fields_ = [("clip_coefficient", C.c_float), ("value_loss_coefficient", C.c_float),
                 ("entropy_loss_coefficient", C.c_float), ("max_grad_norm", C.c_float),
                 ("learning_rate", C.c_float), ("adam_b1", C.c_float), ("adam_b2", C.c_float),
-                ("adam_eps", C.c_float), ("clip_value_loss", C.c_int32), ("normalize_advantages", C.c_int32)]
+                ("adam_eps", C.c_float), ("clip_value_loss", C.c_int32), ("normalize_advantages", C.c_int32),
+                ("surrogate", C.c_int32)]
 
 
 class LrxBatchView(C.Structure):

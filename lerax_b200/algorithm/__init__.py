@@ -103,6 +103,9 @@ class PPO(AbstractAlgorithm):
         self.normalize_advantages = normalize_advantages
         self.learning_rate = learning_rate
         self.adam_b1, self.adam_b2, self.adam_eps = 0.9, 0.999, 1e-8  # optax.adam defaults
+        self._surrogate = 0   # LrxPpoHyper.surrogate: PPO's clipped ratio
+        self._shuffle = True  # PPO permutes the buffer every epoch (base_buffer.py:85-88)
+        self._log_keys = ("approx_kl", "loss", "policy_loss", "value_loss", "entropy_loss", "explained_variance")
         self._bufs = None
         if self.batch_size <= 0:
             raise ValueError("num_batches larger than num_envs * num_steps")
@@ -132,7 +135,7 @@ class PPO(AbstractAlgorithm):
     def _hyper(self, lr: float) -> L.LrxPpoHyper:
         return L.LrxPpoHyper(self.clip_coefficient, self.value_loss_coefficient, self.entropy_loss_coefficient,
                              self.max_grad_norm, lr, self.adam_b1, self.adam_b2, self.adam_eps,
-                             int(self.clip_value_loss), int(self.normalize_advantages))
+                             int(self.clip_value_loss), int(self.normalize_advantages), int(self._surrogate))
 
     def _lr_at(self, count: int) -> float:
         return float(self.learning_rate(count)) if callable(self.learning_rate) else float(self.learning_rate)
@@ -232,7 +235,8 @@ class PPO(AbstractAlgorithm):
         for e in range(self.num_epochs):
             # base_buffer.py:85-88.  With several ranks each rank permutes its own shard and
             # contributes B/world rows to every minibatch (SURVEY.md 8e mode ii).
-            idx = buffer.batch_indices(B_local, key=Key((int(epoch_keys[e]) + rank) & _MASK64))[: self.minibatches_per_epoch]
+            perm_key = Key((int(epoch_keys[e]) + rank) & _MASK64) if self._shuffle else None
+            idx = buffer.batch_indices(B_local, key=perm_key)[: self.minibatches_per_epoch]
             nb = idx.shape[0]
             if world == 1 and not callable(self.learning_rate):
                 h = self._hyper(self._lr_at(count))
@@ -271,7 +275,7 @@ class PPO(AbstractAlgorithm):
             "approx_kl": s[0], "loss": s[1], "policy_loss": s[2], "value_loss": s[3], "entropy_loss": s[4],
             "explained_variance": (1.0 - var_err / (var_ret + eps)).to(torch.float32),  # ppo.py:523-528
         }
-        return policy, opt_state, log
+        return policy, opt_state, {k: v for k, v in log.items() if k in self._log_keys}
 
     # ------------------------------------------------------------------ iteration
     def iteration(self, state: PPOState, *, key: Key | int, callback: AbstractCallback) -> PPOState:
@@ -326,4 +330,40 @@ class PPO(AbstractAlgorithm):
         return state.policy
 
 
-__all__ = ["AbstractAlgorithm", "AdamState", "PPO", "PPOState", "PPOStepState"]
+class A2C(PPO):
+    """Advantage Actor-Critic; kwargs and defaults of algorithm/a2c.py:150-177.
+
+    The rollout step and `collect_rollout` of the reference's A2C are line-for-line those of PPO
+    (a2c.py:183-300 vs ppo.py:199-316), so the same rollout and GAE kernels serve it; `train`
+    (a2c.py:415-444) is ONE gradient step on the whole buffer with the policy loss
+    -mean(log_prob * advantage) (a2c.py:381-411): the update kernels with `surrogate = 1`,
+    one minibatch of N*T rows in buffer order."""
+
+    def __init__(self, *, num_envs: int = 4, num_steps: int = 5, gae_lambda: float = 1.0, gamma: float = 0.99,
+                 entropy_loss_coefficient: float = 0.0, value_loss_coefficient: float = 0.5,
+                 max_grad_norm: float = 0.5, normalize_advantages: bool = False,
+                 learning_rate: float | Callable[[int], float] = 7e-4):
+        super().__init__(num_envs=num_envs, num_steps=num_steps, num_epochs=1, num_batches=1, gae_lambda=gae_lambda,
+                         gamma=gamma, entropy_loss_coefficient=entropy_loss_coefficient,
+                         value_loss_coefficient=value_loss_coefficient, max_grad_norm=max_grad_norm,
+                         normalize_advantages=normalize_advantages, learning_rate=learning_rate)
+        self._surrogate = 1
+        self._shuffle = False
+        self._log_keys = ("loss", "policy_loss", "value_loss", "entropy_loss")  # a2c.py:438-443
+
+
+class REINFORCE(A2C):
+    """Monte-Carlo policy gradient with a value baseline; kwargs and defaults of
+    algorithm/reinforce.py:145-168 (GAE with lambda fixed to 1, no entropy term, :372-396)."""
+
+    def __init__(self, *, num_envs: int = 1, num_steps: int = 512, gamma: float = 0.99,
+                 normalize_advantages: bool = True, value_loss_coefficient: float = 0.5, max_grad_norm: float = 0.5,
+                 learning_rate: float | Callable[[int], float] = 3e-4):
+        super().__init__(num_envs=num_envs, num_steps=num_steps, gae_lambda=1.0, gamma=gamma,
+                         entropy_loss_coefficient=0.0, value_loss_coefficient=value_loss_coefficient,
+                         max_grad_norm=max_grad_norm, normalize_advantages=normalize_advantages,
+                         learning_rate=learning_rate)
+        self._log_keys = ("loss", "policy_loss", "value_loss")  # reinforce.py:425-429
+
+
+__all__ = ["A2C", "AbstractAlgorithm", "AdamState", "PPO", "PPOState", "PPOStepState", "REINFORCE"]

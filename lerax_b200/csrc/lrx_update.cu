@@ -250,11 +250,17 @@ __global__ void __launch_bounds__(LRX_LOSS_THREADS) loss_kernel(const LossArgs a
       A = (A - (float)mean) / (std + 1.1920928955078125e-07f);  // + finfo(float32).eps
     }
     const float c = a.h.clip_coefficient, lo = 1.f - c, hi = 1.f + c;
-    const float s1 = A * ratio, s2 = A * lrx_clipf(ratio, lo, hi);
-    s_pol = (double)fminf(s1, s2);
-    float w1, w2;
-    tie_weights(s1, s2, w1, w2);
-    const float dlogp = -invB * (w1 * A * ratio + w2 * A * clip_grad(ratio, lo, hi) * ratio);
+    float dlogp;
+    if (a.h.surrogate == 1) {  // A2C / REINFORCE: -mean(logp * A)   (a2c.py:401, reinforce.py:391)
+      s_pol = (double)(logp * A);
+      dlogp = -invB * A;
+    } else {
+      const float s1 = A * ratio, s2 = A * lrx_clipf(ratio, lo, hi);
+      s_pol = (double)fminf(s1, s2);
+      float w1, w2;
+      tie_weights(s1, s2, w1, w2);
+      dlogp = -invB * (w1 * A * ratio + w2 * A * clip_grad(ratio, lo, hi) * ratio);
+    }
 
     float dvl;
     const float e1 = value - a.ret[m];

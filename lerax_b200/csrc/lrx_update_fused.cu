@@ -593,11 +593,17 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
         s_kl += (double)(ratio - log_ratio);
         const float c = h.clip_coefficient, lo = 1.f - c, hi = 1.f + c;
         const float An = h.normalize_advantages ? (A - adv_mean) / adv_den : A;  // ppo.py:424-427
-        const float s1 = An * ratio, s2 = An * lrx_clipf(ratio, lo, hi);
-        s_pol += (double)fminf(s1, s2);
-        float w1, w2;
-        tie_weights_f(s1, s2, w1, w2);
-        const float dlogp = -invB * (w1 * An * ratio + w2 * An * clip_grad_f(ratio, lo, hi) * ratio);
+        float dlogp;
+        if (h.surrogate == 1) {  // A2C / REINFORCE: -mean(logp * A)   (a2c.py:401, reinforce.py:391)
+          s_pol += (double)(logp * An);
+          dlogp = -invB * An;
+        } else {
+          const float s1 = An * ratio, s2 = An * lrx_clipf(ratio, lo, hi);
+          s_pol += (double)fminf(s1, s2);
+          float w1, w2;
+          tie_weights_f(s1, s2, w1, w2);
+          dlogp = -invB * (w1 * An * ratio + w2 * An * clip_grad_f(ratio, lo, hi) * ratio);
+        }
         s_ent += (double)entropy;
         const float ch = h.entropy_loss_coefficient;
         if (a.is_box) {

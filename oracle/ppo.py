@@ -39,6 +39,9 @@ class Hyper:
     b1: float = 0.9
     b2: float = 0.999
     eps: float = 1e-8
+    # 0: PPO clipped surrogate (ppo.py:429-434); 1: -mean(log_prob * advantage) of A2C / REINFORCE
+    # (algorithm/a2c.py:401, algorithm/reinforce.py:391)
+    surrogate: int = 0
 
 
 class NonFiniteError(FloatingPointError):
@@ -98,11 +101,15 @@ def ppo_loss_and_grad(spec: P.PolicySpec, params, mb, hp: Hyper, eps_dtype_eps=N
 
     c = dt(hp.clip_coefficient)
     lo, hi = dt(1.0) - c, dt(1.0) + c
-    s1 = adv * ratio
-    s2 = adv * np.clip(ratio, lo, hi)
-    policy_loss = -np.mean(np.minimum(s1, s2))
-    w1, w2 = _tie_weights(s1, s2)
-    dlogp = -invB * (w1 * adv * ratio + w2 * adv * _clip_grad(ratio, lo, hi) * ratio)
+    if hp.surrogate == 1:
+        policy_loss = -np.mean(logp * adv)
+        dlogp = -invB * adv
+    else:
+        s1 = adv * ratio
+        s2 = adv * np.clip(ratio, lo, hi)
+        policy_loss = -np.mean(np.minimum(s1, s2))
+        w1, w2 = _tie_weights(s1, s2)
+        dlogp = -invB * (w1 * adv * ratio + w2 * adv * _clip_grad(ratio, lo, hi) * ratio)
 
     if hp.clip_value_loss:
         dv_old = value - mb["val"]

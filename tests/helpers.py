@@ -121,7 +121,7 @@ def make_hyper(hp):
 
     return L.LrxPpoHyper(hp.clip_coefficient, hp.value_loss_coefficient, hp.entropy_loss_coefficient,
                          hp.max_grad_norm, hp.learning_rate, hp.b1, hp.b2, hp.eps, int(hp.clip_value_loss),
-                         int(hp.normalize_advantages))
+                         int(hp.normalize_advantages), int(getattr(hp, "surrogate", 0)))
 
 
 def run_grad(policy, buf: DeviceBuffer, idx_row, hp, B_global=None):

@@ -69,3 +69,51 @@ def test_ppo_learns_cartpole():
         out = algo.learn(env, pol, total_timesteps=64 * 128 * 40, key=jr.key(seed + 100))
         best = max(best, average_reward(env, out))
     assert best >= 475.0, best
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "pendulum", "acrobot"])
+def test_a2c_surrogate_gradient_matches_oracle(kind):
+    """a2c.py:381-411 / reinforce.py:372-396: policy loss -mean(log_prob * advantage), one step on the whole buffer."""
+    from oracle import ppo as OU
+
+    import helpers as H
+    from test_gpu_parity import synthetic_buffer
+
+    T, N = 24, 20
+    spec, params, pol, rng, flat, buf = synthetic_buffer(kind, T, N, seed=31)
+    hp = OU.Hyper(entropy_loss_coefficient=0.01, normalize_advantages=True, surrogate=1, learning_rate=7e-4)
+    idx = np.arange(T * N, dtype=np.int32)  # buffer order, no shuffle
+    _, stats, g = OU.ppo_loss_and_grad(spec, params, OU.gather(flat, idx), hp)
+    gb, _ = H.run_grad(pol, buf, idx, hp)
+    P = spec.n_params
+    gg = gb[:P].copy()
+    if spec.is_box:
+        gg[-1] -= hp.entropy_loss_coefficient
+    H.assert_close(gg, g, 1e-4, 1e-5 * np.abs(g).max(), "gradient")
+    got = np.array([-gb[P + 1], gb[P + 2] / 2, -gb[P + 3]])
+    H.assert_close(got, stats[2:5], 1e-4, 1e-5, "policy / value / entropy losses")
+    # one full update = the oracle's train on a single minibatch
+    p1, st, log = OU.train(spec, params.copy(), OU.AdamState.init(params), flat, idx[None, None], hp)
+    gp, gm, gv, cnt, _, flag = H.run_update(pol, buf, idx[None, None], hp)
+    assert cnt == 1 and flag == 0
+    H.assert_close(gp, p1, 1e-4, 1e-6, "params after the A2C step")
+
+
+def test_a2c_and_reinforce_train_and_learn():
+    from lerax_b200 import random as jr
+    from lerax_b200.algorithm import A2C, REINFORCE
+    from lerax_b200.env.classic_control import CartPole
+    from lerax_b200.policy import MLPActorCriticPolicy
+
+    env = CartPole()
+    # reference smoke tests: tests/algorithm/test_a2c.py, test_reinforce.py (learn returns a policy)
+    for algo in (A2C(num_envs=2, num_steps=8), REINFORCE(num_envs=1, num_steps=64)):
+        policy = MLPActorCriticPolicy(env, key=jr.key(0))
+        out = algo.learn(env, policy, total_timesteps=4 * algo.num_envs * algo.num_steps, key=jr.key(1))
+        assert np.isfinite(out.numpy()).all() and not np.array_equal(out.numpy(), policy.numpy())
+    # A2C with many envs improves on the untrained policy
+    policy = MLPActorCriticPolicy(env, key=jr.key(3))
+    before = average_reward(env, policy)
+    algo = A2C(num_envs=256, num_steps=16, entropy_loss_coefficient=0.01)
+    after = average_reward(env, algo.learn(env, policy, total_timesteps=256 * 16 * 300, key=jr.key(4)))
+    assert after > 2 * before, (before, after)

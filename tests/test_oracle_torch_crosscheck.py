@@ -62,7 +62,10 @@ def torch_loss(spec, p, mb, hp):
     if hp.normalize_advantages:
         adv = (adv - adv.mean()) / (adv.std(unbiased=False) + O.F32_EPS)
     c = hp.clip_coefficient
-    pl = -torch.minimum(adv * ratio, adv * torch.clamp(ratio, 1 - c, 1 + c)).mean()
+    if hp.surrogate == 1:
+        pl = -(logp * adv).mean()  # a2c.py:401, reinforce.py:391
+    else:
+        pl = -torch.minimum(adv * ratio, adv * torch.clamp(ratio, 1 - c, 1 + c)).mean()
     if hp.clip_value_loss:
         cl = mb["val"] + torch.clamp(value - mb["val"], -c, c)
         vl = torch.minimum((value - mb["ret"]) ** 2, (cl - mb["ret"]) ** 2).mean() / 2
@@ -89,10 +92,10 @@ def make_minibatch(kind, B, dtype, seed=0, **kw):
 
 
 @pytest.mark.parametrize("kind", ["cartpole", "pendulum", "acrobot"])
-@pytest.mark.parametrize("clip_v,ch", [(False, 0.0), (True, 0.01)])
-def test_loss_and_grad_match_torch_autograd_fp64(kind, clip_v, ch):
+@pytest.mark.parametrize("clip_v,ch,sur", [(False, 0.0, 0), (True, 0.01, 0), (False, 0.01, 1)])
+def test_loss_and_grad_match_torch_autograd_fp64(kind, clip_v, ch, sur):
     spec, params, mb = make_minibatch(kind, 96, np.float64, seed=3)
-    hp = O.Hyper(clip_value_loss=clip_v, entropy_loss_coefficient=ch)
+    hp = O.Hyper(clip_value_loss=clip_v, entropy_loss_coefficient=ch, surrogate=sur)
     loss, stats, g = O.ppo_loss_and_grad(spec, params, mb, hp)
     p = torch.tensor(params, requires_grad=True)
     tmb = {k: torch.tensor(v) for k, v in mb.items()}
