@@ -140,6 +140,37 @@ __device__ __forceinline__ void gemm(bool leader, uint32_t d_tmem, const Mat& A,
   }
 }
 
+// Same with the A operand in TMEM: piece i of the 64-wide operand occupies 32 packed columns at
+// a_tmem + 32 * i, a K = 16 slice is 8 columns.
+template <bool B_MN, int PA = 3, int PB = 3>
+__device__ __forceinline__ void gemm_ts(bool leader, uint32_t d_tmem, uint32_t a_tmem, const Mat& B, int M, int N,
+                                        int ksteps, uint32_t accumulate) {
+  const uint32_t idesc = umma::idesc_bf16(M, N, 0, B_MN ? 1 : 0);
+  uint64_t bd[PB];
+#pragma unroll
+  for (int j = 0; j < PB; ++j) bd[j] = make_desc(desc_lo<B_MN>(B) + j * (B.piece_bytes >> 4), desc_hi<B_MN>(B));
+  const uint64_t bks = desc_kstep<B_MN>(B);
+  uint32_t acc = accumulate;
+  uint32_t at = a_tmem;
+#pragma unroll 1
+  for (int ks = 0; ks < ksteps; ++ks) {
+#pragma unroll
+    for (int sum = 2; sum >= 0; --sum) {
+#pragma unroll
+      for (int i = 0; i <= sum; ++i) {
+        const int j = sum - i;
+        if (i < PA && j < PB) {
+          if (leader) umma::mma_f16_ts(d_tmem, at + 32u * i, bd[j], idesc, acc);
+          acc = 1u;
+        }
+      }
+    }
+    at += 8u;
+#pragma unroll
+    for (int j = 0; j < PB; ++j) bd[j] += bks;
+  }
+}
+
 // Stage a Linear's weight W[out][in] (fp32, row-major, global) as the canonical matrix with
 // r = out, c = in (zero-padded to in_pad, a multiple of 8).
 __device__ __forceinline__ void stage_weight(const float* __restrict__ W, int out, int in, int in_pad, const Mat& dst,

@@ -182,6 +182,25 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_
       : "memory");
 }
 
+// A operand from TMEM (bf16 pairs packed in 32-bit columns; for M = 64 row m sits in TMEM lane
+// m%16 + 32*(m/16), word c holds K elements 2c, 2c+1 -- tools/tmem_operand_probe.py), B from shared memory.
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// tcgen05.st 16x128b.x1: thread t writes r0 -> (lane t/4, column t%4), r1 -> (lane t/4 + 8, column t%4)
+// (tools/tmem_st_shape_probe.py): the store twin of the 16x256b fragment for packed bf16 pairs.
+__device__ __forceinline__ void tmem_st_frag(uint32_t taddr, uint32_t r0, uint32_t r1) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x1.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
+
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(

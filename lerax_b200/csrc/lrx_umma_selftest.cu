@@ -2,6 +2,8 @@
 // kind::tf32 MMAs (optionally the 3xTF32 split) from operands staged in the canonical shared
 // memory layout, in K-major or MN-major form, and dumps the raw TMEM accumulator
 // [128 lanes][N columns] so the test can also check the lane mapping of M = 64.
+#include <stdlib.h>
+
 #include "lrx_common.cuh"
 #include "lrx_umma.cuh"
 
@@ -415,6 +417,41 @@ extern "C" int lrx_debug_umma_rate(int32_t M, int32_t N, int32_t dsplit, long lo
 // ------------------------------------------------------------------ tcgen05.ld fragment-shape probe
 // TMEM[lane][col] = lane * 100 + col (written 32x32b), read back with the 16x256b.x2 shape: dump[t][r]
 // = register r of thread t, which decodes the (lane, column) each thread receives.
+// variant 1: the STORE shape 16x128b.x1 (two registers per thread, value = 2 * thread + register), read back 32x32b:
+// dump[lane][col] = which (thread, register) wrote TMEM cell (lane, col), cols 0..3.
+__global__ void __launch_bounds__(128) tmem_st_shape_probe_kernel(float* __restrict__ dump) {
+  __shared__ uint32_t tmem_slot;
+  const int warp = umma::warp_idx_sync(), lane = threadIdx.x & 31;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 32);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  float z[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) z[c] = -1.f;
+  umma::tmem_st16(umma::tmem_addr(tb, warp * 32, 0), z);
+  umma::tmem_st_wait();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t r0 = __float_as_uint((float)(2 * lane)), r1 = __float_as_uint((float)(2 * lane + 1));
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x1.b32 [%0], {%1, %2};" ::"r"(umma::tmem_addr(tb, warp * 32, 0)), "r"(r0), "r"(r1)
+               : "memory");
+  umma::tmem_st_wait();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  float v[8];
+  umma::tmem_ld8(umma::tmem_addr(tb, warp * 32, 0), v);
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dump[threadIdx.x * 8 + i] = v[i];
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tb, 32);
+}
+
 __global__ void __launch_bounds__(128) tmem_shape_probe_kernel(float* __restrict__ dump) {
   __shared__ uint32_t tmem_slot;
   const int warp = umma::warp_idx_sync(), lane = threadIdx.x & 31;
@@ -444,6 +481,11 @@ __global__ void __launch_bounds__(128) tmem_shape_probe_kernel(float* __restrict
 }
 extern "C" int lrx_debug_tmem_shape_probe(float* dump, lrx_stream_t stream) {
   LRX_REQUIRE(dump, LRX_ERR_INVALID_ARG, "lrx_debug_tmem_shape_probe: NULL pointer");
+  if (getenv("LRX_PROBE_ST_SHAPE")) {
+    tmem_st_shape_probe_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(dump);
+    LRX_LAUNCH_CHECK();
+    return LRX_OK;
+  }
   tmem_shape_probe_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(dump);
   LRX_LAUNCH_CHECK();
   return LRX_OK;

@@ -17,6 +17,18 @@ s = s.replace('''  auto step = [&](auto&& crit, auto&& bg) {
       pf_i = pf_i + 1;
     }
     if (worker) {''')
+s = s.replace('''  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x,''', '''  extern __shared__ __align__(1024) uint8_t smem[];
+  const long long pf_k0 = clock64();
+  const int tid = threadIdx.x,''')
+s = s.replace('''  int tile_parity = 0;''', '''  const long long pf_k1 = clock64();
+  int tile_parity = 0;''')
+s = s.replace('''  if (warp == 0) umma::tmem_dealloc(tb, TMEM_COLS);
+}''', '''  if (warp == 0) umma::tmem_dealloc(tb, TMEM_COLS);
+  if (blockIdx.x == 0 && tid == 0 && a.prof) { a.prof[15] = pf_k1 - pf_k0; a.prof[16] = pf_k2 - pf_k1; a.prof[17] = clock64() - pf_k2; }
+}''')
+s = s.replace('''  // ------------------------------------------------------------------ flush the gradient partial''', '''  const long long pf_k2 = clock64();
+  // ------------------------------------------------------------------ flush the gradient partial''')
 s = s.replace('''    // hand the prefetched rows down to lanes 0-15; lanes 16-31 fetch the tile after next''', '''    pf_i = 0;
     // hand the prefetched rows down to lanes 0-15; lanes 16-31 fetch the tile after next''')
 s = s.replace('''  // ------------------------------------------------------------------ flush the gradient partial''', '''  if (blockIdx.x == 0 && (tid == 128 || tid == 0 || tid == 512) && a.prof) {
@@ -49,6 +61,7 @@ s = s.replace('''  LRX_LAUNCH_CHECK();
       for (int i = 0; i < 14; ++i) { fprintf(stderr, " %lld", hp[20 * w + i] / tiles0); tot += hp[20 * w + i] / tiles0; }
       fprintf(stderr, "  | total %lld\\n", tot);
     }
+    fprintf(stderr, "[fused prof] block 0: prologue %lld, loop %lld, tail %lld cycles; tiles %d\\n", hp[15], hp[16], hp[17], tiles0);
     --prof_left;
   }
   lrx_launch_reduce_partials(''', 1)
