@@ -53,7 +53,17 @@ constexpr uint32_t OFF_ONES = OFF_DY8 + 3 * PS8;       // [64][8]  all ones (one
 constexpr uint32_t OFF_F32 = OFF_ONES + PS8;           // fp32 biases etc. (tc::F_COUNT floats)
 constexpr uint32_t OFF_VPART = OFF_F32 + tc::F_RESERVE * 4;      // [4 column groups][64 rows] partial value dot products
 constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ROWS * 4;  // 2 mbarriers, TMEM slot
-constexpr uint32_t SMEM_BYTES = OFF_MISC + 64;
+// gathered row data of a tile (cp.async destinations): [5][64] 32-bit planes -- return, old value, action bits,
+// old log-prob, advantage -- then the minibatch indices of the tile after [64] and the valid flags [64] u8
+constexpr int R_RET = 0, R_VAL = 1, R_ACT = 2, R_LOGP = 3, R_ADV = 4, R_PLANES = 5;
+constexpr uint32_t OFF_ROWS = OFF_MISC + 64;
+constexpr uint32_t OFF_IDX = OFF_ROWS + R_PLANES * ROWS * 4;
+constexpr uint32_t OFF_VALID = OFF_IDX + ROWS * 4;
+constexpr uint32_t SMEM_BYTES = OFF_VALID + ROWS;
+// fp32 observations of the tile's rows [64][8]: in flight / live only from the step after the last GEMM that reads
+// the dvalue / dlogits operand (which owns these bytes) to the layer-0 arithmetic of the next tile
+constexpr uint32_t OFF_OBS32 = OFF_DY8;
+static_assert(ROWS * 8 * 4 <= 3 * PS8, "fp32 observation staging must fit the DY8 operand");
 static_assert(SMEM_BYTES <= 227 * 1024, "fused update kernel exceeds shared memory");
 static_assert(tc::F_COUNT <= tc::F_RESERVE, "fp32 parameter block too small");
 
@@ -118,6 +128,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   uint64_t* barA = reinterpret_cast<uint64_t*>(smem + OFF_MISC);      // critical GEMM(s) of a step done
   uint64_t* barB = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 8);  // background GEMMs of a step done
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 16);
+  float* rows_s = reinterpret_cast<float*>(smem + OFF_ROWS);
+  int* idx_s = reinterpret_cast<int*>(smem + OFF_IDX);
+  uint8_t* valid_s = smem + OFF_VALID;
+  float* obs_s = reinterpret_cast<float*>(smem + OFF_OBS32);
 
   const tc::Mat W1{smem + OFF_W1, 64, PS64}, W2{smem + OFF_W2, 16, PS16};
   const tc::Mat WV0{smem + OFF_WV0, 64, PS16}, WV1{smem + OFF_WV1, 64, PS64};
@@ -346,68 +360,72 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     }
   };
 
-  // Row data of a tile (gather of base_buffer.py:90-103).  Lanes 0-15 own the rows of the CURRENT tile; the
-  // otherwise idle lanes 16-31 prefetch the same rows of the NEXT tiles of this CTA and hand them down by shuffle.
-  // The two dependent global loads (minibatch index, then the row's planes) are issued ONE TILE APART -- the index
-  // two tiles ahead, the data one tile ahead -- so no thread ever waits on a load it has just issued.
-  float act_f = 0.f, logp_old = 0.f, A = 0.f, ret = 0.f, val_old = 0.f, o[8];
-  int act_i = 0;
-  bool valid = false;
-  int idx_pf = 0;        // minibatch index of this lane's row in the tile whose data is loaded next
-  bool idx_ok = false;
-  auto load_idx = [&](int tile_of_lane) {
-    const long long row = (long long)tile_of_lane * ROWS + m;
-    idx_ok = tile_of_lane < a.n_tiles && row < a.B;
-    idx_pf = idx_ok ? __ldg(a.idx + row) : 0;
+  // Row data of a tile (gather of base_buffer.py:90-103): cp.async straight into shared memory, issued by the
+  // otherwise idle lanes 16-31 of column group 0 (one lane per row) one tile ahead, the minibatch index two tiles
+  // ahead.  No register is the destination of a global load inside the tile loop: a register gather -- even one
+  // consumed a whole tile later -- cost 9 % of the kernel, because everything that shares a scoreboard with the
+  // outstanding loads waits out their DRAM latency.  The planes are free for the next tile once the policy loss
+  // has read them, the fp32 observations once the last GEMM on DY8 is done: both hold after step 9's wait.
+  auto cp_async4 = [](void* dst, const void* src, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(umma::smem_u32(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
   };
-  auto load_data = [&]() {  // consumes idx_pf / idx_ok
-    valid = idx_ok;
-    act_f = logp_old = A = ret = val_old = 0.f;
-    act_i = 0;
+  auto cp_async16 = [](void* dst, const void* src, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(umma::smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+  };
+  auto tile_row_ok = [&](int t) { return t < a.n_tiles && (long long)t * ROWS + m < a.B; };
+  auto gather_rows = [&](int i, bool ok) {  // buffer row i (zeros when !ok) -> this lane's staging slot m
+    const int n = i / a.buf.T, t = i - n * a.buf.T;
+    const size_t src = ok ? (size_t)t * a.buf.N + n : 0;
+    cp_async4(rows_s + R_RET * ROWS + m, a.buf.ret + src, ok);
+    cp_async4(rows_s + R_VAL * ROWS + m, (h.clip_value_loss ? a.buf.val : a.buf.ret) + src, ok && h.clip_value_loss);
+    cp_async4(rows_s + R_ACT * ROWS + m, (const int32_t*)a.buf.act + src, ok);
+    cp_async4(rows_s + R_LOGP * ROWS + m, a.buf.logp + src, ok);
+    cp_async4(rows_s + R_ADV * ROWS + m, a.buf.adv + src, ok);  // raw; normalised where it is used
+    const float* op = a.buf.obs + src * a.obs_dim;
+    if (a.obs_dim == 4) {  // one 16-byte copy (CartPole)
+      cp_async16(obs_s + m * 8, op, ok);
+      *reinterpret_cast<float4*>(obs_s + m * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = 0.f;
-    if (valid) {
-      const int i = idx_pf;
-      const int n = i / a.buf.T, t = i - n * a.buf.T;
-      const size_t src = (size_t)t * a.buf.N + n;
-      ret = __ldg(a.buf.ret + src);
-      if (h.clip_value_loss) val_old = __ldg(a.buf.val + src);
-      {
-        const float* op = a.buf.obs + src * a.obs_dim;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k < a.obs_dim) o[k] = __ldg(op + k);
-      }
-      if (g0) {
-        if (a.is_box) act_f = __ldg((const float*)a.buf.act + src);
-        else act_i = __ldg((const int32_t*)a.buf.act + src);
-        logp_old = __ldg(a.buf.logp + src);
-        A = __ldg(a.buf.adv + src);  // raw; normalised where it is used
-      }
+      for (int k = 0; k < 8; ++k) cp_async4(obs_s + m * 8 + k, op + (k < a.obs_dim ? k : 0), ok && k < a.obs_dim);
     }
+    valid_s[m] = ok ? 1 : 0;
   };
-  if (worker) {
-    load_idx(lane < 16 ? (int)blockIdx.x : (int)(blockIdx.x + gridDim.x));
-    load_data();
-    if (lane >= 16) load_idx((int)(blockIdx.x + 2 * gridDim.x));
+  auto gather_idx = [&](int t) {  // minibatch indices of tile t -> idx_s
+    const bool ok = tile_row_ok(t);
+    cp_async4(idx_s + m, a.idx + (ok ? (long long)t * ROWS + m : 0), ok);
+  };
+  auto gather_commit = []() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+  auto gather_wait = []() { asm volatile("cp.async.wait_group 0;" ::: "memory"); };
+  if (g0 && !active) {  // first tile: the only register load of an index
+    const int t0 = (int)blockIdx.x;
+    const bool ok = tile_row_ok(t0);
+    const int i = ok ? __ldg(a.idx + (long long)t0 * ROWS + m) : 0;
+    gather_rows(i, ok);
+    gather_idx(t0 + (int)gridDim.x);
+    gather_commit();
+    gather_wait();
   }
+  __syncthreads();
 
+  auto store_xobs = [&](const tc::Mat& xo) {
+    float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o[8];
+    const float4 lo4 = *reinterpret_cast<const float4*>(obs_s + m * 8), hi4 = *reinterpret_cast<const float4*>(obs_s + m * 8 + 4);
+    o[0] = lo4.x; o[1] = lo4.y; o[2] = lo4.z; o[3] = lo4.w; o[4] = hi4.x; o[5] = hi4.y; o[6] = hi4.z; o[7] = hi4.w;
+    tc::store8(xo, 0, m, o);
+    tc::store8(xo, 1, m, z8);
+  };
   int tile_parity = 0;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const tc::Mat& XOBS = XOBS2[tile_parity];
     tile_parity ^= 1;
-    if (g0) {
-      if (active) {
-        float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        tc::store8(XOBS, 0, m, o);
-        tc::store8(XOBS, 1, m, z8);
-      }
-    }
+    if (g0 && active) store_xobs(XOBS);
+    const bool valid = g0 && active && valid_s[m] != 0;  // this thread owns a real row of the minibatch
 
     // ---------------------------------------------------------------- encoder forward
     uint32_t mk_h1 = 0, mk_h2 = 0, mk_b1 = 0, mk_b2 = 0, mk_none = 0;
     // encoder layer 0 (d <= 8 inputs) on the FMA pipe, straight from the gathered observation: no MMA round
-    // trip.  The fragment rows' observations come from the row-owner lanes by shuffle.
+    // trip.  The fragment rows' observations come from the fp32 staging written by the gathering lanes.
     if (worker) {
       const int l0 = lane >> 2, l1 = l0 + 8;
       float v[8];
@@ -417,10 +435,25 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
         v[0] = b0.x; v[1] = b0.y; v[2] = b0.x; v[3] = b0.y; v[4] = b1.x; v[5] = b1.y; v[6] = b1.x; v[7] = b1.y;
       }
       const float* w0p = fp + tc::F_W0;
+      float xa[8], xb[8];
+      {
+        const float4* p0 = reinterpret_cast<const float4*>(obs_s + (q * 16 + l0) * 8);
+        const float4* p1 = reinterpret_cast<const float4*>(obs_s + (q * 16 + l1) * 8);
+        const float4 a0 = p0[0], b0 = p1[0];
+        xa[0] = a0.x; xa[1] = a0.y; xa[2] = a0.z; xa[3] = a0.w;
+        xb[0] = b0.x; xb[1] = b0.y; xb[2] = b0.z; xb[3] = b0.w;
+        if (a.obs_dim > 4) {
+          const float4 a1 = p0[1], b1 = p1[1];
+          xa[4] = a1.x; xa[5] = a1.y; xa[6] = a1.z; xa[7] = a1.w;
+          xb[4] = b1.x; xb[5] = b1.y; xb[6] = b1.z; xb[7] = b1.w;
+        } else {
+          xa[4] = xa[5] = xa[6] = xa[7] = xb[4] = xb[5] = xb[6] = xb[7] = 0.f;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         if (k < a.obs_dim) {
-          const float x0 = __shfl_sync(0xffffffffu, o[k], l0), x1 = __shfl_sync(0xffffffffu, o[k], l1);
+          const float x0 = xa[k], x1 = xb[k];
           const float wa = w0p[fc * 8 + k], wb = w0p[(fc + 1) * 8 + k], wc = w0p[(fc + 8) * 8 + k], wd = w0p[(fc + 9) * 8 + k];
           v[0] = fmaf(wa, x0, v[0]); v[1] = fmaf(wb, x0, v[1]); v[2] = fmaf(wa, x1, v[2]); v[3] = fmaf(wb, x1, v[3]);
           v[4] = fmaf(wc, x0, v[4]); v[5] = fmaf(wd, x0, v[5]); v[6] = fmaf(wc, x1, v[6]); v[7] = fmaf(wd, x1, v[7]);
@@ -492,11 +525,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     };
     bool bad = false;
     if (worker) {
-      // the row scalars live in lanes 0-15 (lane = row of the quadrant); fragment rows fetch them by shuffle
-      const int l0 = lane >> 2, l1 = l0 + 8;
-      const float ret0 = __shfl_sync(0xffffffffu, ret, l0), ret1 = __shfl_sync(0xffffffffu, ret, l1);
-      const float vo0 = __shfl_sync(0xffffffffu, val_old, l0), vo1 = __shfl_sync(0xffffffffu, val_old, l1);
-      const bool va0 = __shfl_sync(0xffffffffu, (int)valid, l0) != 0, va1 = __shfl_sync(0xffffffffu, (int)valid, l1) != 0;
+      // the fragment rows' scalars come from the staging written by the gathering lanes
+      const float ret0 = rows_s[R_RET * ROWS + fr0], ret1 = rows_s[R_RET * ROWS + fr1];
+      const float vo0 = rows_s[R_VAL * ROWS + fr0], vo1 = rows_s[R_VAL * ROWS + fr1];
+      const bool va0 = valid_s[fr0] != 0, va1 = valid_s[fr1] != 0;
       float sv_unused;
       const float dv0 = value_grad(value_of(fr0), ret0, vo0, va0, sv_unused);
       const float dv1 = value_grad(value_of(fr1), ret1, vo1, va1, sv_unused);
@@ -509,7 +541,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       frag_store(DY64, v, false);
       if (g0 && active) {
         float sv;
-        const float dvalue = value_grad(value, ret, val_old, valid, sv);
+        const float dvalue = value_grad(value, rows_s[R_RET * ROWS + m], rows_s[R_VAL * ROWS + m], valid, sv);
         if (valid) {
           bad = !isfinite(value);
           s_val += (double)sv;
@@ -563,12 +595,14 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       float dhead[LRX_MAX_NOUT];
 #pragma unroll
       for (int o2 = 0; o2 < LRX_MAX_NOUT; ++o2) dhead[o2] = 0.f;
-      if (valid && active) {
+      if (valid) {
+        const int act_raw = reinterpret_cast<const int*>(rows_s)[R_ACT * ROWS + m];  // fp32 (Box) or int32 (Discrete) bits
+        const float logp_old = rows_s[R_LOGP * ROWS + m], A = rows_s[R_ADV * ROWS + m];
         float logp, entropy, z_n = 0.f;
         float lp[LRX_MAX_NOUT], pr[LRX_MAX_NOUT];
         if (a.is_box) {
           const float loc = head[0];
-          z_n = (act_f - loc) / scale;
+          z_n = (__int_as_float(act_raw) - loc) / scale;
           logp = -0.5f * (z_n * z_n) - (LRX_HALF_LOG_2PI + log_scale);
           entropy = 0.5f + LRX_HALF_LOG_2PI + log_scale;
         } else {
@@ -582,7 +616,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
             if (j < n_out) {
               pr[j] = expf(lp[j]);
               entropy -= pr[j] * lp[j];
-              if (j == act_i) logp = lp[j];
+              if (j == act_raw) logp = lp[j];
             }
           }
         }
@@ -614,7 +648,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
           for (int j = 0; j < LRX_MAX_NOUT; ++j) {
             if (j < n_out) {
               const float dH = -pr[j] * (lp[j] + entropy);
-              dhead[j] = dlogp * ((j == act_i ? 1.f : 0.f) - pr[j]) + (-ch * invB) * dH;
+              dhead[j] = dlogp * ((j == act_raw ? 1.f : 0.f) - pr[j]) + (-ch * invB) * dH;
             }
           }
         }
@@ -650,6 +684,13 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
          });
 
     // ---------------------------------------------------------------- encoder backward
+    // every GEMM that reads DY8 and every reader of the row planes is done: gather the next tile's rows
+    if (g0 && !active) {
+      const int i = idx_s[m];
+      gather_rows(i, tile_row_ok(tile + (int)gridDim.x));
+      gather_idx(tile + 2 * (int)gridDim.x);
+      gather_commit();
+    }
     if (worker) quarter16(C_DF, nullptr, DY16);                   // background reads DY64 / XF only
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY16, W2, 64, 64, 1, 0u); },
          [&](bool ld) {
@@ -663,31 +704,13 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
            tc::gemm<true, true, 3, 1>(ld, tb + C_G1 + 64, DY64, ONES, 64, 8, 4, 1u);
          });
     if (worker) frag_bwd(C_D0, mk_h1, DY64, true);   // background GEMMs read DY64
+    // the next tile's rows have had three steps to arrive; the barrier of the step below publishes them
+    if (g0 && !active) gather_wait();
     step(none, [&](bool ld) {
       tc::gemm<true, true>(ld, tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
       tc::gemm<true, true, 3, 1>(ld, tb + C_G0 + 16, DY64, ONES, 64, 8, 4, 1u);
     });
 
-    // hand the prefetched rows down to lanes 0-15; lanes 16-31 fetch the tile after next
-    if (worker) {
-      const unsigned full = 0xffffffffu;
-      const float s_actf = __shfl_down_sync(full, act_f, 16), s_lp = __shfl_down_sync(full, logp_old, 16);
-      const float s_A = __shfl_down_sync(full, A, 16), s_ret = __shfl_down_sync(full, ret, 16);
-      const float s_vo = __shfl_down_sync(full, val_old, 16);
-      const int s_acti = __shfl_down_sync(full, act_i, 16);
-      const int s_valid = __shfl_down_sync(full, (int)valid, 16);
-      float so[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) so[k] = __shfl_down_sync(full, o[k], 16);
-      if (active) {
-        act_f = s_actf; logp_old = s_lp; A = s_A; ret = s_ret; val_old = s_vo; act_i = s_acti; valid = s_valid != 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = so[k];
-      } else {
-        load_data();                               // tile + 2 * grid: its index was fetched one tile ago
-        load_idx(tile + 3 * (int)gridDim.x);
-      }
-    }
   }
   if (worker) {
     wait_crit();

@@ -65,6 +65,15 @@ s = s.replace('''  LRX_LAUNCH_CHECK();
     --prof_left;
   }
   lrx_launch_reduce_partials(''', 1)
+# marks inside the tile-start section (slots 12, 13: cycles since the last step entry)
+s = s.replace('''    tile_parity ^= 1;
+''', '''    tile_parity ^= 1;
+    pf_t[12] += clock64() - pf_last;
+''')
+s = s.replace('''      mk_h1 = 0;
+''', '''      pf_t[13] += clock64() - pf_last;
+      mk_h1 = 0;
+''')
 tmp = "/tmp/lrx_update_fused_prof.cu"
 open(tmp, "w").write(s)
 nv = "/usr/local/cuda/bin/nvcc"
