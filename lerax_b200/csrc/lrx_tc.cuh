@@ -179,10 +179,18 @@ __device__ __forceinline__ void stage_weight(const float* __restrict__ W, int ou
   for (int e = tid; e < out * chunks; e += nthreads) {
     const int o = e % out, ch = e / out;
     float v[8];
+    const float* src = W + (size_t)o * in + ch * 8;
+    if (ch * 8 + 8 <= in && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      // one 32-byte sector per lane in two requests: eight scalar loads per lane hit eight times as many sectors
+      // at once as the (mostly carved-out) L1 can hold, and the staging is on every minibatch's critical path
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = ch * 8 + j;
-      v[j] = i < in ? __ldg(W + (size_t)o * in + i) : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const int i = ch * 8 + j;
+        v[j] = i < in ? __ldg(src + j) : 0.f;
+      }
     }
     store8(dst, ch, o, v);
   }
@@ -255,44 +263,6 @@ __device__ __forceinline__ void stage_f32(const float* __restrict__ params, cons
     }
     fp[i] = v;
   }
-}
-
-// All six MMA weights of the default policy in one pass: every thread first issues the loads of all its 8-wide
-// chunks (1536 chunks in total), then splits and stores them, so the staging costs one memory latency instead of
-// one per matrix (it is on the critical path of every minibatch launch of the update kernel).
-template <int NTHREADS>
-__device__ __forceinline__ void stage_default_weights(const float* __restrict__ params, const LayerOffsets& lo,
-                                                      const Mat& W1, const Mat& W2, const Mat& WV0, const Mat& WV1,
-                                                      const Mat& WA0, const Mat& WA1, int tid) {
-  constexpr int TOTAL = 1536, ITERS = (TOTAL + NTHREADS - 1) / NTHREADS;
-  float v[ITERS][8];
-  Mat dst[ITERS];
-  bool live[ITERS];
-  int orow[ITERS], chunk[ITERS];
-#pragma unroll
-  for (int it = 0; it < ITERS; ++it) {
-    const int e = tid + it * NTHREADS;
-    const float* W = params;
-    int local = 0, out = 64, in = 64;
-    live[it] = e < TOTAL;
-    dst[it] = W1;
-    if (e < 512) { W += lo.w[L_ENC1]; local = e; }
-    else if (e < 1024) { W += lo.w[L_V1]; local = e - 512; dst[it] = WV1; }
-    else if (e < 1152) { W += lo.w[L_ENC2]; local = e - 1024; out = 16; dst[it] = W2; }
-    else if (e < 1280) { W += lo.w[L_A1]; local = e - 1152; out = 16; dst[it] = WA1; }
-    else if (e < 1408) { W += lo.w[L_V0]; local = e - 1280; in = 16; dst[it] = WV0; }
-    else if (e < TOTAL) { W += lo.w[L_A0]; local = e - 1408; in = 16; dst[it] = WA0; }
-    orow[it] = local % out;
-    chunk[it] = local / out;
-    if (live[it]) {
-      const float* src = W + (size_t)orow[it] * in + chunk[it] * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[it][j] = __ldg(src + j);
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < ITERS; ++it)
-    if (live[it]) store8(dst[it], chunk[it], orow[it], v[it]);
 }
 
 }  // namespace tc

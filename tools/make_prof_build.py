@@ -29,8 +29,6 @@ s = s.replace('''  if (warp == 0) umma::tmem_dealloc(tb, TMEM_COLS);
 }''')
 s = s.replace('''  // ------------------------------------------------------------------ flush the gradient partial''', '''  const long long pf_k2 = clock64();
   // ------------------------------------------------------------------ flush the gradient partial''')
-s = s.replace('''    // hand the prefetched rows down to lanes 0-15; lanes 16-31 fetch the tile after next''', '''    pf_i = 0;
-    // hand the prefetched rows down to lanes 0-15; lanes 16-31 fetch the tile after next''')
 s = s.replace('''  // ------------------------------------------------------------------ flush the gradient partial''', '''  if (blockIdx.x == 0 && (tid == 128 || tid == 0 || tid == 512) && a.prof) {
     long long* o = a.prof + (tid == 0 ? 0 : tid == 128 ? 20 : 40);
     for (int i = 0; i < 20; ++i) o[i] = pf_t[i];
@@ -61,19 +59,32 @@ s = s.replace('''  LRX_LAUNCH_CHECK();
       for (int i = 0; i < 14; ++i) { fprintf(stderr, " %lld", hp[20 * w + i] / tiles0); tot += hp[20 * w + i] / tiles0; }
       fprintf(stderr, "  | total %lld\\n", tot);
     }
-    fprintf(stderr, "[fused prof] block 0: prologue %lld, loop %lld, tail %lld cycles; tiles %d\\n", hp[15], hp[16], hp[17], tiles0);
+    fprintf(stderr, "[fused prof] block 0: prologue %lld, loop %lld, tail %lld cycles; tiles %d; prologue parts: weights %lld, fp32 %lld, alloc+barrier %lld\\n", hp[15], hp[16], hp[17], tiles0, hp[18], hp[19], hp[14]);
     --prof_left;
   }
   lrx_launch_reduce_partials(''', 1)
 # marks inside the tile-start section (slots 12, 13: cycles since the last step entry)
 s = s.replace('''    tile_parity ^= 1;
 ''', '''    tile_parity ^= 1;
+    pf_i = 0;
     pf_t[12] += clock64() - pf_last;
 ''')
 s = s.replace('''      mk_h1 = 0;
 ''', '''      pf_t[13] += clock64() - pf_last;
       mk_h1 = 0;
 ''')
+# prologue marks (block 0, thread 0): after the weight staging, the fp32 block, the TMEM allocation barrier
+s = s.replace('''  tc::stage_f32(a.params, a.lo, n_out, a.obs_dim, fp, tid, THREADS);
+''', '''  const long long pm0 = clock64();
+  tc::stage_f32(a.params, a.lo, n_out, a.obs_dim, fp, tid, THREADS);
+  const long long pm1 = clock64();
+''')
+s = s.replace('''  const uint32_t tb = *tslot;
+''', '''  const long long pm2 = clock64();
+  const uint32_t tb = *tslot;
+''')
+s = s.replace('''a.prof[17] = clock64() - pf_k2; }''', '''a.prof[17] = clock64() - pf_k2; a.prof[18] = pm0 - pf_k0; a.prof[19] = pm1 - pm0; a.prof[14] = pm2 - pm1; }''')
+s = s.replace('''cycles; tiles %d\\\\n", hp[15], hp[16], hp[17], tiles0);''', '''cycles; tiles %d; prologue parts: weights %lld, fp32 %lld, alloc+barrier %lld\\\\n", hp[15], hp[16], hp[17], tiles0, hp[18], hp[19], hp[14]);''')
 tmp = "/tmp/lrx_update_fused_prof.cu"
 open(tmp, "w").write(s)
 nv = "/usr/local/cuda/bin/nvcc"
