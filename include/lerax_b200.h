@@ -269,6 +269,9 @@ int lrx_debug_umma_time_bf16(const float* A, const float* B, float* dump, int32_
 
 /* Dispatch-rate probe: 256 back-to-back MMAs with constant descriptors over `dsplit` accumulators. */
 int lrx_debug_umma_rate(int32_t M, int32_t N, int32_t dsplit, long long* cycles, lrx_stream_t stream);
+/* Latency of tcgen05.ld from one TMEM region while n_mma MMAs accumulate into another (cycles[0..7] per load,
+ * cycles[8] until the MMA batch completes).  dsplit bits 8 / 9 of lrx_debug_umma_rate select MN-major A / B. */
+int lrx_debug_tmem_ld_under_mma(int32_t n_mma, long long* cycles, lrx_stream_t stream);
 
 /* Decode of the tcgen05.ld 16x256b.x2 fragment shape: dump [128 threads][8 registers]. */
 int lrx_debug_tmem_shape_probe(float* dump, lrx_stream_t stream);

@@ -93,6 +93,7 @@ PROTOTYPES = {
     "lrx_debug_umma_time_bf16": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _P(C.c_int32),
                                            C.c_int32, C.c_int32, _vp, _vp]),
     "lrx_debug_umma_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
+    "lrx_debug_tmem_ld_under_mma": (C.c_int, [C.c_int32, _vp, _vp]),
     "lrx_debug_tmem_shape_probe": (C.c_int, [_vp, _vp]),
     "lrx_debug_set_fused": (None, [C.c_int]),
     "lrx_debug_tmem_operand_probe": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp]),

@@ -361,7 +361,7 @@ extern "C" int lrx_debug_umma_time_bf16(const float* A, const float* B, float* d
 // 256 back-to-back tcgen05.mma with CONSTANT descriptors (no per-instruction arithmetic) rotating
 // over DS independent accumulators: the tensor pipe's own cost per instruction for small shapes.
 template <int DS>
-__global__ void __launch_bounds__(128) umma_rate_kernel(int M, int N, long long* cycles_out) {
+__global__ void __launch_bounds__(128) umma_rate_kernel(int M, int N, int a_mn, int b_mn, long long* cycles_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -379,9 +379,12 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int M, int N, long long*
   const uint32_t tbase = tmem_slot;
   if (warp == 0) {
     const bool leader = umma::elect_one();
-    const uint32_t idesc = umma::idesc_bf16(M, N, 0, 0);
-    const uint64_t ad = umma::smem_desc(umma::smem_u32(smem), (uint32_t)M * 16u, 128u);
-    const uint64_t bd = umma::smem_desc(umma::smem_u32(smem) + 8192u, (uint32_t)N * 16u, 128u);
+    // K-major view: LBO = rows * 16, SBO = 128; MN-major view of the same canonical bytes: LBO = 128, SBO = rows * 16
+    const uint32_t idesc = umma::idesc_bf16(M, N, a_mn, b_mn);
+    const uint64_t ad = a_mn ? umma::smem_desc(umma::smem_u32(smem), 128u, (uint32_t)M * 16u)
+                             : umma::smem_desc(umma::smem_u32(smem), (uint32_t)M * 16u, 128u);
+    const uint64_t bd = b_mn ? umma::smem_desc(umma::smem_u32(smem) + 8192u, 128u, (uint32_t)N * 16u)
+                             : umma::smem_desc(umma::smem_u32(smem) + 8192u, (uint32_t)N * 16u, 128u);
     const long long t0 = clock64();
 #pragma unroll 1
     for (int rep = 0; rep < 16; ++rep) {
@@ -406,10 +409,82 @@ extern "C" int lrx_debug_umma_rate(int32_t M, int32_t N, int32_t dsplit, long lo
               LRX_ERR_INVALID_ARG, "lrx_debug_umma_rate: bad argument");
   const size_t smem = 16384;
   cudaStream_t s = (cudaStream_t)stream;
-  if (dsplit == 1) umma_rate_kernel<1><<<1, 128, smem, s>>>(M, N, cycles);
-  else if (dsplit == 2) umma_rate_kernel<2><<<1, 128, smem, s>>>(M, N, cycles);
-  else if (dsplit == 4) umma_rate_kernel<4><<<1, 128, smem, s>>>(M, N, cycles);
-  else umma_rate_kernel<8><<<1, 128, smem, s>>>(M, N, cycles);
+  const int a_mn = (dsplit >> 8) & 1, b_mn = (dsplit >> 9) & 1;  // operand majorness rides in the upper bits
+  dsplit &= 0xff;
+  if (dsplit == 1) umma_rate_kernel<1><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles);
+  else if (dsplit == 2) umma_rate_kernel<2><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles);
+  else if (dsplit == 4) umma_rate_kernel<4><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles);
+  else umma_rate_kernel<8><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+// ------------------------------------------------------------------ tcgen05.ld latency under MMA load
+// Warp 0 enqueues n_mma MMAs (M = 64, N = 64, accumulating into TMEM columns 0-63) and commits; then warps 0-3
+// time eight tcgen05.ld + wait::ld of ANOTHER TMEM region (columns 256+).  cycles[0..7] = latency of the k-th load
+// of warp 1, cycles[8] = cycles until the MMA batch's mbarrier completes (from the first load).
+__global__ void __launch_bounds__(128) tmem_ld_under_mma_kernel(int n_mma_signed, long long* cycles_out) {
+  const bool acc_first = (n_mma_signed >= 10000);  // +10000: the first MMA accumulates too (onto uninitialised TMEM)
+  if (acc_first) n_mma_signed -= 10000;
+  const int n_mma = n_mma_signed < 0 ? -n_mma_signed : n_mma_signed;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = umma::warp_idx_sync();
+  for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3F803F80u;
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  if (warp == 0) {
+    const bool leader = umma::elect_one();
+    const uint32_t idesc = umma::idesc_bf16(64, 64, 0, 0);
+    const uint64_t ad = umma::smem_desc(umma::smem_u32(smem), 64u * 16u, 128u);
+    const uint64_t bd = umma::smem_desc(umma::smem_u32(smem) + 8192u, 64u * 16u, 128u);
+#pragma unroll 1
+    for (int i = 0; i < n_mma; ++i)
+      if (leader) umma::mma_f16(tbase, ad, bd, idesc, (i > 0 || acc_first) ? 1u : 0u);
+    if (leader) umma::mma_commit(&bar);
+    __syncwarp();
+  }
+  __syncthreads();
+  // n_mma < 0: load the ACCUMULATOR itself (columns 0-63) without waiting for the commit: cycles[9] = the value read
+  // (every MMA adds 16 to each element), to see whether the load is ordered behind the queued MMAs' writes
+  const bool own = n_mma_signed < 0;
+  const uint32_t tw = umma::tmem_addr(tbase, warp * 32, own ? 0 : 256);
+  long long lat[8];
+  float first = 0.f;
+  const long long t_start = clock64();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long long t0 = clock64();
+    float v[8];
+    umma::tmem_ld_frag16(tw + (own ? 16 * (k & 3) : 16 * k), v);
+    umma::tmem_ld_wait();
+    if (k == 0) first = v[0];
+    lat[k] = clock64() - t0 + (long long)(v[0] == 12345.f);
+  }
+  if (n_mma > 0) umma::mbar_wait(&bar, 0);
+  const long long t_done = clock64() - t_start;
+  if (threadIdx.x == 32) {
+    for (int k = 0; k < 8; ++k) cycles_out[k] = lat[k];
+    cycles_out[8] = t_done;
+    cycles_out[9] = (long long)first;
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+
+extern "C" int lrx_debug_tmem_ld_under_mma(int32_t n_mma, long long* cycles, lrx_stream_t stream) {
+  LRX_REQUIRE(cycles && n_mma >= -4096 && n_mma <= 14096, LRX_ERR_INVALID_ARG, "lrx_debug_tmem_ld_under_mma: bad argument");
+  tmem_ld_under_mma_kernel<<<1, 128, 16384, (cudaStream_t)stream>>>(n_mma, cycles);
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }

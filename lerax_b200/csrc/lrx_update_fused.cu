@@ -328,13 +328,25 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     frag_store(dst, v, false);
   };
   // dX fragment masked by the ReLU of the layer that produced X -> operand dY
-  auto frag_bwd = [&](uint32_t col, uint32_t mask, const tc::Mat& dst, bool need_bg) {
+  // Bias gradients of the five 64-wide layers: every thread sums the dY values of its fragment (two rows x four
+  // columns) over all tiles in registers; the cross-thread reduction happens once, at the flush.  As 12 extra
+  // MMAs per layer and tile (dY^T x ones) they only lengthened the queue the epilogues' TMEM loads wait behind.
+  float bs_e0[4] = {0.f, 0.f, 0.f, 0.f}, bs_e1[4] = {0.f, 0.f, 0.f, 0.f}, bs_v0[4] = {0.f, 0.f, 0.f, 0.f};
+  float bs_v1[4] = {0.f, 0.f, 0.f, 0.f}, bs_a0[4] = {0.f, 0.f, 0.f, 0.f};
+  auto bias_add = [](float* bsum, const float* v) {
+    bsum[0] += v[0] + v[2];
+    bsum[1] += v[1] + v[3];
+    bsum[2] += v[4] + v[6];
+    bsum[3] += v[5] + v[7];
+  };
+  auto frag_bwd = [&](uint32_t col, uint32_t mask, const tc::Mat& dst, bool need_bg, float* bsum) {
     wait_crit();
     float v[8];
     umma::tmem_ld_frag16(tw + col + cg, v);
     umma::tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = ((mask >> j) & 1u) ? v[j] : 0.f;
+    bias_add(bsum, v);
     frag_store(dst, v, need_bg);
   };
   auto nopf = [](float*) {};
@@ -538,6 +550,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       float v[8] = {dv0 * w0.x, dv0 * w0.y, dv1 * w0.x, dv1 * w0.y, dv0 * w1.x, dv0 * w1.y, dv1 * w1.x, dv1 * w1.y};
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = ((mk_b2 >> j) & 1u) ? v[j] : 0.f;
+      bias_add(bs_v1, v);
       frag_store(DY64, v, false);
       if (g0 && active) {
         float sv;
@@ -553,17 +566,15 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, WV1, 64, 64, 4, 0u); },        // dX = dY W
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_GV1, DY64, XB1, 64, 64, 4, 1u);                        // dW^T[out][in] += dY^T X
-           tc::gemm<true, true, 3, 1>(ld, tb + C_GV1 + 64, DY64, ONES, 64, 8, 4, 1u);             // db_v1
            tc::gemm<true, true>(ld, tb + C_GV2, XB2, DY8, 64, 8, 4, 1u);                          // dW_v2[in] += X^T dvalue
            tc::gemm<true, true, 1, 3>(ld, tb + C_GBV2, ONES, DY8, 64, 8, 4, 1u);                  // db_v2
          });
-    if (worker) frag_bwd(C_D0, mk_b1, DY64, true);  // background GEMMs read DY64
+    if (worker) frag_bwd(C_D0, mk_b1, DY64, true, bs_v0);  // background GEMMs read DY64
     // all background: d(features) from the value head and the layer-0 gradients; nothing below touches
     // DY64 / XF / C_DF / C_GV0 before these are waited for at the next step
     step(none, [&](bool ld) {
       tc::gemm<false, true>(ld, tb + C_DF, DY64, WV0, 64, 16, 4, 0u);
       tc::gemm<true, true>(ld, tb + C_GV0, DY64, XF, 64, 16, 4, 1u);
-      tc::gemm<true, true, 3, 1>(ld, tb + C_GV0 + 16, DY64, ONES, 64, 8, 4, 1u);
     });
 
     // ---------------------------------------------------------------- action head forward
@@ -676,11 +687,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
            tc::gemm<true, true>(ld, tb + C_GMAP, XA2, DY8, 64, 8, 4, 1u);                         // dW_map[in (16 valid)][out]
            tc::gemm<true, true, 1, 3>(ld, tb + C_GBMAP, ONES, DY8, 64, 8, 4, 1u);
          });
-    if (worker) frag_bwd(C_D0, mk_b1, DY64, false);  // this step's background GEMMs do not read DY64
+    if (worker) frag_bwd(C_D0, mk_b1, DY64, false, bs_a0);  // this step's background GEMMs do not read DY64
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_DF, DY64, WA0, 64, 16, 4, 1u); },        // d(features) += action head
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_GA0, DY64, XF, 64, 16, 4, 1u);
-           tc::gemm<true, true, 3, 1>(ld, tb + C_GA0 + 16, DY64, ONES, 64, 8, 4, 1u);
          });
 
     // ---------------------------------------------------------------- encoder backward
@@ -697,18 +707,16 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
            tc::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
            tc::gemm<true, true, 1, 3>(ld, tb + C_GB2, ONES, DY16, 64, 16, 4, 1u);
          });
-    if (worker) frag_bwd(C_D0, mk_h2, DY64, false);  // background reads XH2 / DY16 only
+    if (worker) frag_bwd(C_D0, mk_h2, DY64, false, bs_e1);  // background reads XH2 / DY16 only
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, W1, 64, 64, 4, 0u); },
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_G1, DY64, XH1, 64, 64, 4, 1u);
-           tc::gemm<true, true, 3, 1>(ld, tb + C_G1 + 64, DY64, ONES, 64, 8, 4, 1u);
          });
-    if (worker) frag_bwd(C_D0, mk_h1, DY64, true);   // background GEMMs read DY64
+    if (worker) frag_bwd(C_D0, mk_h1, DY64, true, bs_e0);   // background GEMMs read DY64
     // the next tile's rows have had three steps to arrive; the barrier of the step below publishes them
     if (g0 && !active) gather_wait();
     step(none, [&](bool ld) {
       tc::gemm<true, true>(ld, tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
-      tc::gemm<true, true, 3, 1>(ld, tb + C_G0 + 16, DY64, ONES, 64, 8, 4, 1u);
     });
 
   }
@@ -720,20 +728,16 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   // ------------------------------------------------------------------ flush the gradient partial
   float* part = a.partial + (size_t)blockIdx.x * a.partial_stride;
   const tc::LayerOffsets& lo = a.lo;
-  // dW^T accumulators: TMEM row = output unit (this thread's m), columns = inputs then bias
+  // dW^T accumulators: TMEM row = output unit (this thread's m), columns = inputs (the bias comes from registers)
   auto flush_T = [&](uint32_t col, int in_real, int in_pad, int layer) {
-    for (int c0 = 0; c0 < in_pad + 8; c0 += 8) {
+    for (int c0 = 0; c0 < in_pad; c0 += 8) {
       float v[8];
       umma::tmem_ld8(tw + col + c0, v);
       umma::tmem_ld_wait();
       if (active) {
-        if (c0 < in_pad) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (c0 + j < in_real) part[lo.w[layer] + m * in_real + c0 + j] = v[j];
-        } else {
-          part[lo.b[layer] + m] = v[0];
-        }
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < in_real) part[lo.w[layer] + m * in_real + c0 + j] = v[j];
       }
     }
   };
@@ -762,6 +766,32 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   if (worker && g == 1) { flush_T(C_G1, 64, 64, tc::L_ENC1); flush_N(C_GV2, C_GBV2, 64, 1, 8, tc::L_V2); }
   if (worker && g == 2) { flush_T(C_GV1, 64, 64, tc::L_V1); flush_T(C_GV0, 16, 16, tc::L_V0); }
   if (worker && g == 3) { flush_T(C_GA0, 16, 16, tc::L_A0); flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1); }
+
+  // ------------------------------------------------------------------ register bias sums (fixed order)
+  __syncthreads();  // every GEMM is done and waited for: XH1 is free
+  {
+    float* bsh = reinterpret_cast<float*>(smem + OFF_XH1);  // [5 layers][4 quadrants][64 columns]
+    float* const bsv[5] = {bs_e0, bs_e1, bs_v0, bs_v1, bs_a0};
+    if (worker) {
+#pragma unroll
+      for (int l = 0; l < 5; ++l) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x = bsv[l][j];  // rows lane/4 and lane/4 + 8 of the quadrant -> all 16 rows
+          x += __shfl_xor_sync(0xffffffffu, x, 4);
+          x += __shfl_xor_sync(0xffffffffu, x, 8);
+          x += __shfl_xor_sync(0xffffffffu, x, 16);
+          if (lane < 4) bsh[(l * 4 + q) * 64 + fc + (j & 1) + (j >> 1) * 8] = x;
+        }
+      }
+    }
+    __syncthreads();
+    const int bl[5] = {tc::L_ENC0, tc::L_ENC1, tc::L_V0, tc::L_V1, tc::L_A0};
+    for (int e = tid; e < 5 * 64; e += THREADS) {
+      const int l = e >> 6, c = e & 63;
+      part[lo.b[bl[l]] + c] = ((bsh[(l * 4 + 0) * 64 + c] + bsh[(l * 4 + 1) * 64 + c]) + bsh[(l * 4 + 2) * 64 + c]) + bsh[(l * 4 + 3) * 64 + c];
+    }
+  }
 
   // ------------------------------------------------------------------ loss statistics (fixed order)
   __syncthreads();
