@@ -327,12 +327,30 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     fn(v);
     frag_store(dst, v, false);
   };
+  // the same without the operand store: the activated fragment stays in registers (value head layer 2, whose only
+  // consumers -- the 64 -> 1 output layer and its weight gradient -- run on the FMA pipe)
+  auto frag_fwd_keep = [&](uint32_t col, const float* bias, uint32_t& mask, float* v) {
+    wait_crit();
+    umma::tmem_ld_frag16(tw + col + cg, v);
+    umma::tmem_ld_wait();
+    const float2 b0 = *reinterpret_cast<const float2*>(bias + fc), b1 = *reinterpret_cast<const float2*>(bias + fc + 8);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.x; v[3] += b0.y;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.x; v[7] += b1.y;
+    mask = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (v[j] > 0.f) mask |= (1u << j);
+      v[j] = fmaxf(v[j], 0.f);
+    }
+  };
   // dX fragment masked by the ReLU of the layer that produced X -> operand dY
   // Bias gradients of the five 64-wide layers: every thread sums the dY values of its fragment (two rows x four
   // columns) over all tiles in registers; the cross-thread reduction happens once, at the flush.  As 12 extra
   // MMAs per layer and tile (dY^T x ones) they only lengthened the queue the epilogues' TMEM loads wait behind.
   float bs_e0[4] = {0.f, 0.f, 0.f, 0.f}, bs_e1[4] = {0.f, 0.f, 0.f, 0.f}, bs_v0[4] = {0.f, 0.f, 0.f, 0.f};
   float bs_v1[4] = {0.f, 0.f, 0.f, 0.f}, bs_a0[4] = {0.f, 0.f, 0.f, 0.f};
+  // value output layer (64 -> 1): weight gradient of this thread's four columns and (one thread per row) the bias
+  float gw_v2[4] = {0.f, 0.f, 0.f, 0.f}, gb_v2 = 0.f;
   auto bias_add = [](float* bsum, const float* v) {
     bsum[0] += v[0] + v[2];
     bsum[1] += v[1] + v[3];
@@ -489,14 +507,16 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
          [&](bool ld) { tc::gemm<false, false>(ld, tb + C_D1, XF, WA0, 64, 64, 1, 0u); });  // action head layer 1, consumed later
     if (worker) frag_fwd(C_D0, fp + tc::F_BV0, XB1, mk_b1, nopf);
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XB1, WV1, 64, 64, 4, 0u); }, none);
+    float xb2[8];  // value layer-2 activations of this thread's fragment
     if (worker) {
-      float pr0 = 0.f, pr1 = 0.f;  // partial value-head dot products of rows fr0, fr1 over this thread's 4 columns
-      frag_fwd(C_D0, fp + tc::F_BV1, XB2, mk_b2, [&](float* v) {
+      float pr0, pr1;  // partial value-head dot products of rows fr0, fr1 over this thread's 4 columns
+      frag_fwd_keep(C_D0, fp + tc::F_BV1, mk_b2, xb2);
+      {
         const float2 w0 = *reinterpret_cast<const float2*>(fp + tc::F_WV2 + fc);
         const float2 w1 = *reinterpret_cast<const float2*>(fp + tc::F_WV2 + fc + 8);
-        pr0 = fmaf(w1.y, v[5], fmaf(w1.x, v[4], fmaf(w0.y, v[1], w0.x * v[0])));
-        pr1 = fmaf(w1.y, v[7], fmaf(w1.x, v[6], fmaf(w0.y, v[3], w0.x * v[2])));
-      });
+        pr0 = fmaf(w1.y, xb2[5], fmaf(w1.x, xb2[4], fmaf(w0.y, xb2[1], w0.x * xb2[0])));
+        pr1 = fmaf(w1.y, xb2[7], fmaf(w1.x, xb2[6], fmaf(w0.y, xb2[3], w0.x * xb2[2])));
+      }
       pr0 += __shfl_xor_sync(0xffffffffu, pr0, 1);
       pr1 += __shfl_xor_sync(0xffffffffu, pr1, 1);
       pr0 += __shfl_xor_sync(0xffffffffu, pr0, 2);
@@ -545,6 +565,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       const float dv0 = value_grad(value_of(fr0), ret0, vo0, va0, sv_unused);
       const float dv1 = value_grad(value_of(fr1), ret1, vo1, va1, sv_unused);
       // ---------------------------------------------------------------- value head backward (64 -> 1 on the FMA pipe)
+      gw_v2[0] = fmaf(xb2[0], dv0, fmaf(xb2[2], dv1, gw_v2[0]));
+      gw_v2[1] = fmaf(xb2[1], dv0, fmaf(xb2[3], dv1, gw_v2[1]));
+      gw_v2[2] = fmaf(xb2[4], dv0, fmaf(xb2[6], dv1, gw_v2[2]));
+      gw_v2[3] = fmaf(xb2[5], dv0, fmaf(xb2[7], dv1, gw_v2[3]));
+      if (g0 && (lane & 3) == 0) gb_v2 += dv0 + dv1;
       const float2 w0 = *reinterpret_cast<const float2*>(fp + tc::F_WV2 + fc);
       const float2 w1 = *reinterpret_cast<const float2*>(fp + tc::F_WV2 + fc + 8);
       float v[8] = {dv0 * w0.x, dv0 * w0.y, dv1 * w0.x, dv1 * w0.y, dv0 * w1.x, dv0 * w1.y, dv1 * w1.x, dv1 * w1.y};
@@ -554,20 +579,16 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       frag_store(DY64, v, false);
       if (g0 && active) {
         float sv;
-        const float dvalue = value_grad(value, rows_s[R_RET * ROWS + m], rows_s[R_VAL * ROWS + m], valid, sv);
+        value_grad(value, rows_s[R_RET * ROWS + m], rows_s[R_VAL * ROWS + m], valid, sv);
         if (valid) {
           bad = !isfinite(value);
           s_val += (double)sv;
         }
-        float d8[8] = {dvalue, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        tc::store8(DY8, 0, m, d8);
       }
     }
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, WV1, 64, 64, 4, 0u); },        // dX = dY W
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_GV1, DY64, XB1, 64, 64, 4, 1u);                        // dW^T[out][in] += dY^T X
-           tc::gemm<true, true>(ld, tb + C_GV2, XB2, DY8, 64, 8, 4, 1u);                          // dW_v2[in] += X^T dvalue
-           tc::gemm<true, true, 1, 3>(ld, tb + C_GBV2, ONES, DY8, 64, 8, 4, 1u);                  // db_v2
          });
     if (worker) frag_bwd(C_D0, mk_b1, DY64, true, bs_v0);  // background GEMMs read DY64
     // all background: d(features) from the value head and the layer-0 gradients; nothing below touches
@@ -763,18 +784,25 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   umma::tc_fence_after();
   if (!worker) { /* issuer warp: nothing to flush */ } else
   if (g == 0) { flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0); flush_N(C_G2, C_GB2, 64, 16, 16, tc::L_ENC2); flush_N(C_GMAP, C_GBMAP, 16, n_out, 8, tc::L_MAP); }
-  if (worker && g == 1) { flush_T(C_G1, 64, 64, tc::L_ENC1); flush_N(C_GV2, C_GBV2, 64, 1, 8, tc::L_V2); }
+  if (worker && g == 1) flush_T(C_G1, 64, 64, tc::L_ENC1);
   if (worker && g == 2) { flush_T(C_GV1, 64, 64, tc::L_V1); flush_T(C_GV0, 16, 16, tc::L_V0); }
   if (worker && g == 3) { flush_T(C_GA0, 16, 16, tc::L_A0); flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1); }
 
   // ------------------------------------------------------------------ register bias sums (fixed order)
   __syncthreads();  // every GEMM is done and waited for: XH1 is free
   {
-    float* bsh = reinterpret_cast<float*>(smem + OFF_XH1);  // [5 layers][4 quadrants][64 columns]
-    float* const bsv[5] = {bs_e0, bs_e1, bs_v0, bs_v1, bs_a0};
+    float* bsh = reinterpret_cast<float*>(smem + OFF_XH1);  // [6 vectors][4 quadrants][64 columns], then [4] db_v2
+    float* const bsv[6] = {bs_e0, bs_e1, bs_v0, bs_v1, bs_a0, gw_v2};
     if (worker) {
+      {
+        float x = gb_v2;  // lanes 0, 4, .., 28 of column group 0 hold the quadrant's rows
+        x += __shfl_xor_sync(0xffffffffu, x, 4);
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+        if (g0 && lane == 0) bsh[6 * 4 * 64 + q] = x;
+      }
 #pragma unroll
-      for (int l = 0; l < 5; ++l) {
+      for (int l = 0; l < 6; ++l) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float x = bsv[l][j];  // rows lane/4 and lane/4 + 8 of the quadrant -> all 16 rows
@@ -786,10 +814,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       }
     }
     __syncthreads();
-    const int bl[5] = {tc::L_ENC0, tc::L_ENC1, tc::L_V0, tc::L_V1, tc::L_A0};
-    for (int e = tid; e < 5 * 64; e += THREADS) {
+    const int bl[6] = {lo.b[tc::L_ENC0], lo.b[tc::L_ENC1], lo.b[tc::L_V0], lo.b[tc::L_V1], lo.b[tc::L_A0], lo.w[tc::L_V2]};
+    if (tid == 0) part[lo.b[tc::L_V2]] = ((bsh[6 * 4 * 64] + bsh[6 * 4 * 64 + 1]) + bsh[6 * 4 * 64 + 2]) + bsh[6 * 4 * 64 + 3];
+    for (int e = tid; e < 6 * 64; e += THREADS) {
       const int l = e >> 6, c = e & 63;
-      part[lo.b[bl[l]] + c] = ((bsh[(l * 4 + 0) * 64 + c] + bsh[(l * 4 + 1) * 64 + c]) + bsh[(l * 4 + 2) * 64 + c]) + bsh[(l * 4 + 3) * 64 + c];
+      part[bl[l] + c] = ((bsh[(l * 4 + 0) * 64 + c] + bsh[(l * 4 + 1) * 64 + c]) + bsh[(l * 4 + 2) * 64 + c]) + bsh[(l * 4 + 3) * 64 + c];
     }
   }
 
