@@ -202,7 +202,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       umma::tc_fence_after();
     }
   };
-  auto step = [&](auto&& crit, auto&& bg) {
+  // track_bg: commit the background GEMMs to barB.  Only needed where something must know that THEY are done
+  // before the next critical GEMM is: an epilogue that overwrites one of their operands (need_bg), and the last
+  // step of a tile.  Everywhere else the tensor pipe's in-order execution is enough -- the next critical GEMM's
+  // commit implies theirs -- and not waiting for barB saves its ~300-cycle commit latency per step.
+  auto step_impl = [&](auto&& crit, auto&& bg, bool track_bg) {
     if (worker) {
       wait_crit();
       wait_bg();
@@ -216,12 +220,15 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       crit(leader);
       if (leader) umma::mma_commit(barA);
       bg(leader);
-      if (leader) umma::mma_commit(barB);
+      if (track_bg && leader) umma::mma_commit(barB);
       __syncwarp();
     } else {
-      pendA = pendB = true;
+      pendA = true;
+      pendB = track_bg;
     }
   };
+  auto step = [&](auto&& crit, auto&& bg) { step_impl(crit, bg, false); };
+  auto step_track = [&](auto&& crit, auto&& bg) { step_impl(crit, bg, true); };
   auto none = [](bool) {};
 
   const LrxPpoHyper h = a.h;
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
         }
       }
     }
-    step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, WV1, 64, 64, 4, 0u); },        // dX = dY W
+    step_track([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, WV1, 64, 64, 4, 0u); },        // dX = dY W
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_GV1, DY64, XB1, 64, 64, 4, 1u);                        // dW^T[out][in] += dY^T X
          });
@@ -715,28 +722,29 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
          });
 
     // ---------------------------------------------------------------- encoder backward
-    // every GEMM that reads DY8 and every reader of the row planes is done: gather the next tile's rows
+    if (worker) quarter16(C_DF, nullptr, DY16);                   // background reads DY64 / XF only
+    // this step's critical GEMM is done, so (in-order tensor pipe) is every GEMM that reads DY8; every reader of
+    // the row planes is long done: gather the next tile's rows
     if (g0 && !active) {
       const int i = idx_s[m];
       gather_rows(i, tile_row_ok(tile + (int)gridDim.x));
       gather_idx(tile + 2 * (int)gridDim.x);
       gather_commit();
     }
-    if (worker) quarter16(C_DF, nullptr, DY16);                   // background reads DY64 / XF only
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY16, W2, 64, 64, 1, 0u); },
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
            tc::gemm<true, true, 1, 3>(ld, tb + C_GB2, ONES, DY16, 64, 16, 4, 1u);
          });
     if (worker) frag_bwd(C_D0, mk_h2, DY64, false, bs_e1);  // background reads XH2 / DY16 only
-    step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, W1, 64, 64, 4, 0u); },
+    step_track([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, W1, 64, 64, 4, 0u); },
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_G1, DY64, XH1, 64, 64, 4, 1u);
          });
     if (worker) frag_bwd(C_D0, mk_h1, DY64, true, bs_e0);   // background GEMMs read DY64
     // the next tile's rows have had three steps to arrive; the barrier of the step below publishes them
     if (g0 && !active) gather_wait();
-    step(none, [&](bool ld) {
+    step_track(none, [&](bool ld) {
       tc::gemm<true, true>(ld, tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
     });
 
