@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   uint64_t* barA = reinterpret_cast<uint64_t*>(smem + OFF_MISC);      // critical GEMM(s) of a step done
   uint64_t* barB = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 8);  // background GEMMs of a step done
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 16);
+  uint64_t* barL = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 24);  // every epilogue warp has done its TMEM loads
   float* rows_s = reinterpret_cast<float*>(smem + OFF_ROWS);
   int* idx_s = reinterpret_cast<int*>(smem + OFF_IDX);
   uint8_t* valid_s = smem + OFF_VALID;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   if (tid == 0) {
     umma::mbar_init(barA, 1);
     umma::mbar_init(barB, 1);
+    umma::mbar_init(barL, WORKERS / 32);
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc(tslot, TMEM_COLS);
@@ -206,8 +208,22 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   // before the next critical GEMM is: an epilogue that overwrites one of their operands (need_bg), and the last
   // step of a tile.  Everywhere else the tensor pipe's in-order execution is enough -- the next critical GEMM's
   // commit implies theirs -- and not waiting for barB saves its ~300-cycle commit latency per step.
-  auto step_impl = [&](auto&& crit, auto&& bg, bool track_bg) {
+  // after_loads: a tcgen05.ld does not overtake MMAs that are already queued (tools/tmem_ld_under_mma.py: it
+  // returns when the queue has all but drained), so background GEMMs enqueued right behind the critical one delay
+  // the epilogue by their full length.  The issuer then holds them back until every epilogue warp has signalled
+  // (barL) that its TMEM loads of this step are done; they run under the epilogue's arithmetic and stores.
+  uint32_t phL = 0;
+  bool pendL = false;
+  auto signal_loaded = [&]() {  // epilogue warps, after tcgen05.wait::ld (or with nothing to load)
+    if (pendL) {
+      pendL = false;
+      umma::tc_fence_before();
+      if (lane == 0) umma::mbar_arrive(barL);
+    }
+  };
+  auto step_impl = [&](auto&& crit, auto&& bg, bool track_bg, bool after_loads = false) {
     if (worker) {
+      signal_loaded();
       wait_crit();
       wait_bg();
       umma::fence_async_smem();
@@ -219,14 +235,21 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       const bool leader = umma::elect_one();
       crit(leader);
       if (leader) umma::mma_commit(barA);
+      if (after_loads) {
+        umma::mbar_wait(barL, phL);
+        phL ^= 1u;
+        umma::tc_fence_after();
+      }
       bg(leader);
       if (track_bg && leader) umma::mma_commit(barB);
       __syncwarp();
     } else {
       pendA = true;
       pendB = track_bg;
+      pendL = after_loads;
     }
   };
+  auto step_late = [&](auto&& crit, auto&& bg) { step_impl(crit, bg, false, true); };
   auto step = [&](auto&& crit, auto&& bg) { step_impl(crit, bg, false); };
   auto step_track = [&](auto&& crit, auto&& bg) { step_impl(crit, bg, true); };
   auto none = [](bool) {};
@@ -258,6 +281,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     float v[16];
     umma::tmem_ld16(tw + col + c0, v);
     umma::tmem_ld_wait();
+    signal_loaded();
     mask = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -322,6 +346,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     float v[8];
     umma::tmem_ld_frag16(tw + col + cg, v);
     umma::tmem_ld_wait();
+    signal_loaded();
     const float2 b0 = *reinterpret_cast<const float2*>(bias + fc), b1 = *reinterpret_cast<const float2*>(bias + fc + 8);
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.x; v[3] += b0.y;
     v[4] += b1.x; v[5] += b1.y; v[6] += b1.x; v[7] += b1.y;
@@ -369,6 +394,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     float v[8];
     umma::tmem_ld_frag16(tw + col + cg, v);
     umma::tmem_ld_wait();
+    signal_loaded();
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = ((mask >> j) & 1u) ? v[j] : 0.f;
     bias_add(bsum, v);
@@ -382,6 +408,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     float v[4];
     umma::tmem_ld4(tw + col + 4 * g, v);
     umma::tmem_ld_wait();
+    signal_loaded();
     if (bias) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] += bias[4 * g + j];
@@ -597,17 +624,19 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_GV1, DY64, XB1, 64, 64, 4, 1u);                        // dW^T[out][in] += dY^T X
          });
-    if (worker) frag_bwd(C_D0, mk_b1, DY64, true, bs_v0);  // background GEMMs read DY64
-    // all background: d(features) from the value head and the layer-0 gradients; nothing below touches
-    // DY64 / XF / C_DF / C_GV0 before these are waited for at the next step
-    step(none, [&](bool ld) {
-      tc::gemm<false, true>(ld, tb + C_DF, DY64, WV0, 64, 16, 4, 0u);
-      tc::gemm<true, true>(ld, tb + C_GV0, DY64, XF, 64, 16, 4, 1u);
-    });
-
-    // ---------------------------------------------------------------- action head forward
-    if (worker) frag_fwd(C_D1, fp + tc::F_BA0, XB1, mk_b1, nopf);
-    step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XB1, WA1, 64, 16, 4, 0u); }, none);
+    if (worker) {
+      frag_bwd(C_D0, mk_b1, DY64, true, bs_v0);  // background GEMMs read DY64 and XB1
+      // -------------------------------------------------------------- action head forward
+      frag_fwd(C_D1, fp + tc::F_BA0, XB1, mk_b1, nopf);
+    }
+    // background, issued once the action head's output has been loaded from TMEM: d(features) from the value head
+    // and the value layer-0 weight gradient run under the policy-loss arithmetic (the longest stretch of a tile
+    // without tensor work).  Nothing touches DY64 / XF / C_DF / C_GV0 before the next critical GEMM is done.
+    step_late([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XB1, WA1, 64, 16, 4, 0u); },
+              [&](bool ld) {
+                tc::gemm<false, true>(ld, tb + C_DF, DY64, WV0, 64, 16, 4, 0u);
+                tc::gemm<true, true>(ld, tb + C_GV0, DY64, XF, 64, 16, 4, 1u);
+              });
     if (worker && g == 1) epilogue_fwd(C_D0, 0, fp + tc::F_BA1, false, XA2, mk_none, false, nop);
     if (g0) {
       // column group 1 (idle otherwise) writes the layer output back as the mapping-gradient operand while the
@@ -616,6 +645,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       wait_crit();
       umma::tmem_ld16(tw + C_D0, a2);
       umma::tmem_ld_wait();
+      signal_loaded();
 #pragma unroll
       for (int j = 0; j < 16; ++j) a2[j] += fp[tc::F_BA1 + j];
       // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261) on the FMA pipe
