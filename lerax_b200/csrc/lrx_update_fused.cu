@@ -53,17 +53,16 @@ constexpr uint32_t OFF_ONES = OFF_DY8 + 3 * PS8;       // [64][8]  all ones (one
 constexpr uint32_t OFF_F32 = OFF_ONES + PS8;           // fp32 biases etc. (tc::F_COUNT floats)
 constexpr uint32_t OFF_VPART = OFF_F32 + tc::F_RESERVE * 4;      // [4 column groups][64 rows] partial value dot products
 constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ROWS * 4;  // 2 mbarriers, TMEM slot
-// gathered row data of a tile (cp.async destinations): [5][64] 32-bit planes -- return, old value, action bits,
-// old log-prob, advantage -- then the minibatch indices of the tile after [64] and the valid flags [64] u8
+// gathered row data of a tile (cp.async destinations), double-buffered so that the next tile's gather can be issued
+// while this tile still reads its own: [5][64] 32-bit planes -- return, old value, action bits, old log-prob,
+// advantage --, the valid flags [64] u8 and the fp32 observations [64][8].  They live in the part of the XB2
+// region that only the (discarded) rows 16-63 of the mapping-gradient GEMM's A operand read: XA2 owns the first
+// two 8-column groups (2 KB) of each 8 KB piece, buffer b of the observations sits behind piece 0's, the planes
+// and flags behind piece 1's.
 constexpr int R_RET = 0, R_VAL = 1, R_ACT = 2, R_LOGP = 3, R_ADV = 4, R_PLANES = 5;
-constexpr uint32_t OFF_ROWS = OFF_MISC + 64;
-constexpr uint32_t OFF_IDX = OFF_ROWS + R_PLANES * ROWS * 4;
-constexpr uint32_t OFF_VALID = OFF_IDX + ROWS * 4;
-constexpr uint32_t SMEM_BYTES = OFF_VALID + ROWS;
-// fp32 observations of the tile's rows [64][8]: in flight / live only from the step after the last GEMM that reads
-// the dvalue / dlogits operand (which owns these bytes) to the layer-0 arithmetic of the next tile
-constexpr uint32_t OFF_OBS32 = OFF_DY8;
-static_assert(ROWS * 8 * 4 <= 3 * PS8, "fp32 observation staging must fit the DY8 operand");
+constexpr uint32_t OBS32_BYTES = ROWS * 8 * 4, PLANES_BYTES = R_PLANES * ROWS * 4;
+constexpr uint32_t OFF_IDX = OFF_MISC + 64;               // minibatch indices of the tile after the one being gathered
+constexpr uint32_t SMEM_BYTES = OFF_IDX + ROWS * 4;
 static_assert(SMEM_BYTES <= 227 * 1024, "fused update kernel exceeds shared memory");
 static_assert(tc::F_COUNT <= tc::F_RESERVE, "fp32 parameter block too small");
 
@@ -129,10 +128,15 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   uint64_t* barB = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 8);  // background GEMMs of a step done
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 16);
   uint64_t* barL = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 24);  // every epilogue warp has done its TMEM loads
-  float* rows_s = reinterpret_cast<float*>(smem + OFF_ROWS);
   int* idx_s = reinterpret_cast<int*>(smem + OFF_IDX);
-  uint8_t* valid_s = smem + OFF_VALID;
-  float* obs_s = reinterpret_cast<float*>(smem + OFF_OBS32);
+  // current (read by this tile) and next (being gathered) staging buffers; swapped at the end of a tile
+  float* obs_s = reinterpret_cast<float*>(smem + OFF_XB2 + 2 * PS8);
+  float* obs_n = obs_s + OBS32_BYTES / 4;
+  float* rows_s = reinterpret_cast<float*>(smem + OFF_XB2 + PS64 + 2 * PS8);
+  float* rows_n = rows_s + PLANES_BYTES / 4;
+  uint8_t* valid_s = smem + OFF_XB2 + PS64 + 2 * PS8 + 2 * PLANES_BYTES;
+  uint8_t* valid_n = valid_s + ROWS;
+  static_assert(2 * OBS32_BYTES <= PS64 - 2 * PS8 && 2 * PLANES_BYTES + 2 * ROWS <= PS64 - 2 * PS8, "staging does not fit");
 
   const tc::Mat W1{smem + OFF_W1, 64, PS64}, W2{smem + OFF_W2, 16, PS16};
   const tc::Mat WV0{smem + OFF_WV0, 64, PS16}, WV1{smem + OFF_WV1, 64, PS64};
@@ -425,11 +429,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   };
 
   // Row data of a tile (gather of base_buffer.py:90-103): cp.async straight into shared memory, issued by the
-  // otherwise idle lanes 16-31 of column group 0 (one lane per row) one tile ahead, the minibatch index two tiles
+  // otherwise idle lanes 16-31 of column group 2 (one lane per row) one tile ahead -- while the row-owner threads of
+  // group 0 work through the policy loss and groups 2 and 3 have nothing to do --, the minibatch index two tiles
   // ahead.  No register is the destination of a global load inside the tile loop: a register gather -- even one
   // consumed a whole tile later -- cost 9 % of the kernel, because everything that shares a scoreboard with the
-  // outstanding loads waits out their DRAM latency.  The planes are free for the next tile once the policy loss
-  // has read them, the fp32 observations once the last GEMM on DY8 is done: both hold after step 9's wait.
+  // outstanding loads waits out their DRAM latency.  The staging is double-buffered (see the shared-memory map).
   auto cp_async4 = [](void* dst, const void* src, bool ok) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(umma::smem_u32(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
   };
@@ -440,20 +444,20 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   auto gather_rows = [&](int i, bool ok) {  // buffer row i (zeros when !ok) -> this lane's staging slot m
     const int n = i / a.buf.T, t = i - n * a.buf.T;
     const size_t src = ok ? (size_t)t * a.buf.N + n : 0;
-    cp_async4(rows_s + R_RET * ROWS + m, a.buf.ret + src, ok);
-    cp_async4(rows_s + R_VAL * ROWS + m, (h.clip_value_loss ? a.buf.val : a.buf.ret) + src, ok && h.clip_value_loss);
-    cp_async4(rows_s + R_ACT * ROWS + m, (const int32_t*)a.buf.act + src, ok);
-    cp_async4(rows_s + R_LOGP * ROWS + m, a.buf.logp + src, ok);
-    cp_async4(rows_s + R_ADV * ROWS + m, a.buf.adv + src, ok);  // raw; normalised where it is used
+    cp_async4(rows_n + R_RET * ROWS + m, a.buf.ret + src, ok);
+    cp_async4(rows_n + R_VAL * ROWS + m, (h.clip_value_loss ? a.buf.val : a.buf.ret) + src, ok && h.clip_value_loss);
+    cp_async4(rows_n + R_ACT * ROWS + m, (const int32_t*)a.buf.act + src, ok);
+    cp_async4(rows_n + R_LOGP * ROWS + m, a.buf.logp + src, ok);
+    cp_async4(rows_n + R_ADV * ROWS + m, a.buf.adv + src, ok);  // raw; normalised where it is used
     const float* op = a.buf.obs + src * a.obs_dim;
     if (a.obs_dim == 4) {  // one 16-byte copy (CartPole)
-      cp_async16(obs_s + m * 8, op, ok);
-      *reinterpret_cast<float4*>(obs_s + m * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      cp_async16(obs_n + m * 8, op, ok);
+      *reinterpret_cast<float4*>(obs_n + m * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) cp_async4(obs_s + m * 8 + k, op + (k < a.obs_dim ? k : 0), ok && k < a.obs_dim);
+      for (int k = 0; k < 8; ++k) cp_async4(obs_n + m * 8 + k, op + (k < a.obs_dim ? k : 0), ok && k < a.obs_dim);
     }
-    valid_s[m] = ok ? 1 : 0;
+    valid_n[m] = ok ? 1 : 0;
   };
   auto gather_idx = [&](int t) {  // minibatch indices of tile t -> idx_s
     const bool ok = tile_row_ok(t);
@@ -461,7 +465,13 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   };
   auto gather_commit = []() { asm volatile("cp.async.commit_group;" ::: "memory"); };
   auto gather_wait = []() { asm volatile("cp.async.wait_group 0;" ::: "memory"); };
-  if (g0 && !active) {  // first tile: the only register load of an index
+  const bool gatherer = worker && g == 2 && !active;
+  auto swap_staging = [&]() {
+    float* t = obs_s; obs_s = obs_n; obs_n = t;
+    t = rows_s; rows_s = rows_n; rows_n = t;
+    uint8_t* u = valid_s; valid_s = valid_n; valid_n = u;
+  };
+  if (gatherer) {  // first tile: the only register load of an index
     const int t0 = (int)blockIdx.x;
     const bool ok = tile_row_ok(t0);
     const int i = ok ? __ldg(a.idx + (long long)t0 * ROWS + m) : 0;
@@ -470,6 +480,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     gather_commit();
     gather_wait();
   }
+  swap_staging();  // what was gathered as "next" is the first tile's "current"
   __syncthreads();
 
   auto store_xobs = [&](const tc::Mat& xo) {
@@ -637,6 +648,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
                 tc::gemm<false, true>(ld, tb + C_DF, DY64, WV0, 64, 16, 4, 0u);
                 tc::gemm<true, true>(ld, tb + C_GV0, DY64, XF, 64, 16, 4, 1u);
               });
+    if (gatherer) {  // the next tile's rows, into the staging buffers this tile does not read
+      gather_rows(idx_s[m], tile_row_ok(tile + (int)gridDim.x));
+      gather_idx(tile + 2 * (int)gridDim.x);
+      gather_commit();
+    }
     if (worker && g == 1) epilogue_fwd(C_D0, 0, fp + tc::F_BA1, false, XA2, mk_none, false, nop);
     if (g0) {
       // column group 1 (idle otherwise) writes the layer output back as the mapping-gradient operand while the
@@ -753,14 +769,6 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
 
     // ---------------------------------------------------------------- encoder backward
     if (worker) quarter16(C_DF, nullptr, DY16);                   // background reads DY64 / XF only
-    // this step's critical GEMM is done, so (in-order tensor pipe) is every GEMM that reads DY8; every reader of
-    // the row planes is long done: gather the next tile's rows
-    if (g0 && !active) {
-      const int i = idx_s[m];
-      gather_rows(i, tile_row_ok(tile + (int)gridDim.x));
-      gather_idx(tile + 2 * (int)gridDim.x);
-      gather_commit();
-    }
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY16, W2, 64, 64, 1, 0u); },
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
@@ -773,10 +781,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
          });
     if (worker) frag_bwd(C_D0, mk_h1, DY64, true, bs_e0);   // background GEMMs read DY64
     // the next tile's rows have had three steps to arrive; the barrier of the step below publishes them
-    if (g0 && !active) gather_wait();
+    if (gatherer) gather_wait();
     step_track(none, [&](bool ld) {
       tc::gemm<true, true>(ld, tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
     });
+    swap_staging();
 
   }
   if (worker) {

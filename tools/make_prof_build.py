@@ -5,11 +5,11 @@ import os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CS = os.path.join(ROOT, "lerax_b200", "csrc")
 s = open(os.path.join(CS, "lrx_update_fused.cu")).read()
-s = s.replace('''  auto step = [&](auto&& crit, auto&& bg) {
+s = s.replace('''  auto step_impl = [&](auto&& crit, auto&& bg, bool track_bg, bool after_loads = false) {
     if (worker) {''', '''  long long pf_t[20] = {0};
   long long pf_last = clock64();
   int pf_i = 0;
-  auto step = [&](auto&& crit, auto&& bg) {
+  auto step_impl = [&](auto&& crit, auto&& bg, bool track_bg, bool after_loads = false) {
     {
       const long long now = clock64();
       pf_t[pf_i] += now - pf_last;
