@@ -136,6 +136,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   float* rows_n = rows_s + PLANES_BYTES / 4;
   uint8_t* valid_s = smem + OFF_XB2 + PS64 + 2 * PS8 + 2 * PLANES_BYTES;
   uint8_t* valid_n = valid_s + ROWS;
+  // fp32 action layer-2 outputs [64][16] and d(loss)/d(head) [64][8] of the tile: the mapping layer's gradients are
+  // accumulated from them on the FMA pipe
+  float* a2_s = reinterpret_cast<float*>(smem + OFF_XB2 + 2 * PS64 + 2 * PS8);
+  float* dh_s = a2_s + ROWS * 16;
+  static_assert(ROWS * 16 * 4 + ROWS * 8 * 4 <= PS64 - 2 * PS8, "mapping staging does not fit");
   static_assert(2 * OBS32_BYTES <= PS64 - 2 * PS8 && 2 * PLANES_BYTES + 2 * ROWS <= PS64 - 2 * PS8, "staging does not fit");
 
   const tc::Mat W1{smem + OFF_W1, 64, PS64}, W2{smem + OFF_W2, 16, PS16};
@@ -387,6 +392,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   float bs_v1[4] = {0.f, 0.f, 0.f, 0.f}, bs_a0[4] = {0.f, 0.f, 0.f, 0.f};
   // value output layer (64 -> 1): weight gradient of this thread's four columns and (one thread per row) the bias
   float gw_v2[4] = {0.f, 0.f, 0.f, 0.f}, gb_v2 = 0.f;
+  // action_dist.mapping (16 -> n_out): this thread's share of dW[o][i] and db[o], o = 2q + lane/16, i = lane%16,
+  // over the 16 rows of the tile that belong to its column group
+  float gm_w = 0.f, gm_b = 0.f;
+  float bs_e2[4] = {0.f, 0.f, 0.f, 0.f};  // encoder output layer's bias: columns 4g..4g+3 of this (row-owner) thread
   auto bias_add = [](float* bsum, const float* v) {
     bsum[0] += v[0] + v[2];
     bsum[1] += v[1] + v[3];
@@ -407,7 +416,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   auto nopf = [](float*) {};
   // 16-wide layer outputs (features, d(features)): every column group takes 4 of the 16 columns of its
   // quadrant's rows (lane = row), so the step is not left to one group while twelve warps wait.
-  auto quarter16 = [&](uint32_t col, const float* bias, const tc::Mat& dst) {
+  auto quarter16 = [&](uint32_t col, const float* bias, const tc::Mat& dst, float* qsum) {
     wait_crit();
     float v[4];
     umma::tmem_ld4(tw + col + 4 * g, v);
@@ -416,6 +425,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     if (bias) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] += bias[4 * g + j];
+    }
+    if (qsum && active) {  // column sums over the tiles (bias gradient), reduced across threads at the flush
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qsum[j] += v[j];
     }
     uint32_t w[6];
     tc::split2(v[0], v[1], w[0], w[1], w[2]);
@@ -545,7 +558,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH1, W1, 64, 64, 4, 0u); }, none);
     if (worker) frag_fwd(C_D0, fp + tc::F_B1, XH2, mk_h2, nopf);
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH2, W2, 64, 16, 4, 0u); }, none);
-    if (worker) quarter16(C_D0, fp + tc::F_B2, XF);
+    if (worker) quarter16(C_D0, fp + tc::F_B2, XF, nullptr);
 
     // ---------------------------------------------------------------- value head forward
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XF, WV0, 64, 64, 1, 0u); },
@@ -653,10 +666,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       gather_idx(tile + 2 * (int)gridDim.x);
       gather_commit();
     }
-    if (worker && g == 1) epilogue_fwd(C_D0, 0, fp + tc::F_BA1, false, XA2, mk_none, false, nop);
     if (g0) {
-      // column group 1 (idle otherwise) writes the layer output back as the mapping-gradient operand while the
-      // row-owner threads here go straight on with the loss
       float a2[16];
       wait_crit();
       umma::tmem_ld16(tw + C_D0, a2);
@@ -664,6 +674,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       signal_loaded();
 #pragma unroll
       for (int j = 0; j < 16; ++j) a2[j] += fp[tc::F_BA1 + j];
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(a2_s + m * 16 + j) = make_float4(a2[j], a2[j + 1], a2[j + 2], a2[j + 3]);
+      }
       // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261) on the FMA pipe
       float head[LRX_MAX_NOUT];
 #pragma unroll
@@ -740,7 +755,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       }
       // -------------------------------------------------------------- action head backward (mapping, FMA)
       if (active) {
-        tc::store8(DY8, 0, m, dhead);
+        *reinterpret_cast<float4*>(dh_s + m * 8) = make_float4(dhead[0], dhead[1], dhead[2], dhead[3]);
+        *reinterpret_cast<float4*>(dh_s + m * 8 + 4) = make_float4(dhead[4], dhead[5], dhead[6], dhead[7]);
         float d16[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -757,10 +773,22 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY16, WA1, 64, 64, 1, 0u); },        // dX = dY16 W_a1 (K = 16 outputs)
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_GA1, XB1, DY16, 64, 16, 4, 1u);                        // dW[in][out] += X^T dY
-           tc::gemm<true, true, 1, 3>(ld, tb + C_GBA1, ONES, DY16, 64, 16, 4, 1u);
-           tc::gemm<true, true>(ld, tb + C_GMAP, XA2, DY8, 64, 8, 4, 1u);                         // dW_map[in (16 valid)][out]
-           tc::gemm<true, true, 1, 3>(ld, tb + C_GBMAP, ONES, DY8, 64, 8, 4, 1u);
          });
+    // mapping layer gradients on the FMA pipe while the GEMM above runs: dW[o][i] += dhead[r][o] a2[r][i],
+    // db[o] += dhead[r][o] over this column group's 16 rows (the a1 bias gradient follows from db at the flush)
+    if (worker) {
+      const int o2 = 2 * q + (lane >> 4), i2 = lane & 15;
+      if (o2 < n_out) {
+        const float* ap = a2_s + (g * 16) * 16 + i2;
+        const float* dp = dh_s + (g * 16) * 8 + o2;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const float dh = dp[r * 8];
+          gm_w = fmaf(ap[r * 16], dh, gm_w);
+          gm_b += dh;
+        }
+      }
+    }
     if (worker) frag_bwd(C_D0, mk_b1, DY64, false, bs_a0);  // this step's background GEMMs do not read DY64
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_DF, DY64, WA0, 64, 16, 4, 1u); },        // d(features) += action head
          [&](bool ld) {
@@ -768,11 +796,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
          });
 
     // ---------------------------------------------------------------- encoder backward
-    if (worker) quarter16(C_DF, nullptr, DY16);                   // background reads DY64 / XF only
+    if (worker) quarter16(C_DF, nullptr, DY16, bs_e2);                   // background reads DY64 / XF only
     step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY16, W2, 64, 64, 1, 0u); },
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
-           tc::gemm<true, true, 1, 3>(ld, tb + C_GB2, ONES, DY16, 64, 16, 4, 1u);
          });
     if (worker) frag_bwd(C_D0, mk_h2, DY64, false, bs_e1);  // background reads XH2 / DY16 only
     step_track([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, W1, 64, 64, 4, 0u); },
@@ -810,18 +837,18 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     }
   };
   // dW accumulators: TMEM row = input unit (m), columns = outputs; db in row 0 of its own block
-  auto flush_N = [&](uint32_t col, uint32_t colb, int in_real, int out_real, int out_pad, int layer) {
+  auto flush_N = [&](uint32_t col, uint32_t colb, int in_real, int out_real, int out_pad, int layer, bool with_bias) {
     for (int c0 = 0; c0 < out_pad; c0 += 8) {
       float v[8], b[8];
       umma::tmem_ld8(tw + col + c0, v);
-      umma::tmem_ld8(tw + colb + c0, b);
+      if (with_bias) umma::tmem_ld8(tw + colb + c0, b);
       umma::tmem_ld_wait();
       if (active) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (c0 + j < out_real) {
             if (m < in_real) part[lo.w[layer] + (c0 + j) * in_real + m] = v[j];
-            if (m == 0) part[lo.b[layer] + c0 + j] = b[j];
+            if (with_bias && m == 0) part[lo.b[layer] + c0 + j] = b[j];
           }
         }
       }
@@ -830,10 +857,10 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   // nine layers over the four column groups of warps
   umma::tc_fence_after();
   if (!worker) { /* issuer warp: nothing to flush */ } else
-  if (g == 0) { flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0); flush_N(C_G2, C_GB2, 64, 16, 16, tc::L_ENC2); flush_N(C_GMAP, C_GBMAP, 16, n_out, 8, tc::L_MAP); }
+  if (g == 0) { flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0); flush_N(C_G2, C_GB2, 64, 16, 16, tc::L_ENC2, false); }
   if (worker && g == 1) flush_T(C_G1, 64, 64, tc::L_ENC1);
   if (worker && g == 2) { flush_T(C_GV1, 64, 64, tc::L_V1); flush_T(C_GV0, 16, 16, tc::L_V0); }
-  if (worker && g == 3) { flush_T(C_GA0, 16, 16, tc::L_A0); flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1); }
+  if (worker && g == 3) { flush_T(C_GA0, 16, 16, tc::L_A0); flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1, false); }
 
   // ------------------------------------------------------------------ register bias sums (fixed order)
   __syncthreads();  // every GEMM is done and waited for: XH1 is free
@@ -849,6 +876,16 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
         if (g0 && lane == 0) bsh[6 * 4 * 64 + q] = x;
       }
 #pragma unroll
+      for (int j = 0; j < 4; ++j) {  // encoder output bias: the quadrant's 16 row-owner lanes (the others hold 0)
+        float x = bs_e2[j];
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        x += __shfl_xor_sync(0xffffffffu, x, 4);
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+        if (lane == 0) bsh[6 * 4 * 64 + 4 + q * 16 + 4 * g + j] = x;
+      }
+#pragma unroll
       for (int l = 0; l < 6; ++l) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -862,6 +899,31 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     }
     __syncthreads();
     const int bl[6] = {lo.b[tc::L_ENC0], lo.b[tc::L_ENC1], lo.b[tc::L_V0], lo.b[tc::L_V1], lo.b[tc::L_A0], lo.w[tc::L_V2]};
+    {  // mapping layer: sum the four row groups; db_a1 = W_map^T db_map (the layers are linear in between)
+      float* mw = bsh + 6 * 4 * 64 + 4 + 64;  // [4 groups][128 (o, i)] then [4][8] db
+      float* mb = mw + 4 * 128;
+      if (worker) {
+        const int p2 = q * 32 + lane;
+        mw[g * 128 + p2] = gm_w;
+        if ((lane & 15) == 0) mb[g * 8 + (p2 >> 4)] = gm_b;
+      }
+      __syncthreads();
+      if (tid < 128 && (tid >> 4) < n_out)
+        part[lo.w[tc::L_MAP] + tid] = ((mw[tid] + mw[128 + tid]) + mw[256 + tid]) + mw[384 + tid];
+      if (tid >= 128 && tid < 136 && tid - 128 < n_out)
+        part[lo.b[tc::L_MAP] + tid - 128] = ((mb[tid - 128] + mb[8 + tid - 128]) + mb[16 + tid - 128]) + mb[24 + tid - 128];
+      if (tid >= 160 && tid < 176) {
+        const int i2 = tid - 160;
+        float sacc = 0.f;
+        for (int o2 = 0; o2 < n_out; ++o2)
+          sacc = fmaf(((mb[o2] + mb[8 + o2]) + mb[16 + o2]) + mb[24 + o2], fp[tc::F_WMAP + o2 * 16 + i2], sacc);
+        part[lo.b[tc::L_A1] + i2] = sacc;
+      }
+    }
+    if (tid >= 32 && tid < 48) {
+      const float* e2 = bsh + 6 * 4 * 64 + 4 + (tid - 32);
+      part[lo.b[tc::L_ENC2] + tid - 32] = ((e2[0] + e2[16]) + e2[32]) + e2[48];
+    }
     if (tid == 0) part[lo.b[tc::L_V2]] = ((bsh[6 * 4 * 64] + bsh[6 * 4 * 64 + 1]) + bsh[6 * 4 * 64 + 2]) + bsh[6 * 4 * 64 + 3];
     for (int e = tid; e < 6 * 64; e += THREADS) {
       const int l = e >> 6, c = e & 63;
