@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   // the next tile's are written
   const tc::Mat XOBS2[2] = {tc::Mat{smem + OFF_XOBS, ROWS, PS16}, tc::Mat{smem + OFF_W0, ROWS, PS16}};
   const tc::Mat XH1{smem + OFF_XH1, ROWS, PS64}, XH2{smem + OFF_XH2, ROWS, PS64};
+  const tc::Mat DH1 = XH2;  // d(loss)/d(h1) of a tile reuses the XH2 buffer (see the last two steps of a tile)
   const tc::Mat XF{smem + OFF_XF, ROWS, PS16}, XB1{smem + OFF_XB1, ROWS, PS64}, XB2{smem + OFF_XB2, ROWS, PS64};
   const tc::Mat XA2{smem + OFF_XB2, ROWS, PS64};  // [64][16] action layer-2 output; reads past col 16 stay inside XB2
   const tc::Mat DY64{smem + OFF_DY64, ROWS, PS64}, DY16{smem + OFF_DY16, ROWS, PS16}, DY8{smem + OFF_DY8, ROWS, PS8};
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
         if (v[j] > 0.f) mk_h1 |= (1u << j);
         v[j] = fmaxf(v[j], 0.f);
       }
-      frag_store(XH1, v, false);
+      frag_store(XH1, v, true);  // the previous tile's last GEMMs read XH1 / XH2
     }
     step([&](bool ld) { tc::gemm<false, false>(ld, tb + C_D0, XH1, W1, 64, 64, 4, 0u); }, none);
     if (worker) frag_fwd(C_D0, fp + tc::F_B1, XH2, mk_h2, nopf);
@@ -802,16 +803,18 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
            tc::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 4, 1u);
          });
     if (worker) frag_bwd(C_D0, mk_h2, DY64, false, bs_e1);  // background reads XH2 / DY16 only
-    step_track([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, W1, 64, 64, 4, 0u); },
+    step([&](bool ld) { tc::gemm<false, true>(ld, tb + C_D0, DY64, W1, 64, 64, 4, 0u); },
          [&](bool ld) {
            tc::gemm<true, true>(ld, tb + C_G1, DY64, XH1, 64, 64, 4, 1u);
          });
-    if (worker) frag_bwd(C_D0, mk_h1, DY64, true, bs_e0);   // background GEMMs read DY64
+    // d(h1) goes into the XH2 buffer, dead since the GEMMs of the step before (ordered before this step's critical
+    // GEMM) read it: no wait for this step's weight-gradient GEMM, which still reads DY64 and XH1
+    if (worker) frag_bwd(C_D0, mk_h1, DH1, false, bs_e0);
     // the next tile's rows have had three steps to arrive; the barrier of the step below publishes them
     if (gatherer) gather_wait();
     step_track(none, [&](bool ld) {
-      tc::gemm<true, true>(ld, tb + C_G0, DY64, XOBS, 64, 16, 4, 1u);
-    });
+      tc::gemm<true, true>(ld, tb + C_G0, DH1, XOBS, 64, 16, 4, 1u);
+    });  // its commit also covers the GEMM on XH1 of the step before: waited for before XH1 / XH2 are rewritten
     swap_staging();
 
   }
