@@ -45,22 +45,22 @@ constexpr uint32_t OFF_XH1 = OFF_XOBS + 3 * PS16;      // [64][64]
 constexpr uint32_t OFF_XH2 = OFF_XH1 + 3 * PS64;       // [64][64]
 constexpr uint32_t OFF_XF = OFF_XH2 + 3 * PS64;        // [64][16] features
 constexpr uint32_t OFF_XB1 = OFF_XF + 3 * PS16;        // [64][64] head layer-1 activations (value, then action)
-constexpr uint32_t OFF_XB2 = OFF_XB1 + 3 * PS64;       // [64][64] value layer-2 / [64][16] action layer-2
-constexpr uint32_t OFF_DY64 = OFF_XB2 + 3 * PS64;      // [64][64] current upstream gradient
+constexpr uint32_t OFF_DY64 = OFF_XB1 + 3 * PS64;      // [64][64] current upstream gradient
 constexpr uint32_t OFF_DY16 = OFF_DY64 + 3 * PS64;     // [64][16]
-constexpr uint32_t OFF_DY8 = OFF_DY16 + 3 * PS16;      // [64][8]  dvalue / dlogits
-constexpr uint32_t OFF_ONES = OFF_DY8 + 3 * PS8;       // [64][8]  all ones (one piece)
-constexpr uint32_t OFF_F32 = OFF_ONES + PS8;           // fp32 biases etc. (tc::F_COUNT floats)
-constexpr uint32_t OFF_VPART = OFF_F32 + tc::F_RESERVE * 4;      // [4 column groups][64 rows] partial value dot products
-constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ROWS * 4;  // 2 mbarriers, TMEM slot
-// gathered row data of a tile (cp.async destinations), double-buffered so that the next tile's gather can be issued
-// while this tile still reads its own: [5][64] 32-bit planes -- return, old value, action bits, old log-prob,
-// advantage --, the valid flags [64] u8 and the fp32 observations [64][8].  They live in the part of the XB2
-// region that only the (discarded) rows 16-63 of the mapping-gradient GEMM's A operand read: XA2 owns the first
-// two 8-column groups (2 KB) of each 8 KB piece, buffer b of the observations sits behind piece 0's, the planes
-// and flags behind piece 1's.
+// fp32 staging (no MMA operand).  Gathered row data of a tile (cp.async destinations), double-buffered so that the
+// next tile's gather can be issued while this tile still reads its own: fp32 observations [64][8], then [5][64]
+// 32-bit planes -- return, old value, action bits, old log-prob, advantage -- and the valid flags [64] u8; then the
+// action layer-2 outputs [64][16] and d(loss)/d(head) [64][8] the mapping layer's gradients are accumulated from.
 constexpr int R_RET = 0, R_VAL = 1, R_ACT = 2, R_LOGP = 3, R_ADV = 4, R_PLANES = 5;
 constexpr uint32_t OBS32_BYTES = ROWS * 8 * 4, PLANES_BYTES = R_PLANES * ROWS * 4;
+constexpr uint32_t OFF_OBS32 = OFF_DY16 + 3 * PS16;                  // [2][64][8] fp32
+constexpr uint32_t OFF_PLANES = OFF_OBS32 + 2 * OBS32_BYTES;         // [2][5][64] 32-bit
+constexpr uint32_t OFF_VALID = OFF_PLANES + 2 * PLANES_BYTES;        // [2][64] u8
+constexpr uint32_t OFF_A2 = OFF_VALID + 2 * ROWS;                    // [64][16] fp32
+constexpr uint32_t OFF_DHEAD = OFF_A2 + ROWS * 16 * 4;               // [64][8] fp32
+constexpr uint32_t OFF_F32 = OFF_DHEAD + ROWS * 8 * 4;  // fp32 biases etc. (tc::F_COUNT floats)
+constexpr uint32_t OFF_VPART = OFF_F32 + tc::F_RESERVE * 4;      // [4 column groups][64 rows] partial value dot products
+constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ROWS * 4;  // 2 mbarriers, TMEM slot
 constexpr uint32_t OFF_IDX = OFF_MISC + 64;               // minibatch indices of the tile after the one being gathered
 constexpr uint32_t SMEM_BYTES = OFF_IDX + ROWS * 4;
 static_assert(SMEM_BYTES <= 227 * 1024, "fused update kernel exceeds shared memory");
@@ -130,18 +130,14 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   uint64_t* barL = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 24);  // every epilogue warp has done its TMEM loads
   int* idx_s = reinterpret_cast<int*>(smem + OFF_IDX);
   // current (read by this tile) and next (being gathered) staging buffers; swapped at the end of a tile
-  float* obs_s = reinterpret_cast<float*>(smem + OFF_XB2 + 2 * PS8);
+  float* obs_s = reinterpret_cast<float*>(smem + OFF_OBS32);
   float* obs_n = obs_s + OBS32_BYTES / 4;
-  float* rows_s = reinterpret_cast<float*>(smem + OFF_XB2 + PS64 + 2 * PS8);
+  float* rows_s = reinterpret_cast<float*>(smem + OFF_PLANES);
   float* rows_n = rows_s + PLANES_BYTES / 4;
-  uint8_t* valid_s = smem + OFF_XB2 + PS64 + 2 * PS8 + 2 * PLANES_BYTES;
+  uint8_t* valid_s = smem + OFF_VALID;
   uint8_t* valid_n = valid_s + ROWS;
-  // fp32 action layer-2 outputs [64][16] and d(loss)/d(head) [64][8] of the tile: the mapping layer's gradients are
-  // accumulated from them on the FMA pipe
-  float* a2_s = reinterpret_cast<float*>(smem + OFF_XB2 + 2 * PS64 + 2 * PS8);
-  float* dh_s = a2_s + ROWS * 16;
-  static_assert(ROWS * 16 * 4 + ROWS * 8 * 4 <= PS64 - 2 * PS8, "mapping staging does not fit");
-  static_assert(2 * OBS32_BYTES <= PS64 - 2 * PS8 && 2 * PLANES_BYTES + 2 * ROWS <= PS64 - 2 * PS8, "staging does not fit");
+  float* a2_s = reinterpret_cast<float*>(smem + OFF_A2);
+  float* dh_s = reinterpret_cast<float*>(smem + OFF_DHEAD);
 
   const tc::Mat W1{smem + OFF_W1, 64, PS64}, W2{smem + OFF_W2, 16, PS16};
   const tc::Mat WV0{smem + OFF_WV0, 64, PS16}, WV1{smem + OFF_WV1, 64, PS64};
@@ -151,10 +147,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   const tc::Mat XOBS2[2] = {tc::Mat{smem + OFF_XOBS, ROWS, PS16}, tc::Mat{smem + OFF_W0, ROWS, PS16}};
   const tc::Mat XH1{smem + OFF_XH1, ROWS, PS64}, XH2{smem + OFF_XH2, ROWS, PS64};
   const tc::Mat DH1 = XH2;  // d(loss)/d(h1) of a tile reuses the XH2 buffer (see the last two steps of a tile)
-  const tc::Mat XF{smem + OFF_XF, ROWS, PS16}, XB1{smem + OFF_XB1, ROWS, PS64}, XB2{smem + OFF_XB2, ROWS, PS64};
-  const tc::Mat XA2{smem + OFF_XB2, ROWS, PS64};  // [64][16] action layer-2 output; reads past col 16 stay inside XB2
-  const tc::Mat DY64{smem + OFF_DY64, ROWS, PS64}, DY16{smem + OFF_DY16, ROWS, PS16}, DY8{smem + OFF_DY8, ROWS, PS8};
-  const tc::Mat ONES{smem + OFF_ONES, 0, PS8};  // R = 0: as an MN-major A operand every MN group aliases the same ones
+  const tc::Mat XF{smem + OFF_XF, ROWS, PS16}, XB1{smem + OFF_XB1, ROWS, PS64};
+  const tc::Mat DY64{smem + OFF_DY64, ROWS, PS64}, DY16{smem + OFF_DY16, ROWS, PS16};
 
   // ------------------------------------------------------------------ one-time staging
   tc::stage_weight(a.params + a.lo.w[tc::L_ENC1], 64, 64, 64, W1, tid, THREADS);
@@ -164,11 +158,6 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   tc::stage_weight(a.params + a.lo.w[tc::L_A0], 64, 16, 16, WA0, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_A1], 16, 64, 64, WA1, tid, THREADS);
   tc::stage_f32(a.params, a.lo, n_out, a.obs_dim, fp, tid, THREADS);
-  for (int i = tid; i < (int)(PS8 / 4); i += THREADS)
-    reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;  // two bf16 1.0
-  // XB2 is read past the 16 action columns by the mapping-gradient GEMM: keep it finite
-  for (int i = tid; i < (int)(3 * PS64 / 16); i += THREADS)
-    reinterpret_cast<uint4*>(smem + OFF_XB2)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     umma::mbar_init(barA, 1);
     umma::mbar_init(barB, 1);
@@ -282,55 +271,6 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
   }
   double s_kl = 0, s_pol = 0, s_val = 0, s_ent = 0, s_dls = 0, s_bad = 0;
 
-  // This thread's 16 columns [c0, c0+16) of a layer output in TMEM -> + bias -> optional ReLU (mask
-  // recorded) -> operand X.  fn(v) sees the 16 activated values.  need_bg: the destination is still
-  // read by this step's background GEMMs.
-  auto epilogue_fwd = [&](uint32_t col, int c0, const float* bias, bool relu, const tc::Mat& dst, uint32_t& mask,
-                          bool need_bg, auto&& fn) {
-    wait_crit();
-    float v[16];
-    umma::tmem_ld16(tw + col + c0, v);
-    umma::tmem_ld_wait();
-    signal_loaded();
-    mask = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      v[j] += bias[c0 + j];
-      if (relu) {
-        if (v[j] > 0.f) mask |= (1u << j);
-        v[j] = fmaxf(v[j], 0.f);
-      }
-    }
-    fn(v);
-    uint4 p[6];
-    tc::split8(v, p[0], p[1], p[2]);
-    tc::split8(v + 8, p[3], p[4], p[5]);
-    if (need_bg) wait_bg();
-    if (active) {
-      tc::store_pieces(dst, (c0 >> 3), m, p[0], p[1], p[2]);
-      tc::store_pieces(dst, (c0 >> 3) + 1, m, p[3], p[4], p[5]);
-    }
-  };
-  // dX columns [c0, c0+16) masked by the ReLU of the layer that produced X -> operand dY.
-  auto epilogue_bwd = [&](uint32_t col, int c0, uint32_t mask, bool use_mask, const tc::Mat& dst, bool need_bg) {
-    wait_crit();
-    float v[16];
-    umma::tmem_ld16(tw + col + c0, v);
-    umma::tmem_ld_wait();
-    if (use_mask) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = ((mask >> j) & 1u) ? v[j] : 0.f;
-    }
-    uint4 p[6];
-    tc::split8(v, p[0], p[1], p[2]);
-    tc::split8(v + 8, p[3], p[4], p[5]);
-    if (need_bg) wait_bg();
-    if (active) {
-      tc::store_pieces(dst, (c0 >> 3), m, p[0], p[1], p[2]);
-      tc::store_pieces(dst, (c0 >> 3) + 1, m, p[3], p[4], p[5]);
-    }
-  };
-  auto nop = [](float*) {};
   const int cg = g * 16;  // first column of this thread's group in a 64-wide layer
 
   // 64-wide layers use the 16x256b TMEM load shape so that ALL 32 lanes of the warp hold a fragment of
@@ -512,7 +452,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
     const bool valid = g0 && active && valid_s[m] != 0;  // this thread owns a real row of the minibatch
 
     // ---------------------------------------------------------------- encoder forward
-    uint32_t mk_h1 = 0, mk_h2 = 0, mk_b1 = 0, mk_b2 = 0, mk_none = 0;
+    uint32_t mk_h1 = 0, mk_h2 = 0, mk_b1 = 0, mk_b2 = 0;
     // encoder layer 0 (d <= 8 inputs) on the FMA pipe, straight from the gathered observation: no MMA round
     // trip.  The fragment rows' observations come from the fp32 staging written by the gathering lanes.
     if (worker) {
