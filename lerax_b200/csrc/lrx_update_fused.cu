@@ -32,7 +32,6 @@ constexpr int THREADS = WORKERS + 32;  // + warp 16: issues every tcgen05.mma (c
 // ---- shared memory map (bytes).  Matrices: piece stride = R * C * 2.
 constexpr uint32_t PS16 = ROWS * 16 * 2;  // [64][16] piece
 constexpr uint32_t PS64 = ROWS * 64 * 2;  // [64][64] piece
-constexpr uint32_t PS8 = ROWS * 8 * 2;    // [64][8] piece
 constexpr uint32_t OFF_W0 = 0;                         // second observation buffer [64][16] (encoder layer 0 itself runs on the FMA pipe)
 constexpr uint32_t OFF_W1 = OFF_W0 + 3 * PS16;         // [64][64]
 constexpr uint32_t OFF_W2 = OFF_W1 + 3 * PS64;         // [16][64]  (piece = 16*64*2 = PS16)
@@ -70,19 +69,13 @@ static_assert(tc::F_COUNT <= tc::F_RESERVE, "fp32 parameter block too small");
 constexpr uint32_t C_D0 = 0;       // 64: layer outputs
 constexpr uint32_t C_D1 = 64;      // 64: action head layer-1 pre-activations (issued with the value head's)
 constexpr uint32_t C_DF = 128;     // 16: d(features), summed over both heads
-constexpr uint32_t C_G0 = 144;     // enc0  dW^T [64 out][16 in | 8 bias]
-constexpr uint32_t C_G1 = 168;     // enc1  dW^T [64][64 | 8]
+constexpr uint32_t C_G0 = 144;     // enc0  dW^T [64 out][16 in]
+constexpr uint32_t C_G1 = 168;     // enc1  dW^T [64][64]
 constexpr uint32_t C_G2 = 240;     // enc2  dW   [64 in][16 out]
-constexpr uint32_t C_GB2 = 256;    // enc2  db   [*][16]
-constexpr uint32_t C_GV0 = 272;    // v0    dW^T [64][16 | 8]
-constexpr uint32_t C_GV1 = 296;    // v1    dW^T [64][64 | 8]
-constexpr uint32_t C_GV2 = 368;    // v2    dW   [64 in][8] (col 0)
-constexpr uint32_t C_GBV2 = 376;   // v2    db   [*][8]  (col 0)
-constexpr uint32_t C_GA0 = 384;    // a0    dW^T [64][16 | 8]
+constexpr uint32_t C_GV0 = 272;    // v0    dW^T [64][16]
+constexpr uint32_t C_GV1 = 296;    // v1    dW^T [64][64]
+constexpr uint32_t C_GA0 = 384;    // a0    dW^T [64][16]
 constexpr uint32_t C_GA1 = 408;    // a1    dW   [64 in][16 out]
-constexpr uint32_t C_GBA1 = 424;   // a1    db   [*][16]
-constexpr uint32_t C_GMAP = 440;   // map   dW   [64 (16 valid) in][8 (n_out valid)]
-constexpr uint32_t C_GBMAP = 448;  // map   db   [*][8]
 constexpr uint32_t TMEM_COLS = 512;
 
 struct FusedArgs {
@@ -779,31 +772,26 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
       }
     }
   };
-  // dW accumulators: TMEM row = input unit (m), columns = outputs; db in row 0 of its own block
-  auto flush_N = [&](uint32_t col, uint32_t colb, int in_real, int out_real, int out_pad, int layer, bool with_bias) {
+  // dW accumulators: TMEM row = input unit (m), columns = outputs (the biases come from registers)
+  auto flush_N = [&](uint32_t col, int in_real, int out_real, int out_pad, int layer) {
     for (int c0 = 0; c0 < out_pad; c0 += 8) {
-      float v[8], b[8];
+      float v[8];
       umma::tmem_ld8(tw + col + c0, v);
-      if (with_bias) umma::tmem_ld8(tw + colb + c0, b);
       umma::tmem_ld_wait();
       if (active) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (c0 + j < out_real) {
-            if (m < in_real) part[lo.w[layer] + (c0 + j) * in_real + m] = v[j];
-            if (with_bias && m == 0) part[lo.b[layer] + c0 + j] = b[j];
-          }
-        }
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < out_real && m < in_real) part[lo.w[layer] + (c0 + j) * in_real + m] = v[j];
       }
     }
   };
   // nine layers over the four column groups of warps
   umma::tc_fence_after();
   if (!worker) { /* issuer warp: nothing to flush */ } else
-  if (g == 0) { flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0); flush_N(C_G2, C_GB2, 64, 16, 16, tc::L_ENC2, false); }
+  if (g == 0) { flush_T(C_G0, a.obs_dim, 16, tc::L_ENC0); flush_N(C_G2, 64, 16, 16, tc::L_ENC2); }
   if (worker && g == 1) flush_T(C_G1, 64, 64, tc::L_ENC1);
   if (worker && g == 2) { flush_T(C_GV1, 64, 64, tc::L_V1); flush_T(C_GV0, 16, 16, tc::L_V0); }
-  if (worker && g == 3) { flush_T(C_GA0, 16, 16, tc::L_A0); flush_N(C_GA1, C_GBA1, 64, 16, 16, tc::L_A1, false); }
+  if (worker && g == 3) { flush_T(C_GA0, 16, 16, tc::L_A0); flush_N(C_GA1, 64, 16, 16, tc::L_A1); }
 
   // ------------------------------------------------------------------ register bias sums (fixed order)
   __syncthreads();  // every GEMM is done and waited for: XH1 is free
