@@ -343,7 +343,7 @@ def run_ours(args):
                    "measured bf16 tensor peak",
         "gae": "gae_tn2_kernel: 17 algorithmic bytes per element",
     }
-    traffic = {"update": 128.0e6 if (args.envs, args.horizon, args.batches) == (N_ENVS, T_STEPS, N_BATCHES) else None}
+    traffic = {"update": 131.0e6 if (args.envs, args.horizon, args.batches) == (N_ENVS, T_STEPS, N_BATCHES) else None}
     roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": traffic.get(dominant), "kernel": dominant,
                  "peak_source": peaks["source"], "note": notes[dominant]})
 
