@@ -166,6 +166,24 @@ int lrx_rollout(const LrxEnvDesc* env, const LrxPolicyDesc* pol, const float* pa
                 LrxEnvState state, LrxRng rng, const LrxReplay* replay, LrxRolloutOut out,
                 int32_t N, int32_t T, float gamma, lrx_stream_t stream);
 
+/* ---------------------------------------------------------------------------- built-in on_step states
+ * LoggingCallbackStepState (callback/logging/callback.py:90-176) of every env, advanced over
+ * the T steps of a rollout from the reward / done streams the rollout kernel wrote: replaces
+ * LoggingCallback.on_step (:477-480) traced into the per-step scan.  All arrays are [N] device
+ * arrays; they carry the state in and out (zero-initialised = LoggingCallbackStepState.initial()).
+ * ProgressBarCallbackStepState.steps (callback/progress_bar.py:177-181) is `step`. */
+typedef struct {
+  int64_t* step;            /* env steps seen */
+  float* episode_return;    /* running return of the current episode */
+  int32_t* episode_length;
+  uint8_t* episode_done;    /* the previous step ended an episode */
+  float* average_return;    /* EMA over finished episodes, weight alpha on the newest */
+  float* average_length;
+} LrxEpisodeStats;
+/* layout: LRX_LAYOUT_TN / LRX_LAYOUT_NT as for lrx_gae. */
+int lrx_episode_stats(const float* rew, const uint8_t* done, const LrxEpisodeStats* st, int32_t N, int32_t T,
+                      float alpha, int32_t layout, lrx_stream_t stream);
+
 /* ---------------------------------------------------------------------------- GAE
  * advantage/gae.py:36-66 via buffer/rollout.py:64-79.  layout LRX_LAYOUT_TN: arrays are
  * [T][N] (kernel-native); LRX_LAYOUT_NT: [N][T] (reference-native, T contiguous).

@@ -59,6 +59,11 @@ class LrxPpoHyper(C.Structure):
                 ("surrogate", C.c_int32)]
 
 
+class LrxEpisodeStats(C.Structure):
+    _fields_ = [("step", C.c_void_p), ("episode_return", C.c_void_p), ("episode_length", C.c_void_p),
+                ("episode_done", C.c_void_p), ("average_return", C.c_void_p), ("average_length", C.c_void_p)]
+
+
 class LrxBatchView(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("act", C.c_void_p), ("logp", C.c_void_p), ("val", C.c_void_p),
                 ("ret", C.c_void_p), ("adv", C.c_void_p), ("N", C.c_int32), ("T", C.c_int32)]
@@ -79,6 +84,7 @@ PROTOTYPES = {
     "lrx_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,
                           _vp, _vp]),
     "lrx_permutation": (C.c_int, [_vp, C.c_int64, C.c_uint64, _vp]),
+    "lrx_episode_stats": (C.c_int, [_vp, _vp, _P(LrxEpisodeStats), C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp]),
     "lrx_ppo_workspace_bytes": (C.c_size_t, [_P(LrxPolicyDesc), C.c_int64]),
     "lrx_ppo_adv_sums": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int64, _vp, _vp]),
     "lrx_ppo_grad": (C.c_int, [_P(LrxPolicyDesc), _vp, _P(LrxBatchView), _vp, C.c_int64, C.c_int64, _vp,

@@ -210,6 +210,8 @@ class PPO(AbstractAlgorithm):
         rng = L.LrxRng(seed & _MASK64, rank * N, step_offset & 0xFFFFFFFF)
         L.check(L.lib.lrx_rollout(env.desc(), policy.desc(), L.ptr(policy.params), step_state.env_state.c_state(),
                                   rng, replay, out, N, T, float(self.gamma), L.stream_ptr()), "lrx_rollout")
+        # the T on_step calls per env of ppo.py:262-277, for the callbacks whose step state the fused path supports
+        step_state.callback_state = callback.advance_step_state(step_state.callback_state, b["rew"], b["done"], N, T)
         buf = RolloutBuffer(b["obs"], b["act"], b["rew"], b["done"], b["logp"], b["val"],
                             squeeze_env=(self.num_envs == 1))
         buf = buf.compute_returns_and_advantages(b["last_value"], self.gae_lambda, self.gamma, ev_sums=b["ev_sums"])

@@ -3,8 +3,9 @@ callback/list.py:48-162, callback/empty.py:17).
 
 The hooks run on the host between kernel launches.  `on_step` is special: in the reference
 it is traced into the per-step scan; here the rollout is one fused kernel, so only callbacks
-whose `on_step` state is a pure function of the (reward, done) streams can be supported
-(they are recomputed from the buffer, see lerax_b200.callback.EpisodeStatsCallback);
+whose `on_step` state is a pure function of the (reward, done) streams can be supported:
+they implement `advance_step_state`, called once per rollout with the [T][N] reward / done
+buffers (LoggingCallback -> the `lrx_episode_stats` kernel, ProgressBarCallback -> a counter);
 a user callback that overrides `on_step` with anything else raises NotImplementedError.
 """
 
@@ -90,9 +91,17 @@ class AbstractCallback:
     def apply_curriculum(self, state, callback_state):
         return state, callback_state
 
+    # The fused-rollout replacement of T on_step calls per env: rewards / dones are the [T][N] device buffers
+    # of the rollout that just ran.  Built-in callbacks whose step state is a function of those streams override
+    # this (and set _fused_on_step); the default keeps the state.
+    _fused_on_step = False
+
+    def advance_step_state(self, step_state, rewards, dones, num_envs: int, num_steps: int):
+        return step_state
+
     # whether on_step is the inherited no-op (anything else cannot run inside the fused rollout)
     def _has_custom_on_step(self) -> bool:
-        return type(self).on_step is not AbstractCallback.on_step
+        return type(self).on_step is not AbstractCallback.on_step and not self._fused_on_step
 
 
 class EmptyCallback(AbstractCallback):
@@ -111,10 +120,14 @@ class CallbackList(AbstractCallback):
 
     def _each(self, hook, ctx, key):
         states = ctx.state if isinstance(ctx.state, list) else [None] * len(self.callbacks)
+        step_states = getattr(ctx, "step_state", None)
+        step_states = step_states if isinstance(step_states, list) else [None] * len(self.callbacks)
         out = []
-        for cb, st in zip(self.callbacks, states):
-            sub = type(ctx)(**{**ctx.__dict__, "state": st})
-            out.append(getattr(cb, hook)(sub, key=key))
+        for cb, st, sst in zip(self.callbacks, states, step_states):
+            fields = {**ctx.__dict__, "state": st}
+            if "step_state" in fields:
+                fields["step_state"] = sst  # every callback sees its own states (callback/list.py:96-128)
+            out.append(getattr(cb, hook)(type(ctx)(**fields), key=key))
         return out
 
     def on_iteration(self, ctx, *, key=None):
@@ -129,6 +142,11 @@ class CallbackList(AbstractCallback):
     def continue_training(self, ctx, *, key=None):
         return all(self._each("continue_training", ctx, key)) if self.callbacks else True
 
+    def advance_step_state(self, step_state, rewards, dones, num_envs, num_steps):
+        states = step_state if isinstance(step_state, list) else [None] * len(self.callbacks)
+        return [cb.advance_step_state(st, rewards, dones, num_envs, num_steps)
+                for cb, st in zip(self.callbacks, states)]
+
     def apply_curriculum(self, state, callback_state):
         states = callback_state if isinstance(callback_state, list) else [None] * len(self.callbacks)
         new = []
@@ -141,5 +159,11 @@ class CallbackList(AbstractCallback):
         return any(cb._has_custom_on_step() for cb in self.callbacks)
 
 
-__all__ = ["AbstractCallback", "AbstractCallbackState", "AbstractCallbackStepState", "CallbackList",
-           "EmptyCallback", "IterationContext", "ResetContext", "StepContext", "TrainingContext"]
+from .logging import (AbstractLoggingBackend, ConsoleBackend, HistoryBackend, LoggingCallback,  # noqa: E402
+                      LoggingCallbackStepState)
+from .progress_bar import ProgressBarCallback, ProgressBarCallbackStepState  # noqa: E402
+
+__all__ = ["AbstractCallback", "AbstractCallbackState", "AbstractCallbackStepState", "AbstractLoggingBackend",
+           "CallbackList", "ConsoleBackend", "EmptyCallback", "HistoryBackend", "IterationContext", "LoggingCallback",
+           "LoggingCallbackStepState", "ProgressBarCallback", "ProgressBarCallbackStepState", "ResetContext",
+           "StepContext", "TrainingContext"]
