@@ -166,6 +166,26 @@ int lrx_rollout(const LrxEnvDesc* env, const LrxPolicyDesc* pol, const float* pa
                 LrxEnvState state, LrxRng rng, const LrxReplay* replay, LrxRolloutOut out,
                 int32_t N, int32_t T, float gamma, lrx_stream_t stream);
 
+/* ---------------------------------------------------------------------------- multi-GPU gradient exchange
+ * The reference has no collective (single-device vmap); on G GPUs the data-parallel update sums
+ * gradbuf over the ranks between backward and clip + Adam.  These entry points do that
+ * sum over NVLink peer memory instead of a collective library call: every rank allocates an exchange
+ * buffer, hands its 64-byte IPC handle to the peers (any host channel), opens theirs, and passes a
+ * DEVICE array of the G buffer addresses (own buffer at index `rank`) to lrx_p2p_allreduce.
+ * Per minibatch: lrx_ppo_grad writes into lrx_p2p_slot(own, n, seq); lrx_p2p_allreduce(seq) leaves the
+ * rank-ordered sum in `out` (bit-identical on every rank); lrx_ppo_apply consumes `out`.
+ * seq starts at 1 and increases by 1 per exchange on every rank. */
+#define LRX_P2P_HANDLE_BYTES 64
+size_t lrx_p2p_buffer_bytes(int32_t n_floats);
+int lrx_p2p_alloc(int32_t n_floats, void** buffer, unsigned char* ipc_handle /* [LRX_P2P_HANDLE_BYTES] */);
+int lrx_p2p_open(const unsigned char* ipc_handle, void** buffer);
+int lrx_p2p_close(void* peer_buffer);
+int lrx_p2p_free(void* own_buffer);
+float* lrx_p2p_slot(void* own_buffer, int32_t n_floats, uint32_t seq);
+/* error_flag: device int set to 1 if a peer did not arrive within ~10 s (instead of hanging). */
+int lrx_p2p_allreduce(void* const* peer_buffers, int32_t rank, int32_t world, int32_t n_floats, float* out,
+                      uint32_t seq, int32_t* error_flag, lrx_stream_t stream);
+
 /* ---------------------------------------------------------------------------- built-in on_step states
  * LoggingCallbackStepState (callback/logging/callback.py:90-176) of every env, advanced over
  * the T steps of a rollout from the reward / done streams the rollout kernel wrote: replaces
@@ -255,6 +275,15 @@ int lrx_ppo_apply(const LrxPolicyDesc* pol, float* params, float* adam_m, float*
                   int32_t* adam_count, const float* gradbuf, const LrxPpoHyper* h,
                   float* stats_out, int32_t* nonfinite_flag, lrx_stream_t stream);
 
+/* lrx_p2p_allreduce + lrx_ppo_apply in ONE cooperative launch: every block sums its 256 gradient elements over the
+ * ranks' exchange slots, the global norm is assembled at a grid barrier, then clip + Adam (train_batch,
+ * ppo.py:471-492).  The exchange buffers hold n_params + LRX_PPO_NSTATS floats per slot. */
+size_t lrx_ppo_apply_p2p_scratch_bytes(const LrxPolicyDesc* pol);
+int lrx_ppo_apply_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v, int32_t* adam_count,
+                      void* const* peer_buffers, int32_t rank, int32_t world, uint32_t seq, const LrxPpoHyper* h,
+                      float* stats_out, int32_t* nonfinite_flag, int32_t* error_flag, void* scratch,
+                      size_t scratch_bytes, lrx_stream_t stream);
+
 /* One epoch on one GPU: for each of num_batches rows of idx: adv sums, grad, apply
  * (train_epoch, ppo.py:494-521).  stats_out [num_batches][LRX_PPO_NSTATS]. */
 int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
@@ -297,6 +326,8 @@ int lrx_debug_tmem_shape_probe(float* dump, lrx_stream_t stream);
 /* 1 (default): default-width policies run the specialised tensor-core kernels; 0: everything runs
  * the generic-width kernels (also selectable with the environment variable LRX_DISABLE_FUSED=1). */
 void lrx_debug_set_fused(int enabled);
+/* test helper: device-to-device copy of n floats to a raw device address (an exchange slot). */
+int lrx_debug_copy_f32(float* dst, const float* src, int32_t n, lrx_stream_t stream);
 
 /* Probes of the A-operand-in-TMEM layout (mode 0) and of an M = 64 accumulator at TMEM lane 16 (mode 1):
  * dump [128 threads][16 columns] of the accumulator. */

@@ -18,6 +18,7 @@ LRX_ENV_MAX_PARAMS = 16
 LRX_MAX_LAYERS = 8
 LRX_MAX_NOUT = 8
 LRX_LAYOUT_TN, LRX_LAYOUT_NT = 0, 1
+LRX_P2P_HANDLE_BYTES = 64
 LRX_PPO_NSTATS = 8
 
 
@@ -84,6 +85,17 @@ PROTOTYPES = {
     "lrx_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,
                           _vp, _vp]),
     "lrx_permutation": (C.c_int, [_vp, C.c_int64, C.c_uint64, _vp]),
+    "lrx_p2p_buffer_bytes": (C.c_size_t, [C.c_int32]),
+    "lrx_p2p_alloc": (C.c_int, [C.c_int32, _P(C.c_void_p), _vp]),
+    "lrx_p2p_open": (C.c_int, [_vp, _P(C.c_void_p)]),
+    "lrx_p2p_close": (C.c_int, [_vp]),
+    "lrx_p2p_free": (C.c_int, [_vp]),
+    "lrx_p2p_slot": (C.c_void_p, [_vp, C.c_int32, C.c_uint32]),
+    "lrx_p2p_allreduce": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_uint32, _vp, _vp]),
+    "lrx_ppo_apply_p2p_scratch_bytes": (C.c_size_t, [_P(LrxPolicyDesc)]),
+    "lrx_ppo_apply_p2p": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_uint32,
+                                    _P(LrxPpoHyper), _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "lrx_debug_copy_f32": (C.c_int, [_vp, _vp, C.c_int32, _vp]),
     "lrx_episode_stats": (C.c_int, [_vp, _vp, _P(LrxEpisodeStats), C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp]),
     "lrx_ppo_workspace_bytes": (C.c_size_t, [_P(LrxPolicyDesc), C.c_int64]),
     "lrx_ppo_adv_sums": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int64, _vp, _vp]),

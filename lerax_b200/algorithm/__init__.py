@@ -140,6 +140,18 @@ class PPO(AbstractAlgorithm):
     def _lr_at(self, count: int) -> float:
         return float(self.learning_rate(count)) if callable(self.learning_rate) else float(self.learning_rate)
 
+    def _exchange(self, policy, dist):
+        """The peer-memory gradient exchange of this process (None: single GPU, or NCCL fallback)."""
+        if dist is None:
+            return None
+        n = policy.n_params + L.LRX_PPO_NSTATS
+        if getattr(self, "_ex_key", None) != (n, dist.get_world_size()):
+            from .._p2p import make_exchange
+
+            self._ex = make_exchange(n, dist, policy.params.device)
+            self._ex_key = (n, dist.get_world_size())
+        return self._ex
+
     def _local_envs(self) -> int:
         rank, world, _ = _dist()
         if self.num_envs % world:
@@ -252,13 +264,21 @@ class PPO(AbstractAlgorithm):
                                            L.stream_ptr()), "lrx_ppo_adv_sums")
             if dist is not None:
                 dist.all_reduce(b["adv_sums"])  # one collective for the whole epoch
+            ex = self._exchange(policy, dist)
             for i in range(nb):
                 h = self._hyper(self._lr_at(count))
+                # the local gradient goes straight into this rank's exchange slot when peers read it over NVLink
+                grad_dst = ex.next_slot() if ex is not None else L.ptr(b["gradbuf"])
                 L.check(L.lib.lrx_ppo_grad(pol_d, L.ptr(policy.params), view, L.ptr(idx[i]), B_local, B_global,
-                                           L.ptr(b["adv_sums"][i]), h, L.ptr(b["gradbuf"]), ws, ws_bytes,
+                                           L.ptr(b["adv_sums"][i]), h, grad_dst, ws, ws_bytes,
                                            L.stream_ptr()), "lrx_ppo_grad")
+                if ex is not None:
+                    # SUM over the ranks' exchange slots (NVLink peer memory, rank order) + clip + Adam: one launch
+                    ex.apply(pol_d, policy, opt_state, h, stats[e, i], b["nonfinite"])
+                    count += 1
+                    continue
                 if dist is not None:
-                    dist.all_reduce(b["gradbuf"])  # grads || stat sums, SUM over ranks
+                    dist.all_reduce(b["gradbuf"])  # grads || stat sums, SUM over ranks (NCCL)
                 L.check(L.lib.lrx_ppo_apply(pol_d, L.ptr(policy.params), L.ptr(opt_state.mu), L.ptr(opt_state.nu),
                                             L.ptr(opt_state.count), L.ptr(b["gradbuf"]), h, L.ptr(stats[e, i]),
                                             L.ptr(b["nonfinite"]), L.stream_ptr()), "lrx_ppo_apply")
@@ -305,6 +325,8 @@ class PPO(AbstractAlgorithm):
         if self._bufs is not None and int(self._bufs["nonfinite"].item()) != 0:
             self._bufs["nonfinite"].zero_()
             raise FloatingPointError("Non-finite values / log_probs / entropy in ppo_loss (update skipped).")
+        if getattr(self, "_ex", None) is not None:
+            self._ex.check()
 
     # ------------------------------------------------------------------ learn
     def learn(self, env, policy, total_timesteps: int, *, key: Key | int, callback=None):

@@ -13,6 +13,7 @@
 #include <cooperative_groups.h>
 
 #include "lrx_common.cuh"
+#include "lrx_p2p.cuh"
 #include "lrx_policy.cuh"
 
 constexpr int64_t LRX_CHUNK_ROWS = 1 << 20;  // rows of a minibatch processed per pass
@@ -485,6 +486,79 @@ apply_kernel(float* __restrict__ params, float* __restrict__ m, float* __restric
   }
 }
 
+// The same with the exchange inside: every block first sums ITS 256 gradient elements over the ranks'
+// exchange slots in NVLink peer memory (lrx_p2p.cuh; rank order, bit-identical on every rank), the blocks' sums of
+// squares meet at the grid barrier, then clip + Adam on the block's own elements -- gradient all-reduce, global norm
+// and optimiser step in one cooperative launch, no collective library call.  gsum[P + 8] receives the summed
+// gradbuf (the stat sums are read from it); blk_ss holds one double per block.
+__global__ void __launch_bounds__(256)
+apply_p2p_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, int32_t* count,
+                 char* const* __restrict__ peers, int rank, int world, size_t slot_b, uint32_t seq, int* error_flag,
+                 float* __restrict__ gsum, double* __restrict__ blk_ss, int P, int log_std_off, LrxPpoHyper h,
+                 float* stats_out, int32_t* nonfinite_flag) {
+  __shared__ double red[8];
+  __shared__ float norm_s;
+  const int tid = threadIdx.x;
+  p2p::publish_and_wait(peers, rank, world, seq, blockIdx.x == 0, error_flag);
+  const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
+  const int cnt = *count + 1;
+  const int p = blockIdx.x * blockDim.x + tid;
+  float gp = 0.f;
+  if (p < P + LRX_PPO_NSTATS) {
+    const float s = p2p::peer_sum(peers, world, slot_b, seq, p);
+    gsum[p] = s;
+    if (p < P) gp = s + (p == log_std_off ? ls_extra : 0.f);
+  }
+  double ss = warp_sum((double)gp * gp);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    blk_ss[blockIdx.x] = t;
+  }
+  cooperative_groups::this_grid().sync();
+  if (tid == 0) {
+    double t = 0;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += blk_ss[b];  // block order: deterministic
+    norm_s = (float)sqrt(t);
+  }
+  __syncthreads();
+  const float norm = norm_s;
+  const float nbad = gsum[P + 6];
+  const bool bad = nbad > 0.f || !isfinite(norm);
+  if (!bad && p < P) {
+    const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
+    const float bc2 = 1.0f - powf(h.adam_b2, (float)cnt);
+    if (!(norm < h.max_grad_norm)) gp = (gp / norm) * h.max_grad_norm;
+    const float mn = h.adam_b1 * m[p] + (1.0f - h.adam_b1) * gp;
+    const float vn = h.adam_b2 * v[p] + (1.0f - h.adam_b2) * (gp * gp);
+    m[p] = mn;
+    v[p] = vn;
+    const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
+    params[p] = params[p] + (-h.learning_rate) * upd;
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    if (!bad) *count = cnt;
+    else if (nonfinite_flag) atomicOr(nonfinite_flag, 1);
+    if (stats_out) {
+      const float kl = gsum[P + 0] - 1.0f;
+      const float pl = -gsum[P + 1];
+      const float vl = gsum[P + 2] / 2.0f;
+      const float el = -gsum[P + 3];
+      stats_out[0] = kl;
+      stats_out[1] = pl + vl * h.value_loss_coefficient + el * h.entropy_loss_coefficient;
+      stats_out[2] = pl;
+      stats_out[3] = vl;
+      stats_out[4] = el;
+      stats_out[5] = norm;
+      stats_out[6] = nbad;
+      stats_out[7] = 0.f;
+    }
+  }
+}
+
 static int launch_apply(float* params, float* m, float* v, int32_t* count, const float* g, int P, int log_std_off,
                         const LrxPpoHyper& h, float* stats_out, int32_t* nonfinite_flag, cudaStream_t s) {
   LrxPpoHyper hh = h;
@@ -758,6 +832,42 @@ extern "C" int lrx_ppo_apply(const LrxPolicyDesc* pol, float* params, float* ada
   int rc2 = launch_apply(params, adam_m, adam_v, adam_count, gradbuf, pol->n_params, tab.log_std_off, *h, stats_out,
                          nonfinite_flag, (cudaStream_t)stream);
   if (rc2) return rc2;
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+extern "C" size_t lrx_ppo_apply_p2p_scratch_bytes(const LrxPolicyDesc* pol) {
+  if (!pol) return 0;
+  const size_t n = (size_t)pol->n_params + LRX_PPO_NSTATS;
+  return align_up(n * 4, 256) + ((n + 255) / 256) * sizeof(double);
+}
+
+extern "C" int lrx_ppo_apply_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
+                                 int32_t* adam_count, void* const* peer_buffers, int32_t rank, int32_t world,
+                                 uint32_t seq, const LrxPpoHyper* h, float* stats_out, int32_t* nonfinite_flag,
+                                 int32_t* error_flag, void* scratch, size_t scratch_bytes, lrx_stream_t stream) {
+  int rc = lrx_validate_policy(pol);
+  if (rc) return rc;
+  LRX_REQUIRE(params && adam_m && adam_v && adam_count && peer_buffers && h && error_flag && scratch,
+              LRX_ERR_INVALID_ARG, "lrx_ppo_apply_p2p: NULL pointer");
+  LRX_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && seq != 0, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_apply_p2p: bad rank / world / seq");
+  LRX_REQUIRE(scratch_bytes >= lrx_ppo_apply_p2p_scratch_bytes(pol), LRX_ERR_INVALID_ARG,
+              "lrx_ppo_apply_p2p: scratch too small");
+  PolicyTable tab = lrx_make_table(*pol);
+  int P = pol->n_params, n = P + LRX_PPO_NSTATS, log_std_off = tab.log_std_off;
+  char* const* peers = reinterpret_cast<char* const*>(peer_buffers);
+  size_t slot_b = p2p::slot_bytes(n);
+  float* gsum = (float*)scratch;
+  double* blk_ss = (double*)((char*)scratch + align_up((size_t)n * 4, 256));
+  LrxPpoHyper hh = *h;
+  int rk = rank, wd = world;
+  uint32_t sq = seq;
+  void* args[] = {(void*)&params, (void*)&adam_m, (void*)&adam_v, (void*)&adam_count, (void*)&peers, (void*)&rk,
+                  (void*)&wd, (void*)&slot_b, (void*)&sq, (void*)&error_flag, (void*)&gsum, (void*)&blk_ss, (void*)&P,
+                  (void*)&log_std_off, (void*)&hh, (void*)&stats_out, (void*)&nonfinite_flag};
+  LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)apply_p2p_kernel, dim3((n + 255) / 256), dim3(256), args, 0,
+                                             (cudaStream_t)stream));
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }
