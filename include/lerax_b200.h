@@ -214,6 +214,11 @@ int lrx_episode_stats(const float* rew, const uint8_t* done, const LrxEpisodeSta
 int lrx_gae(const float* rew, const float* val, const uint8_t* done, const float* last_value,
             float* adv, float* ret, int32_t N, int32_t T, float gamma, float lam, int32_t layout,
             double* ev_sums, lrx_stream_t stream);
+/* The reference's two other estimators, same arrays and layouts: n_step == 0 is BootstrappedReturn
+ * (advantage/bootstrapped.py:12-79: G_t = r_t + gamma (1 - done_t) G_{t+1}, G_T = last_value), n_step >= 1 is
+ * NStepReturn(n) (advantage/n_step.py:30-70).  adv = ret - val. */
+int lrx_returns(const float* rew, const float* val, const uint8_t* done, const float* last_value, float* adv,
+                float* ret, int32_t N, int32_t T, float gamma, int32_t n_step, int32_t layout, lrx_stream_t stream);
 
 /* ------------------------------------------------------------------- permutation
  * buffer/base_buffer.py:85-88: jr.permutation(key, N*T).  out[n] receives a pseudo-random

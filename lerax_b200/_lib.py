@@ -84,6 +84,7 @@ PROTOTYPES = {
                               LrxRolloutOut, C.c_int32, C.c_int32, C.c_float, _vp]),
     "lrx_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,
                           _vp, _vp]),
+    "lrx_returns": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, _vp]),
     "lrx_permutation": (C.c_int, [_vp, C.c_int64, C.c_uint64, _vp]),
     "lrx_p2p_buffer_bytes": (C.c_size_t, [C.c_int32]),
     "lrx_p2p_alloc": (C.c_int, [C.c_int32, _P(C.c_void_p), _vp]),

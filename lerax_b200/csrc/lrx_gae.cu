@@ -287,3 +287,74 @@ extern "C" int lrx_gae(const float* rew, const float* val, const uint8_t* done,
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }
+
+// ================================================================================ other estimators
+// BootstrappedReturn (advantage/bootstrapped.py:12-79) and NStepReturn (advantage/n_step.py:30-70): the two
+// other AbstractAdvantageEstimators of the reference.  They are not on the PPO path
+// (buffer/rollout.py:70 always builds a GAE); one thread per env (bootstrapped: a serial reverse scan) or per
+// element (n-step: n Horner steps), unfused multiplies and adds so the result equals the NumPy oracle bit for bit.
+__device__ __forceinline__ size_t est_index(int layout, int N, int T, int n, int t) {
+  return layout == LRX_LAYOUT_TN ? (size_t)t * N + n : (size_t)n * T + t;
+}
+
+__global__ void bootstrapped_return_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                                           const uint8_t* __restrict__ done, const float* __restrict__ last_value,
+                                           float* __restrict__ adv, float* __restrict__ ret, int N, int T, float gamma,
+                                           int layout) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float carry = last_value[n];
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t i = est_index(layout, N, T, n, t);
+    const float not_done = done[i] ? 0.0f : 1.0f;
+    carry = __fadd_rn(rew[i], __fmul_rn(__fmul_rn(gamma, not_done), carry));  // reward + gamma * discount * carry
+    ret[i] = carry;
+    adv[i] = __fsub_rn(carry, val[i]);
+  }
+}
+
+__global__ void n_step_return_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                                     const uint8_t* __restrict__ done, const float* __restrict__ last_value,
+                                     float* __restrict__ adv, float* __restrict__ ret, int N, int T, float gamma, int nstep,
+                                     int layout) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)N * T) return;
+  // consecutive threads walk the contiguous axis of the layout
+  const int n = layout == LRX_LAYOUT_TN ? (int)(e % N) : (int)(e / T);
+  const int t = layout == LRX_LAYOUT_TN ? (int)(e / N) : (int)(e % T);
+  // bootstrap value n steps ahead (last_value past the segment), then Horner from k = n-1 down to 0 over the
+  // zero-reward / unit-discount padding of n_step.py:43-52
+  float carry = (t + nstep < T) ? val[est_index(layout, N, T, n, t + nstep)] : last_value[n];
+  for (int k = nstep - 1; k >= 0; --k) {
+    const int tk = t + k;
+    if (tk < T) {
+      const size_t i = est_index(layout, N, T, n, tk);
+      const float disc = __fmul_rn(gamma, done[i] ? 0.0f : 1.0f);
+      carry = __fadd_rn(rew[i], __fmul_rn(disc, carry));
+    }  // padding: 0 + 1 * carry
+  }
+  const size_t i0 = est_index(layout, N, T, n, t);
+  ret[i0] = carry;
+  adv[i0] = __fsub_rn(carry, val[i0]);
+}
+
+extern "C" int lrx_returns(const float* rew, const float* val, const uint8_t* done, const float* last_value, float* adv,
+                           float* ret, int32_t N, int32_t T, float gamma, int32_t n_step, int32_t layout,
+                           lrx_stream_t stream) {
+  LRX_REQUIRE(N >= 0 && T >= 0, LRX_ERR_INVALID_ARG, "lrx_returns: negative size");
+  LRX_REQUIRE(n_step >= 0, LRX_ERR_INVALID_ARG, "lrx_returns: n must be at least 1 (0 selects BootstrappedReturn)");
+  LRX_REQUIRE(layout == LRX_LAYOUT_TN || layout == LRX_LAYOUT_NT, LRX_ERR_INVALID_ARG, "lrx_returns: unknown layout %d",
+              layout);
+  if (N == 0 || T == 0) return LRX_OK;
+  LRX_REQUIRE(rew && val && done && last_value && adv && ret, LRX_ERR_INVALID_ARG, "lrx_returns: NULL pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_step == 0) {
+    bootstrapped_return_kernel<<<(N + 127) / 128, 128, 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, layout);
+  } else {
+    const long long total = (long long)N * T;
+    n_step_return_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma,
+                                                                         n_step, layout);
+  }
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
