@@ -44,7 +44,7 @@ extern "C" {
 typedef void* lrx_stream_t; /* cudaStream_t */
 
 /* ------------------------------------------------------------------ environments
- * env/classic_control/{cartpole,pendulum,acrobot}.py.  Physical parameters are RUNTIME
+ * env/classic_control/{cartpole,pendulum,acrobot,mountain_car,continuous_mountain_car}.py.  Physical parameters are RUNTIME
  * values (curriculum callbacks rewrite them between iterations, curriculum/scheduled.py:133-138).
  * p[] per kind:
  *   CARTPOLE : 0 gravity, 1 cart_mass, 2 pole_mass, 3 half_length, 4 force_mag,
@@ -53,12 +53,18 @@ typedef void* lrx_stream_t; /* cudaStream_t */
  *   ACROBOT  : 0 gravity, 1 link_length_1, 2 link_length_2, 3 link_mass_1, 4 link_mass_2,
  *              5 link_com_pos_1, 6 link_com_pos_2, 7 link_moi, 8 max_vel_1, 9 max_vel_2,
  *              10..12 torques[0..2]                                       (acrobot.py:114-132)
+ *   MOUNTAINCAR : 0 min_position, 1 max_position, 2 max_speed, 3 goal_position, 4 goal_velocity,
+ *              5 force, 6 gravity                                         (mountain_car.py:106-129)
+ *   CONTINUOUS_MOUNTAINCAR : 0 min_action, 1 max_action, 2 min_position, 3 max_position, 4 max_speed,
+ *              5 goal_position, 6 goal_velocity, 7 power                  (continuous_mountain_car.py:91-113)
  * max_episode_steps > 0 applies wrapper/misc.py:115-206 (TimeLimit): truncate when the
  * per-episode step counter reaches it; 0 = bare env, never truncates
  * (base_classic_control.py:74-75). */
 #define LRX_ENV_CARTPOLE 0
 #define LRX_ENV_PENDULUM 1
 #define LRX_ENV_ACROBOT 2
+#define LRX_ENV_MOUNTAINCAR 3
+#define LRX_ENV_CONTINUOUS_MOUNTAINCAR 4
 #define LRX_ENV_MAX_PARAMS 16
 
 typedef struct LrxEnvDesc {
@@ -68,7 +74,7 @@ typedef struct LrxEnvDesc {
   float p[LRX_ENV_MAX_PARAMS];
 } LrxEnvDesc;
 
-/* Per-env carried state, struct-of-arrays: y[k][N] (k = 4, 2, 4), t[N], step_count[N]
+/* Per-env carried state, struct-of-arrays: y[k][N] (k = 4, 2, 4, 2, 2), t[N], step_count[N]
  * (CartPoleState/PendulumState/AcrobotState .y/.t and TimeLimitState.step_count). */
 typedef struct LrxEnvState {
   float* y;

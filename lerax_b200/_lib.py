@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "_C", "liblerax_b200.so")
 
 LRX_OK = 0
 LRX_ENV_CARTPOLE, LRX_ENV_PENDULUM, LRX_ENV_ACROBOT = 0, 1, 2
+LRX_ENV_MOUNTAINCAR, LRX_ENV_CONTINUOUS_MOUNTAINCAR = 3, 4
 LRX_ENV_MAX_PARAMS = 16
 LRX_MAX_LAYERS = 8
 LRX_MAX_NOUT = 8

@@ -38,13 +38,20 @@ int lrx_fused_enabled() {
 }
 extern "C" void lrx_debug_set_fused(int enabled) { g_fused = enabled ? 1 : 0; }
 
-int lrx_env_state_dim(int kind) { return kind == LRX_ENV_PENDULUM ? 2 : 4; }
-int lrx_env_obs_dim(int kind) { return kind == LRX_ENV_CARTPOLE ? 4 : kind == LRX_ENV_PENDULUM ? 3 : 6; }
+int lrx_env_state_dim(int kind) { return (kind == LRX_ENV_CARTPOLE || kind == LRX_ENV_ACROBOT) ? 4 : 2; }
+int lrx_env_obs_dim(int kind) {
+  return kind == LRX_ENV_CARTPOLE ? 4 : kind == LRX_ENV_PENDULUM ? 3 : kind == LRX_ENV_ACROBOT ? 6 : 2;
+}
+bool lrx_env_is_box(int kind) { return kind == LRX_ENV_PENDULUM || kind == LRX_ENV_CONTINUOUS_MOUNTAINCAR; }
+int lrx_env_num_outputs(int kind) {  // policy head width: number of discrete actions, 1 for a scalar Box
+  return kind == LRX_ENV_CARTPOLE ? 2 : (kind == LRX_ENV_ACROBOT || kind == LRX_ENV_MOUNTAINCAR) ? 3 : 1;
+}
 
 int lrx_validate_env(const LrxEnvDesc* env) {
   LRX_REQUIRE(env != nullptr, LRX_ERR_INVALID_ARG, "NULL LrxEnvDesc");
-  LRX_REQUIRE(env->kind >= LRX_ENV_CARTPOLE && env->kind <= LRX_ENV_ACROBOT, LRX_ERR_UNSUPPORTED,
-              "unsupported env kind %d (supported: CartPole, Pendulum, Acrobot)", env->kind);
+  LRX_REQUIRE(env->kind >= LRX_ENV_CARTPOLE && env->kind <= LRX_ENV_CONTINUOUS_MOUNTAINCAR, LRX_ERR_UNSUPPORTED,
+              "unsupported env kind %d (supported: CartPole, Pendulum, Acrobot, MountainCar, ContinuousMountainCar)",
+              env->kind);
   LRX_REQUIRE(env->dt > 0.0f, LRX_ERR_INVALID_ARG, "env dt must be positive");
   LRX_REQUIRE(env->max_episode_steps >= 0, LRX_ERR_INVALID_ARG, "max_episode_steps must be >= 0");
   return LRX_OK;

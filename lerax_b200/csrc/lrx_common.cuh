@@ -66,6 +66,8 @@ int lrx_validate_policy(const LrxPolicyDesc* pol);
 int lrx_validate_env(const LrxEnvDesc* env);
 int lrx_env_state_dim(int kind);
 int lrx_env_obs_dim(int kind);
+bool lrx_env_is_box(int kind);
+int lrx_env_num_outputs(int kind);
 
 // --------------------------------------------------------------------------- Philox
 // Philox4x32-10 (Salmon et al., SC'11).  Restated in oracle/philox.py; KAT in tests/golden.

@@ -10,6 +10,8 @@ template <int KIND> struct EnvDims;
 template <> struct EnvDims<LRX_ENV_CARTPOLE> { static constexpr int SD = 4, OD = 4, NA = 2; static constexpr bool BOX = false; };
 template <> struct EnvDims<LRX_ENV_PENDULUM> { static constexpr int SD = 2, OD = 3, NA = 1; static constexpr bool BOX = true; };
 template <> struct EnvDims<LRX_ENV_ACROBOT>  { static constexpr int SD = 4, OD = 6, NA = 3; static constexpr bool BOX = false; };
+template <> struct EnvDims<LRX_ENV_MOUNTAINCAR> { static constexpr int SD = 2, OD = 2, NA = 3; static constexpr bool BOX = false; };
+template <> struct EnvDims<LRX_ENV_CONTINUOUS_MOUNTAINCAR> { static constexpr int SD = 2, OD = 2, NA = 1; static constexpr bool BOX = true; };
 
 // An action is carried as both views; discrete envs read .i, Box envs read .f.
 struct EnvAction {
@@ -71,6 +73,14 @@ struct Env {
     }
   }
 
+  // ---- Box action bounds (space of the env; ppo.py:228-235 clips the sampled action to them)
+  __device__ __forceinline__ float action_low() const {
+    return KIND == LRX_ENV_PENDULUM ? -c[1] : KIND == LRX_ENV_CONTINUOUS_MOUNTAINCAR ? c[0] : 0.f;
+  }
+  __device__ __forceinline__ float action_high() const {
+    return KIND == LRX_ENV_PENDULUM ? c[1] : KIND == LRX_ENV_CONTINUOUS_MOUNTAINCAR ? c[1] : 0.f;
+  }
+
   // ---- dynamics: cartpole.py:162-177, pendulum.py:89-98, acrobot.py:167-232
   __device__ __forceinline__ void dynamics(const float (&y)[SD], const EnvAction& a,
                                            float (&dy)[SD]) const {
@@ -89,6 +99,16 @@ struct Env {
       float u = lrx_clipf(a.f, -mt, mt);
       float theta_dd = 3.0f * g / (2.0f * l) * sinf(y[0]) + 3.0f / (m * (l * l)) * u;
       dy[0] = y[1]; dy[1] = theta_dd;
+    } else if constexpr (KIND == LRX_ENV_MOUNTAINCAR) {
+      // mountain_car.py:152-158
+      const float u = (float)(a.i - 1) * c[5];
+      const float x_dd = u - c[6] * cosf(3.0f * y[0]);
+      dy[0] = y[1]; dy[1] = x_dd;
+    } else if constexpr (KIND == LRX_ENV_CONTINUOUS_MOUNTAINCAR) {
+      // continuous_mountain_car.py:138-144
+      const float act = lrx_clipf(a.f, c[0], c[1]);
+      const float x_dd = c[7] * act - 0.0025f * cosf(3.0f * y[0]);
+      dy[0] = y[1]; dy[1] = x_dd;
     } else {
       const float g = c[0], l1 = c[1], m1 = c[3], m2 = c[4], lc1 = c[5], lc2 = c[6], moi = c[7];
       const float HALF_PI = 1.57079632679489661923f;
@@ -118,6 +138,16 @@ struct Env {
       y[1] = lrx_wrap_angle(y[1]);
       y[2] = lrx_clipf(y[2], -c[8], c[8]);
       y[3] = lrx_clipf(y[3], -c[9], c[9]);
+    } else if constexpr (KIND == LRX_ENV_MOUNTAINCAR) {
+      // mountain_car.py:160-165: the car stops dead at the left wall
+      float v = lrx_clipf(y[1], -c[2], c[2]);
+      const float x = lrx_clipf(y[0], c[0], c[1]);
+      v = v * (((x != c[0]) || (v > 0.0f)) ? 1.0f : 0.0f);
+      y[0] = x; y[1] = v;
+    } else if constexpr (KIND == LRX_ENV_CONTINUOUS_MOUNTAINCAR) {
+      // continuous_mountain_car.py:146-150
+      y[1] = lrx_clipf(y[1], -c[4], c[4]);
+      y[0] = lrx_clipf(y[0], c[2], c[3]);
     }
   }
 
@@ -170,6 +200,8 @@ struct Env {
       float s, co;
       sincosf(y[0], &s, &co);
       o[0] = co; o[1] = s; o[2] = y[1];
+    } else if constexpr (KIND == LRX_ENV_MOUNTAINCAR || KIND == LRX_ENV_CONTINUOUS_MOUNTAINCAR) {
+      o[0] = y[0]; o[1] = y[1];  // mountain_car.py:167-170, continuous_mountain_car.py:152-155
     } else {
       float s1, c1, s2, c2;
       sincosf(y[0], &s1, &c1);
@@ -178,14 +210,20 @@ struct Env {
     }
   }
 
-  // ---- reward: cartpole.py:187-195, pendulum.py:112-123, acrobot.py:258-270
-  __device__ __forceinline__ float reward(const EnvAction& a, const float (&yn)[SD]) const {
+  // ---- reward(state, action, next_state): cartpole.py:187-195, pendulum.py:112-123, acrobot.py:258-270,
+  // mountain_car.py:172-180, continuous_mountain_car.py:157-168 (the latter tests the PRE-transition state)
+  __device__ __forceinline__ float reward(const EnvAction& a, const float (&y)[SD], const float (&yn)[SD]) const {
     if constexpr (KIND == LRX_ENV_CARTPOLE) {
       return 1.0f;
     } else if constexpr (KIND == LRX_ENV_PENDULUM) {
       float u = lrx_clipf(a.f, -c[1], c[1]);
       float cost = yn[0] * yn[0] + 0.1f * (yn[1] * yn[1]) + 0.001f * (u * u);
       return -cost;
+    } else if constexpr (KIND == LRX_ENV_MOUNTAINCAR) {
+      return -1.0f;
+    } else if constexpr (KIND == LRX_ENV_CONTINUOUS_MOUNTAINCAR) {
+      const float act = lrx_clipf(a.f, c[0], c[1]);
+      return 100.0f * (terminal(y) ? 1.0f : 0.0f) - 0.1f * (act * act);
     } else {
       return terminal(yn) ? 0.0f : -1.0f;
     }
@@ -199,6 +237,10 @@ struct Env {
       return !within;
     } else if constexpr (KIND == LRX_ENV_PENDULUM) {
       return false;
+    } else if constexpr (KIND == LRX_ENV_MOUNTAINCAR) {
+      return (y[0] >= c[3]) && (y[1] >= c[4]);  // mountain_car.py:182-186
+    } else if constexpr (KIND == LRX_ENV_CONTINUOUS_MOUNTAINCAR) {
+      return (y[0] >= c[5]) && (y[1] >= c[6]);  // continuous_mountain_car.py:170-174
     } else {
       return (-cosf(y[0]) - cosf(y[0] + y[1])) > 1.0f;
     }
@@ -219,6 +261,10 @@ struct Env {
       const float PI_F = 3.14159265358979323846f;
       y[0] = fmaxf(-PI_F, __fadd_rn(__fmul_rn(u[0], PI_F - (-PI_F)), -PI_F));
       y[1] = fmaxf(-1.0f, __fadd_rn(__fmul_rn(u[1], 2.0f), -1.0f));
+    } else if constexpr (KIND == LRX_ENV_MOUNTAINCAR || KIND == LRX_ENV_CONTINUOUS_MOUNTAINCAR) {
+      // mountain_car.py:145-149, continuous_mountain_car.py:132-136: x ~ U(-0.6, -0.4), v = 0
+      y[0] = fmaxf(-0.6f, __fadd_rn(__fmul_rn(u[0], -0.4f - (-0.6f)), -0.6f));
+      y[1] = 0.0f;
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) y[i] = fmaxf(-0.1f, __fadd_rn(__fmul_rn(u[i], 0.1f - (-0.1f)), -0.1f));

@@ -51,7 +51,7 @@ __global__ void env_step_kernel(LrxEnvDesc envd, LrxEnvState st, const void* __r
   a.f = EnvDims<KIND>::BOX ? ((const float*)action)[n] : 0.f;
   env.transition(y, st.t[n], a, y1, t1);
   int sc = st.step_count[n] + 1;
-  if (reward) reward[n] = env.reward(a, y1);
+  if (reward) reward[n] = env.reward(a, y, y1);
   if (terminal) terminal[n] = env.terminal(y1) ? 1 : 0;
   if (truncated) truncated[n] = env.truncate(sc) ? 1 : 0;
   if (obs_next) {
@@ -186,7 +186,7 @@ rollout_generic_kernel(const __grid_constant__ LrxEnvDesc envd, const __grid_con
       }
       float a_raw = loc + scale * eps;
       logp = normal_log_prob(loc, scale, log_scale, a_raw);  // log-prob of the UNCLIPPED sample
-      a.f = lrx_clipf(a_raw, -env.c[1], env.c[1]);           // ppo.py:228-235 (Box bounds = +-max_torque)
+      a.f = lrx_clipf(a_raw, env.action_low(), env.action_high());  // ppo.py:228-235 (Box bounds of the env)
     } else {
       float z[LRX_MAX_NOUT];
 #pragma unroll
@@ -225,7 +225,7 @@ rollout_generic_kernel(const __grid_constant__ LrxEnvDesc envd, const __grid_con
     float y1[SD], t1;
     env.transition(y, t, a, y1, t1);
     int sc1 = sc + 1;
-    float r = env.reward(a, y1);
+    float r = env.reward(a, y, y1);
     bool term = env.terminal(y1);
     bool trunc = env.truncate(sc1);
     bool done = term || trunc;
@@ -312,6 +312,8 @@ static int warps_for_smem(const PolicyTable& tab, int max_warps, size_t budget) 
     case LRX_ENV_CARTPOLE: { constexpr int K_ = LRX_ENV_CARTPOLE; __VA_ARGS__; } break; \
     case LRX_ENV_PENDULUM: { constexpr int K_ = LRX_ENV_PENDULUM; __VA_ARGS__; } break; \
     case LRX_ENV_ACROBOT:  { constexpr int K_ = LRX_ENV_ACROBOT;  __VA_ARGS__; } break; \
+    case LRX_ENV_MOUNTAINCAR: { constexpr int K_ = LRX_ENV_MOUNTAINCAR; __VA_ARGS__; } break; \
+    case LRX_ENV_CONTINUOUS_MOUNTAINCAR: { constexpr int K_ = LRX_ENV_CONTINUOUS_MOUNTAINCAR; __VA_ARGS__; } break; \
     default: lrx_set_error("unknown env kind %d", kind); return LRX_ERR_UNSUPPORTED; \
   }
 
@@ -392,9 +394,9 @@ extern "C" int lrx_rollout(const LrxEnvDesc* env, const LrxPolicyDesc* pol, cons
               LRX_ERR_INVALID_ARG, "lrx_rollout: NULL output plane");
   LRX_REQUIRE(pol->obs_dim == lrx_env_obs_dim(env->kind), LRX_ERR_INVALID_ARG,
               "policy obs_dim %d does not match env obs dim %d", pol->obs_dim, lrx_env_obs_dim(env->kind));
-  const bool box = env->kind == LRX_ENV_PENDULUM;
+  const bool box = lrx_env_is_box(env->kind);
   LRX_REQUIRE((pol->is_box != 0) == box, LRX_ERR_INVALID_ARG, "policy action type does not match env");
-  const int na = env->kind == LRX_ENV_CARTPOLE ? 2 : env->kind == LRX_ENV_ACROBOT ? 3 : 1;
+  const int na = lrx_env_num_outputs(env->kind);
   LRX_REQUIRE(pol->n_out == na, LRX_ERR_INVALID_ARG, "policy n_out %d does not match env (%d)", pol->n_out, na);
   if (N == 0) return LRX_OK;
   cudaStream_t s = (cudaStream_t)stream;

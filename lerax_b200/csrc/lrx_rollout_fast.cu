@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_tc_kernel(const __grid_con
         }
         const float a_raw = loc + scale * eps;
         logp = normal_log_prob(loc, scale, log_scale, a_raw);  // log-prob of the UNCLIPPED sample
-        act.f = lrx_clipf(a_raw, -env.c[1], env.c[1]);         // ppo.py:228-235 (Box bounds = +-max_torque)
+        act.f = lrx_clipf(a_raw, env.action_low(), env.action_high());  // ppo.py:228-235 (Box bounds of the env)
       } else {
         float z[LRX_MAX_NOUT];
 #pragma unroll
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_tc_kernel(const __grid_con
       // ---- env.transition / reward / terminal / truncate (ppo.py:237-246)
       env.transition(y, t, act, y1, t1);
       sc1 = sc + 1;
-      r = env.reward(act, y1);
+      r = env.reward(act, y, y1);
       const bool term = env.terminal(y1);
       trunc = env.truncate(sc1);
       done = term || trunc;
@@ -402,6 +402,8 @@ int lrx_rollout_fast(const LrxEnvDesc* env, const LrxPolicyDesc* pol, const floa
     case LRX_ENV_CARTPOLE: rc = launch_tc<LRX_ENV_CARTPOLE>(a, stream); break;
     case LRX_ENV_PENDULUM: rc = launch_tc<LRX_ENV_PENDULUM>(a, stream); break;
     case LRX_ENV_ACROBOT: rc = launch_tc<LRX_ENV_ACROBOT>(a, stream); break;
+    case LRX_ENV_MOUNTAINCAR: rc = launch_tc<LRX_ENV_MOUNTAINCAR>(a, stream); break;
+    case LRX_ENV_CONTINUOUS_MOUNTAINCAR: rc = launch_tc<LRX_ENV_CONTINUOUS_MOUNTAINCAR>(a, stream); break;
     default: return LRX_OK;
   }
   if (rc) return rc;

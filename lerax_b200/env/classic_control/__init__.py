@@ -1,9 +1,10 @@
-"""CartPole, Pendulum and Acrobot with the reference's constructor kwargs and functional
+"""CartPole, Pendulum, Acrobot, MountainCar and ContinuousMountainCar with the reference's constructor kwargs and functional
 env interface (initial / observation / transition / reward / terminal / truncate), batched
 over N envs on the GPU.
 
 Reference: env/classic_control/base_classic_control.py:49-75, cartpole.py:110-203,
-pendulum.py:51-126, acrobot.py:114-277, env/base_env.py:32-131.  The dynamics run in the
+pendulum.py:51-126, acrobot.py:114-277, mountain_car.py:106-186, continuous_mountain_car.py:91-174,
+env/base_env.py:32-131.  The dynamics run in the
 kernels of lerax_b200/csrc/lrx_env.cuh through the C ABI (lrx_env_reset / lrx_env_step /
 lrx_env_observe); physical parameters travel in LrxEnvDesc at call time, so mutating an env
 attribute between iterations (curriculum) takes effect without recompiling anything.
@@ -227,4 +228,51 @@ class Acrobot(AbstractClassicControlEnv):
                 *self.torques]
 
 
-__all__ = ["Acrobot", "CartPole", "Pendulum", "ClassicControlState", "AbstractClassicControlEnv"]
+class MountainCar(AbstractClassicControlEnv):
+    """mountain_car.py:32-186: three discrete actions (push left / none / right), reward -1 per step."""
+
+    name = "MountainCar"
+    kind = L.LRX_ENV_MOUNTAINCAR
+    state_dim = 2
+
+    def __init__(self, *, min_position=-1.2, max_position=0.6, max_speed=0.07, goal_position=0.5, goal_velocity=0.0,
+                 force=0.001, gravity=0.0025, dt=1.0, solver=None, stepsize_controller=None):
+        super().__init__(solver, stepsize_controller)
+        self.min_position, self.max_position, self.max_speed = min_position, max_position, max_speed
+        self.goal_position, self.goal_velocity = goal_position, goal_velocity
+        self.force, self.gravity, self.dt = force, gravity, dt
+        self.low = np.array([min_position, -max_speed], np.float32)
+        self.high = np.array([max_position, max_speed], np.float32)
+        self.action_space = Discrete(3)
+        self.observation_space = Box(self.low, self.high)
+
+    def _params(self):
+        return [self.min_position, self.max_position, self.max_speed, self.goal_position, self.goal_velocity,
+                self.force, self.gravity]
+
+
+class ContinuousMountainCar(AbstractClassicControlEnv):
+    """continuous_mountain_car.py:32-174: scalar Box action (engine power), reward -0.1 a^2 (+100 at the goal)."""
+
+    name = "ContinuousMountainCar"
+    kind = L.LRX_ENV_CONTINUOUS_MOUNTAINCAR
+    state_dim = 2
+
+    def __init__(self, *, min_action=-1.0, max_action=1.0, min_position=-1.2, max_position=0.6, max_speed=0.07,
+                 goal_position=0.5, goal_velocity=0.0, power=0.0015, dt=1.0, solver=None, stepsize_controller=None):
+        super().__init__(solver, stepsize_controller)
+        self.min_action, self.max_action = min_action, max_action
+        self.min_position, self.max_position, self.max_speed = min_position, max_position, max_speed
+        self.goal_position, self.goal_velocity, self.power, self.dt = goal_position, goal_velocity, power, dt
+        self.low = np.array([min_position, -max_speed], np.float32)
+        self.high = np.array([max_position, max_speed], np.float32)
+        self.action_space = Box(min_action, max_action)
+        self.observation_space = Box(self.low, self.high)
+
+    def _params(self):
+        return [self.min_action, self.max_action, self.min_position, self.max_position, self.max_speed,
+                self.goal_position, self.goal_velocity, self.power]
+
+
+__all__ = ["Acrobot", "CartPole", "ContinuousMountainCar", "MountainCar", "Pendulum", "ClassicControlState",
+           "AbstractClassicControlEnv"]

@@ -1,4 +1,5 @@
-"""Classic-control environments (CartPole, Pendulum, Acrobot), vectorised over envs.
+"""Classic-control environments (CartPole, Pendulum, Acrobot, MountainCar, ContinuousMountainCar),
+vectorised over envs.
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  State arrays are ``y[k, N]`` (state
 component on axis 0).  Each function cites the reference lines it restates; the
@@ -9,6 +10,8 @@ closely as a non-XLA evaluation can.
     CartPole: /root/reference/src/lerax/env/classic_control/cartpole.py:110-203
     Pendulum: /root/reference/src/lerax/env/classic_control/pendulum.py:51-126
     Acrobot:  /root/reference/src/lerax/env/classic_control/acrobot.py:114-277
+    MountainCar: /root/reference/src/lerax/env/classic_control/mountain_car.py:106-186
+    ContinuousMountainCar: /root/reference/src/lerax/env/classic_control/continuous_mountain_car.py:91-174
     TimeLimit:/root/reference/src/lerax/wrapper/misc.py:115-206
 """
 
@@ -20,7 +23,7 @@ import numpy as np
 
 from . import tsit5
 
-CARTPOLE, PENDULUM, ACROBOT = 0, 1, 2
+CARTPOLE, PENDULUM, ACROBOT, MOUNTAINCAR, CONTINUOUS_MOUNTAINCAR = 0, 1, 2, 3, 4
 
 
 def _jnp_mod(x, m):
@@ -45,10 +48,10 @@ class EnvSpec:
     is_box: bool = field(init=False)
 
     def __post_init__(self):
-        self.state_dim = {CARTPOLE: 4, PENDULUM: 2, ACROBOT: 4}[self.kind]
-        self.obs_dim = {CARTPOLE: 4, PENDULUM: 3, ACROBOT: 6}[self.kind]
-        self.n_actions = {CARTPOLE: 2, PENDULUM: 0, ACROBOT: 3}[self.kind]
-        self.is_box = self.kind == PENDULUM
+        self.state_dim = {CARTPOLE: 4, PENDULUM: 2, ACROBOT: 4, MOUNTAINCAR: 2, CONTINUOUS_MOUNTAINCAR: 2}[self.kind]
+        self.obs_dim = {CARTPOLE: 4, PENDULUM: 3, ACROBOT: 6, MOUNTAINCAR: 2, CONTINUOUS_MOUNTAINCAR: 2}[self.kind]
+        self.n_actions = {CARTPOLE: 2, PENDULUM: 0, ACROBOT: 3, MOUNTAINCAR: 3, CONTINUOUS_MOUNTAINCAR: 0}[self.kind]
+        self.is_box = self.kind in (PENDULUM, CONTINUOUS_MOUNTAINCAR)
 
     def p(self, name, dtype):
         return dtype(np.float32(self.params[name]))  # reference stores fp32 jnp scalars
@@ -88,6 +91,26 @@ def acrobot(**kw) -> EnvSpec:
     return EnvSpec(ACROBOT, params, dt, mes)
 
 
+def mountain_car(**kw) -> EnvSpec:
+    # mountain_car.py:106-118 defaults
+    params = dict(min_position=-1.2, max_position=0.6, max_speed=0.07, goal_position=0.5, goal_velocity=0.0,
+                  force=0.001, gravity=0.0025)
+    dt = kw.pop("dt", 1.0)
+    mes = kw.pop("max_episode_steps", 0)
+    params.update(kw)
+    return EnvSpec(MOUNTAINCAR, params, dt, mes)
+
+
+def continuous_mountain_car(**kw) -> EnvSpec:
+    # continuous_mountain_car.py:91-104 defaults
+    params = dict(min_action=-1.0, max_action=1.0, min_position=-1.2, max_position=0.6, max_speed=0.07,
+                  goal_position=0.5, goal_velocity=0.0, power=0.0015)
+    dt = kw.pop("dt", 1.0)
+    mes = kw.pop("max_episode_steps", 0)
+    params.update(kw)
+    return EnvSpec(CONTINUOUS_MOUNTAINCAR, params, dt, mes)
+
+
 # ----------------------------------------------------------------------------- initial
 def initial_from_uniform(spec: EnvSpec, u, dtype=np.float32):
     """env.initial with the uniform draws u[k, N] in [0,1) injected.
@@ -102,6 +125,11 @@ def initial_from_uniform(spec: EnvSpec, u, dtype=np.float32):
     elif spec.kind == PENDULUM:
         hi = np.array([[np.pi], [1.0]], dtype)
         lo = -hi
+    elif spec.kind in (MOUNTAINCAR, CONTINUOUS_MOUNTAINCAR):
+        # mountain_car.py:145-149, continuous_mountain_car.py:132-136: x ~ U(-0.6, -0.4), v = 0 (u[1] unused)
+        lo0, hi0 = u.dtype.type(-0.6), u.dtype.type(-0.4)
+        x = np.maximum(lo0, u[0] * (hi0 - lo0) + lo0)
+        return np.stack([x, np.zeros_like(x)])
     else:
         lo = np.full((4, 1), -0.1, dtype)
         hi = np.full((4, 1), 0.1, dtype)
@@ -135,6 +163,18 @@ def dynamics(spec: EnvSpec, y, action):
         u = np.clip(action.astype(y.dtype), -mt, mt)
         theta_dd = dt(3.0) * g / (dt(2.0) * l) * np.sin(theta) + dt(3.0) / (m * (l * l)) * u
         return np.stack([theta_dot, theta_dd])
+    if spec.kind == MOUNTAINCAR:
+        # mountain_car.py:152-158
+        x, x_d = y
+        u = (action - 1).astype(y.dtype) * spec.p("force", dt)
+        x_dd = u - spec.p("gravity", dt) * np.cos(dt(3.0) * x)
+        return np.stack([x_d, x_dd])
+    if spec.kind == CONTINUOUS_MOUNTAINCAR:
+        # continuous_mountain_car.py:138-144
+        x, x_d = y
+        a = np.clip(action.astype(y.dtype), spec.p("min_action", dt), spec.p("max_action", dt))
+        x_dd = spec.p("power", dt) * a - dt(0.0025) * np.cos(dt(3.0) * x)
+        return np.stack([x_d, x_dd])
     # acrobot.py:167-232
     g = spec.p("gravity", dt)
     l1 = spec.p("link_length_1", dt)
@@ -173,6 +213,17 @@ def clip_state(spec: EnvSpec, y):
         ms = spec.p("max_speed", dt)
         theta = _jnp_mod(y[0] + pi, two_pi) - pi
         return np.stack([theta, np.clip(y[1], -ms, ms)])
+    if spec.kind == MOUNTAINCAR:
+        # mountain_car.py:160-165
+        ms, lo, hi = spec.p("max_speed", dt), spec.p("min_position", dt), spec.p("max_position", dt)
+        v = np.clip(y[1], -ms, ms)
+        x = np.clip(y[0], lo, hi)
+        v = v * ((x != lo) | (v > dt(0.0))).astype(y.dtype)
+        return np.stack([x, v])
+    if spec.kind == CONTINUOUS_MOUNTAINCAR:
+        # continuous_mountain_car.py:146-150
+        ms, lo, hi = spec.p("max_speed", dt), spec.p("min_position", dt), spec.p("max_position", dt)
+        return np.stack([np.clip(y[0], lo, hi), np.clip(y[1], -ms, ms)])
     # acrobot.py:234-241
     mv1, mv2 = spec.p("max_vel_1", dt), spec.p("max_vel_2", dt)
     a1 = _jnp_mod(y[0] + pi, two_pi) - pi
@@ -193,6 +244,8 @@ def observation(spec: EnvSpec, y):
         return y  # cartpole.py:182-185
     if spec.kind == PENDULUM:
         return np.stack([np.cos(y[0]), np.sin(y[0]), y[1]])  # pendulum.py:106-110
+    if spec.kind in (MOUNTAINCAR, CONTINUOUS_MOUNTAINCAR):
+        return y  # mountain_car.py:167-170, continuous_mountain_car.py:152-155
     # acrobot.py:243-256
     return np.stack([np.cos(y[0]), np.sin(y[0]), np.cos(y[1]), np.sin(y[1]), y[2], y[3]])
 
@@ -208,6 +261,12 @@ def reward(spec: EnvSpec, y, action, y_next):
         u = np.clip(action.astype(y.dtype), -mt, mt)
         cost = theta * theta + dt(0.1) * (theta_dot * theta_dot) + dt(0.001) * (u * u)
         return -cost
+    if spec.kind == MOUNTAINCAR:
+        return np.full(y.shape[1], -1.0, dtype=y.dtype)  # mountain_car.py:172-180
+    if spec.kind == CONTINUOUS_MOUNTAINCAR:
+        # continuous_mountain_car.py:157-168: the bonus tests the PRE-transition state
+        a = np.clip(action.astype(y.dtype), spec.p("min_action", dt), spec.p("max_action", dt))
+        return dt(100.0) * terminal(spec, y).astype(y.dtype) - dt(0.1) * (a * a)
     # acrobot.py:258-270
     return _acrobot_done(y_next).astype(y.dtype) - dt(1.0)
 
@@ -227,6 +286,9 @@ def terminal(spec: EnvSpec, y):
         return ~within
     if spec.kind == PENDULUM:
         return np.zeros(y.shape[1], dtype=bool)  # pendulum.py:125-126
+    if spec.kind in (MOUNTAINCAR, CONTINUOUS_MOUNTAINCAR):
+        # mountain_car.py:182-186, continuous_mountain_car.py:170-174
+        return (y[0] >= spec.p("goal_position", dt)) & (y[1] >= spec.p("goal_velocity", dt))
     return _acrobot_done(y)  # acrobot.py:272-277
 
 
@@ -241,5 +303,7 @@ def truncate(spec: EnvSpec, step_count):
 def action_bounds(spec: EnvSpec, dtype=np.float32):
     """Box bounds used by PPO.step's clip (ppo.py:228-235); Pendulum: +-max_torque."""
     assert spec.is_box
+    if spec.kind == CONTINUOUS_MOUNTAINCAR:
+        return spec.p("min_action", dtype), spec.p("max_action", dtype)
     mt = spec.p("max_torque", dtype)
     return -mt, mt

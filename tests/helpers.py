@@ -10,7 +10,8 @@ from oracle import policy as OP
 
 
 def oracle_env(kind: str, **kw):
-    return {"cartpole": OE.cartpole, "pendulum": OE.pendulum, "acrobot": OE.acrobot}[kind](**kw)
+    return {"cartpole": OE.cartpole, "pendulum": OE.pendulum, "acrobot": OE.acrobot,
+            "mountain_car": OE.mountain_car, "continuous_mountain_car": OE.continuous_mountain_car}[kind](**kw)
 
 
 def oracle_policy_spec(env_spec, **kw):
@@ -19,11 +20,12 @@ def oracle_policy_spec(env_spec, **kw):
 
 
 def lib_env(kind: str, **kw):
-    from lerax_b200.env.classic_control import Acrobot, CartPole, Pendulum
+    from lerax_b200.env.classic_control import Acrobot, CartPole, ContinuousMountainCar, MountainCar, Pendulum
     from lerax_b200.wrapper import TimeLimit
 
     mes = kw.pop("max_episode_steps", 0)
-    env = {"cartpole": CartPole, "pendulum": Pendulum, "acrobot": Acrobot}[kind](**kw)
+    env = {"cartpole": CartPole, "pendulum": Pendulum, "acrobot": Acrobot, "mountain_car": MountainCar,
+           "continuous_mountain_car": ContinuousMountainCar}[kind](**kw)
     return TimeLimit(env, mes) if mes else env
 
 

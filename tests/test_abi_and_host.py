@@ -96,11 +96,12 @@ def test_policy_descriptor_matches_oracle_layout():
 
 
 def test_env_descriptors_and_defaults():
-    from lerax_b200.env.classic_control import Acrobot, CartPole, Pendulum
+    from lerax_b200.env.classic_control import Acrobot, CartPole, ContinuousMountainCar, MountainCar, Pendulum
     from lerax_b200.wrapper import TimeLimit
     from oracle import envs as OE
 
-    for env, o in ((CartPole(), OE.cartpole()), (Pendulum(), OE.pendulum()), (Acrobot(), OE.acrobot())):
+    for env, o in ((CartPole(), OE.cartpole()), (Pendulum(), OE.pendulum()), (Acrobot(), OE.acrobot()),
+                   (MountainCar(), OE.mountain_car()), (ContinuousMountainCar(), OE.continuous_mountain_car())):
         d = env.desc()
         assert d.kind == o.kind and d.dt == np.float32(o.dt) and d.max_episode_steps == 0
         vals = [np.float32(v) for v in o.params.values()]

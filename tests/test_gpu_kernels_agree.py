@@ -12,7 +12,7 @@ import helpers as H
 from test_gpu_parity import noise_for, setup, synthetic_buffer
 
 pytestmark = pytest.mark.gpu
-KINDS = ["cartpole", "pendulum", "acrobot"]
+KINDS = ["cartpole", "pendulum", "acrobot", "mountain_car", "continuous_mountain_car"]
 
 
 @pytest.fixture

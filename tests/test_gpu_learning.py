@@ -71,7 +71,7 @@ def test_ppo_learns_cartpole():
     assert best >= 475.0, best
 
 
-@pytest.mark.parametrize("kind", ["cartpole", "pendulum", "acrobot"])
+@pytest.mark.parametrize("kind", ["cartpole", "pendulum", "acrobot", "mountain_car", "continuous_mountain_car"])
 def test_a2c_surrogate_gradient_matches_oracle(kind):
     """a2c.py:381-411 / reinforce.py:372-396: policy loss -mean(log_prob * advantage), one step on the whole buffer."""
     from oracle import ppo as OU

@@ -20,7 +20,7 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL = 1e-5, 2e-6  # north_star: 1e-5 relative in fp32 (atol for values near zero)
-KINDS = ["cartpole", "pendulum", "acrobot"]
+KINDS = ["cartpole", "pendulum", "acrobot", "mountain_car", "continuous_mountain_car"]
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -112,7 +112,8 @@ def test_env_step_teacher_forced(kind):
 
 
 # ------------------------------------------------------------------------- policy
-@pytest.mark.parametrize("kind,pkw", [("cartpole", {}), ("pendulum", {}), ("acrobot", {}),
+@pytest.mark.parametrize("kind,pkw", [("cartpole", {}), ("pendulum", {}), ("acrobot", {}), ("mountain_car", {}),
+                                      ("continuous_mountain_car", {}),
                                       ("pendulum", dict(feature_width=256, value_width=256, action_width=256)),
                                       ("cartpole", dict(feature_size=8, feature_width=24, feature_depth=3,
                                                         value_width=40, value_depth=1, action_width=12,

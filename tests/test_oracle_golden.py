@@ -194,3 +194,37 @@ def test_initial_ranges():
     assert (np.abs(y[0]) <= np.pi + 1e-6).all() and (np.abs(y[1]) <= 1).all()
     y = E.initial_from_uniform(E.acrobot(), u)
     assert (np.abs(y) <= 0.1 + 1e-7).all()
+
+
+# ------------------------------------------------------------------ MountainCar / ContinuousMountainCar
+def test_mountain_car_semantics():
+    """mountain_car.py:145-186: initial range, constant -1 reward, left-wall stop, goal test."""
+    spec = E.mountain_car()
+    u = np.array([[0.0, 0.5, 0.999999], [0.3, 0.3, 0.3]], np.float32)
+    y = E.initial_from_uniform(spec, u)
+    assert np.allclose(y[0], [-0.6, -0.5, -0.4], atol=1e-6) and np.all(y[1] == 0)
+    act = np.array([0, 1, 2])
+    y1, t1 = E.transition(spec, y, np.zeros(3, np.float32), act)
+    assert np.all(t1 == 1.0) and np.all(E.reward(spec, y, act, y1) == -1.0)
+    assert y1[1, 0] < y1[1, 1] < y1[1, 2]  # push left < none < push right
+    # at the left wall a negative velocity is zeroed, a positive one survives (the car stops dead)
+    wall = E.clip_state(spec, np.array([[-1.3, -1.3, -1.0], [-0.05, 0.03, -0.2]], np.float32))
+    assert np.allclose(wall, [[-1.2, -1.2, -1.0], [0.0, 0.03, -0.07]])
+    term = E.terminal(spec, np.array([[0.5, 0.5, 0.49], [0.0, -0.01, 0.05]], np.float32))
+    assert term.tolist() == [True, False, False]
+
+
+def test_continuous_mountain_car_semantics():
+    """continuous_mountain_car.py:132-174: action clipped to the Box, reward -0.1 a^2 (+100 when the PRE-transition
+    state is at the goal), no wall stop."""
+    spec = E.continuous_mountain_car()
+    assert E.action_bounds(spec) == (np.float32(-1.0), np.float32(1.0))
+    y = np.array([[-0.5, -0.5, 0.55], [0.0, 0.0, 0.01]], np.float32)
+    act = np.array([3.0, -0.5, 0.2], np.float32)
+    y1, _ = E.transition(spec, y, np.zeros(3, np.float32), act)
+    r = E.reward(spec, y, act, y1)
+    assert np.allclose(r, [-0.1, -0.025, 100.0 - 0.1 * 0.04], rtol=1e-6)
+    y_sat, _ = E.transition(spec, y, np.zeros(3, np.float32), np.array([1.0, -0.5, 0.2], np.float32))
+    assert y1[1, 0] == y_sat[1, 0]  # 3.0 acts like 1.0
+    wall = E.clip_state(spec, np.array([[-1.3], [-0.05]], np.float32))
+    assert np.allclose(wall, [[-1.2], [-0.05]])
