@@ -16,13 +16,36 @@ class AbstractBuffer:
 
 
 class RolloutBuffer(AbstractBuffer):
-    def __init__(self, obs_tn, act_tn, rew_tn, done_tn, logp_tn, val_tn, ret_tn=None, adv_tn=None,
-                 squeeze_env: bool = False):
+    def __init__(self, obs_tn=None, act_tn=None, rew_tn=None, done_tn=None, logp_tn=None, val_tn=None, ret_tn=None,
+                 adv_tn=None, squeeze_env: bool = False, *, observations=None, actions=None, rewards=None, dones=None,
+                 log_probs=None, values=None, returns=None, advantages=None, states=None, action_masks=None):
+        """Positional arguments: the kernels' time-major [T][N] device tensors (what the training loop passes).
+        Keyword arguments: the reference's constructor (buffer/rollout.py:21-50) with per-env [T] arrays or the
+        vmapped [N, T] form; they are moved to the GPU and stored time-major."""
+        if rewards is not None:
+            torch = L.require_cuda()
+            dev = torch.device("cuda", torch.cuda.current_device())
+            rew = torch.as_tensor(rewards, dtype=torch.float32, device=dev)
+            squeeze_env = rew.dim() == 1
+
+            def tn(x, dtype):
+                if x is None:
+                    return None
+                t = torch.as_tensor(x, device=dev).to(dtype)
+                t = t.unsqueeze(0) if squeeze_env else t
+                return t.transpose(0, 1).contiguous()  # [N, T, ...] -> [T, N, ...]
+
+            act = torch.as_tensor(actions, device=dev)
+            obs_tn = tn(observations, torch.float32)
+            act_tn = tn(actions, torch.float32 if act.is_floating_point() else torch.int32)
+            rew_tn, done_tn = tn(rewards, torch.float32), tn(dones, torch.uint8)
+            logp_tn, val_tn = tn(log_probs, torch.float32), tn(values, torch.float32)
+            ret_tn, adv_tn = tn(returns, torch.float32), tn(advantages, torch.float32)
         self._obs, self._act, self._rew, self._done = obs_tn, act_tn, rew_tn, done_tn
         self._logp, self._val, self._ret, self._adv = logp_tn, val_tn, ret_tn, adv_tn
         self._squeeze = squeeze_env
-        self.states = None
-        self.action_masks = None
+        self.states = states
+        self.action_masks = action_masks
 
     # ---- reference-shaped views
     def _v(self, x):
@@ -58,12 +81,14 @@ class RolloutBuffer(AbstractBuffer):
         T, N = self.num_steps, self.num_envs
         adv = torch.empty_like(self._rew)
         ret = torch.empty_like(self._rew)
-        lv = torch.as_tensor(last_value, dtype=torch.float32, device=self._rew.device).reshape(N).contiguous()
+        lv = torch.as_tensor(last_value, dtype=torch.float32, device=self._rew.device).reshape(-1).expand(N).contiguous()
         L.check(L.lib.lrx_gae(L.ptr(self._rew), L.ptr(self._val), L.ptr(self._done), L.ptr(lv), L.ptr(adv),
                               L.ptr(ret), N, T, float(gamma), float(gae_lambda), L.LRX_LAYOUT_TN,
                               L.ptr(ev_sums), L.stream_ptr()), "lrx_gae")
-        return RolloutBuffer(self._obs, self._act, self._rew, self._done, self._logp, self._val, ret, adv,
-                             self._squeeze)
+        out = RolloutBuffer(self._obs, self._act, self._rew, self._done, self._logp, self._val, ret, adv,
+                            self._squeeze)
+        out.states, out.action_masks = self.states, self.action_masks
+        return out
 
     def view(self) -> L.LrxBatchView:
         return L.LrxBatchView(L.ptr(self._obs), L.ptr(self._act), L.ptr(self._logp), L.ptr(self._val),

@@ -67,3 +67,25 @@ def test_empty_and_invalid():
     assert L.lib.lrx_returns(None, None, None, None, None, None, 5, 0, 0.9, 3, L.LRX_LAYOUT_TN, L.stream_ptr()) == 0
     assert L.lib.lrx_returns(None, None, None, None, None, None, 5, 5, 0.9, 3, L.LRX_LAYOUT_TN, L.stream_ptr()) != 0
     assert L.lib.lrx_returns(None, None, None, None, None, None, 5, 5, 0.9, -1, L.LRX_LAYOUT_TN, L.stream_ptr()) != 0
+
+
+def test_rollout_buffer_reference_constructor_keeps_gae_api():
+    """tests/test_buffer.py:58-82 of the reference: keyword constructor with per-env [T] arrays, stateless policy,
+    action masks carried through, returns == advantages + values."""
+    import torch
+
+    from lerax_b200.buffer import RolloutBuffer
+    from oracle import gae as G
+
+    masks = torch.tensor([[True, True], [True, False]])
+    buffer = RolloutBuffer(observations=np.array([[0.0], [1.0]], f32), actions=np.array([0, 1]),
+                           rewards=np.array([1.0, 1.0], f32), dones=np.array([False, True]),
+                           log_probs=np.array([-0.1, -0.2], f32), values=np.array([0.5, 0.25], f32), states=None,
+                           action_masks=masks)
+    updated = buffer.compute_returns_and_advantages(last_value=0.0, gae_lambda=0.95, gamma=0.99)
+    assert updated.states is None and updated.action_masks is masks and buffer.action_masks is masks
+    adv, ret, val = updated.advantages.cpu().numpy(), updated.returns.cpu().numpy(), updated.values.cpu().numpy()
+    assert adv.shape == (2,) and np.all(np.isfinite(adv)) and np.allclose(ret, adv + val)
+    want = G.gae(np.array([1.0, 1.0], f32), np.array([0.5, 0.25], f32), np.array([False, True]), f32(0.0), 0.99, 0.95)
+    assert np.allclose(adv, want[0], rtol=1e-6) and np.allclose(ret, want[1], rtol=1e-6)
+    assert updated.observations.shape == (2, 1) and updated.actions.tolist() == [0, 1]
