@@ -104,8 +104,22 @@ class AbstractCallback:
         return type(self).on_step is not AbstractCallback.on_step and not self._fused_on_step
 
 
-class EmptyCallback(AbstractCallback):
+class EmptyCallbackState(AbstractCallbackState):
+    """callback/base_callback.py: the state of callbacks that keep none."""
+
+
+class EmptyCallbackStepState(AbstractCallbackStepState):
     pass
+
+
+class EmptyCallback(AbstractCallback):
+    """callback/empty.py:17: every hook hands its (empty) state back unchanged."""
+
+    def reset(self, ctx, *, key=None):
+        return EmptyCallbackState()
+
+    def step_reset(self, ctx, *, key=None):
+        return EmptyCallbackStepState()
 
 
 class CallbackList(AbstractCallback):
@@ -164,6 +178,6 @@ from .logging import (AbstractLoggingBackend, ConsoleBackend, HistoryBackend, Lo
 from .progress_bar import ProgressBarCallback, ProgressBarCallbackStepState  # noqa: E402
 
 __all__ = ["AbstractCallback", "AbstractCallbackState", "AbstractCallbackStepState", "AbstractLoggingBackend",
-           "CallbackList", "ConsoleBackend", "EmptyCallback", "HistoryBackend", "IterationContext", "LoggingCallback",
-           "LoggingCallbackStepState", "ProgressBarCallback", "ProgressBarCallbackStepState", "ResetContext",
-           "StepContext", "TrainingContext"]
+           "CallbackList", "ConsoleBackend", "EmptyCallback", "EmptyCallbackState", "EmptyCallbackStepState",
+           "HistoryBackend", "IterationContext", "LoggingCallback", "LoggingCallbackStepState", "ProgressBarCallback",
+           "ProgressBarCallbackStepState", "ResetContext", "StepContext", "TrainingContext"]

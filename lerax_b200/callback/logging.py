@@ -15,7 +15,7 @@ from datetime import datetime
 from typing import Any, Sequence
 
 from .. import _lib as L
-from . import AbstractCallback, AbstractCallbackStepState
+from . import AbstractCallback, AbstractCallbackStepState, EmptyCallbackState
 
 
 class AbstractLoggingBackend:
@@ -137,6 +137,9 @@ class LoggingCallback(AbstractCallback):
         self._name = name
         for b in self._backends:
             b.open(name)
+
+    def reset(self, ctx, *, key=None):
+        return EmptyCallbackState()
 
     def step_reset(self, ctx, *, key=None):
         loc = ctx.locals

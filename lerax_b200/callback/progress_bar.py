@@ -9,7 +9,7 @@ from dataclasses import dataclass
 from typing import Any
 
 from .. import _lib as L
-from . import AbstractCallback, AbstractCallbackStepState
+from . import AbstractCallback, AbstractCallbackStepState, EmptyCallbackState
 
 
 @dataclass
@@ -36,7 +36,7 @@ class ProgressBarCallback(AbstractCallback):
             from tqdm import tqdm
 
             self._bar = tqdm(total=self.total, desc=self.name, unit="step")
-        return None
+        return EmptyCallbackState()
 
     def step_reset(self, ctx, *, key=None):
         torch = L.require_cuda()

@@ -159,3 +159,24 @@ def test_spaces():
     assert Box(-np.ones(3), np.ones(3)).flat_size == 3
     d = Discrete(3)
     assert d.n == 3 and d.contains(2) and not d.contains(3)
+
+
+def test_empty_callback_preserves_empty_state():
+    """tests/test_empty_callback.py of the reference."""
+    from types import SimpleNamespace
+
+    from lerax_b200.callback import EmptyCallback, EmptyCallbackState, EmptyCallbackStepState, ResetContext
+
+    callback = EmptyCallback()
+    callback_state = callback.reset(ResetContext(locals={}), key=0)
+    callback_step_state = callback.step_reset(ResetContext(locals={}), key=0)
+    step_context = SimpleNamespace(state=callback_step_state)
+    iteration_context = SimpleNamespace(state=callback_state)
+    training_context = SimpleNamespace(state=callback_state)
+    assert isinstance(callback_state, EmptyCallbackState)
+    assert isinstance(callback_step_state, EmptyCallbackStepState)
+    assert callback.on_step(step_context, key=0) is callback_step_state
+    assert callback.on_iteration(iteration_context, key=0) is callback_state
+    assert callback.on_training_start(training_context, key=0) is callback_state
+    assert callback.on_training_end(training_context, key=0) is callback_state
+    assert callback.continue_training(iteration_context, key=0)
