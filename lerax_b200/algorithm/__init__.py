@@ -10,6 +10,8 @@ with more than one rank).  Host code only sequences launches; nothing is compute
 
 from __future__ import annotations
 
+import copy
+
 from dataclasses import dataclass
 from typing import Any, Callable, Sequence
 
@@ -194,6 +196,7 @@ class PPO(AbstractAlgorithm):
         if not policy.params.is_cuda:
             policy = policy.to(torch.device("cuda", torch.cuda.current_device()))  # H2D of the parameters
         policy = policy.with_params(policy.params.clone())  # learn() does not mutate its input
+        env = copy.copy(env)  # curriculum callbacks rewrite fields of the TRAINING state's env, not the caller's
         rank, world, _ = _dist()
         N = self._local_envs()
         dev = policy.params.device

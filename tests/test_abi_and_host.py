@@ -180,3 +180,18 @@ def test_empty_callback_preserves_empty_state():
     assert callback.on_training_start(training_context, key=0) is callback_state
     assert callback.on_training_end(training_context, key=0) is callback_state
     assert callback.continue_training(iteration_context, key=0)
+
+
+def test_schedule_functions():
+    """tests/test_curriculum.py:75-91 of the reference."""
+    from lerax_b200.curriculum import cosine_schedule, linear_schedule, step_schedule
+
+    lin = linear_schedule(start=0.0, end=1.0, total=100)
+    assert np.isclose(lin(0), 0.0) and np.isclose(lin(50), 0.5) and np.isclose(lin(100), 1.0)
+    assert np.isclose(lin(200), 1.0)  # clamped
+    stp = step_schedule(values=[1.0, 2.0, 3.0], boundaries=[10, 20])
+    assert [stp(i) for i in (0, 9, 10, 19, 20)] == [1.0, 1.0, 2.0, 2.0, 3.0]
+    cos = cosine_schedule(start=2.0, end=0.0, total=10)
+    assert np.isclose(cos(0), 2.0) and np.isclose(cos(5), 1.0, atol=1e-6) and np.isclose(cos(10), 0.0, atol=1e-6)
+    with pytest.raises(ValueError):
+        step_schedule(values=[1.0], boundaries=[1, 2])
