@@ -336,9 +336,11 @@ def run_ours(args):
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s"}
     notes = {
         "update": "ppo_grad_fused_kernel (tcgen05, bf16x3 fp32 emulation): achieved = algorithmic fp32 FLOPs (75.3 kFLOP "
-                  "per row-epoch) / update-stage time; the kernel executes 6 bf16 MMAs per fp32 product on top of that. "
-                  "traffic = dram bytes per fused launch (one minibatch of envs*horizon/minibatches rows) from the "
-                  "ncu --set full capture in profiles/r1_ppo_grad_fused.md",
+                  "per row-epoch) / update-stage time. The kernel executes 6 bf16 MMAs per fp32 product and pads 16-wide "
+                  "layers to the M = 64 tile: 384 MMAs = 29.1 MFLOP per 64-row tile = 455 kFLOP per row-epoch, i.e. "
+                  "`executed_tflops` (ncu: tensor pipe 28 % math-active). traffic = dram bytes per fused launch (one "
+                  "minibatch of envs*horizon/minibatches rows; 9.4 MB algorithmic, the rest is one 32-byte sector per "
+                  "gathered 4-byte plane element) from the ncu --set full capture in profiles/r1_ppo_grad_fused.md",
         "rollout": "rollout_tc_kernel (tcgen05, bf16x3 fp32 emulation): algorithmic fp32 FLOPs / rollout time against the "
                    "measured bf16 tensor peak",
         "gae": "gae_tn2_kernel: 17 algorithmic bytes per element",
@@ -346,6 +348,9 @@ def run_ours(args):
     traffic = {"update": 131.0e6 if (args.envs, args.horizon, args.batches) == (N_ENVS, T_STEPS, N_BATCHES) else None}
     roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": traffic.get(dominant), "kernel": dominant,
                  "peak_source": peaks["source"], "note": notes[dominant]})
+    if dominant == "update" and [list(c) for c in policy._dims] == [[4, 64, 64, 16], [16, 64, 64, 1], [16, 64, 16, 2]]:
+        executed = 455.0e3 * rows * args.epochs / (upd_ms / 1e3) / 1e12  # bf16 MMA FLOPs actually issued
+        roof.update({"executed_tflops": executed, "executed_frac": executed / peaks["tflops"]})
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
