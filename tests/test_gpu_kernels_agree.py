@@ -101,7 +101,30 @@ def test_full_size_properties():
     P = spec.n_params
     scale = np.abs(g_all[:P]).max()
     H.assert_close(g_1[:P] + g_2[:P], g_all[:P], 1e-4, 2e-6 * scale, "gradient linearity")
+    g_again, _ = H.run_grad(pol, buf, idx, hp)
+    np.testing.assert_array_equal(g_all, g_again)  # 28 tiles per CTA, prefetched rows, fixed-order reductions
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "pendulum", "mountain_car"])
+def test_gradient_many_tiles_per_cta_vs_generic(kind, fused_toggle):
+    """Every CTA of the fused kernel walks two or three tiles (row staging double buffer, buffer reuse across tiles,
+    a ragged last tile); the generic layer-by-layer kernels are the independent implementation."""
+    T, N = 64, 400
+    B = 64 * 148 * 2 + 37
+    spec, params, pol, rng, flat, buf = synthetic_buffer(kind, T, N, seed=5)
+    hp = OU.Hyper(clip_value_loss=True, entropy_loss_coefficient=0.01)
+    idx = rng.permutation(T * N)[:B].astype(np.int32)
+    fused_toggle(1)
+    ga, _ = H.run_grad(pol, buf, idx, hp)
+    ga2, _ = H.run_grad(pol, buf, idx, hp)
+    np.testing.assert_array_equal(ga, ga2)
+    fused_toggle(0)
+    gb, _ = H.run_grad(pol, buf, idx, hp)
+    P = spec.n_params
+    scale = np.abs(gb[:P]).max()
+    H.assert_close(ga[:P], gb[:P], 1e-4, 1e-5 * scale, "gradient")
+    H.assert_close(ga[P:P + 4], gb[P:P + 4], 1e-5, 1e-6, "stat sums")
 
 
 @pytest.mark.parametrize("n", [1, 2, 7, 256, 1000, 65536, 8388608])
