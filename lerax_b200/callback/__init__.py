@@ -176,8 +176,9 @@ class CallbackList(AbstractCallback):
 from .logging import (AbstractLoggingBackend, ConsoleBackend, HistoryBackend, LoggingCallback,  # noqa: E402
                       LoggingCallbackStepState)
 from .progress_bar import ProgressBarCallback, ProgressBarCallbackStepState  # noqa: E402
+from .tensorboard import TensorBoardBackend  # noqa: E402
 
 __all__ = ["AbstractCallback", "AbstractCallbackState", "AbstractCallbackStepState", "AbstractLoggingBackend",
            "CallbackList", "ConsoleBackend", "EmptyCallback", "EmptyCallbackState", "EmptyCallbackStepState",
            "HistoryBackend", "IterationContext", "LoggingCallback", "LoggingCallbackStepState", "ProgressBarCallback",
-           "ProgressBarCallbackStepState", "ResetContext", "StepContext", "TrainingContext"]
+           "ProgressBarCallbackStepState", "ResetContext", "StepContext", "TensorBoardBackend", "TrainingContext"]

@@ -195,3 +195,65 @@ def test_schedule_functions():
     assert np.isclose(cos(0), 2.0) and np.isclose(cos(5), 1.0, atol=1e-6) and np.isclose(cos(10), 0.0, atol=1e-6)
     with pytest.raises(ValueError):
         step_schedule(values=[1.0], boundaries=[1, 2])
+
+
+def test_tensorboard_event_file_format(tmp_path):
+    """The dependency-free TensorBoardBackend: TFRecord framing with valid masked CRC-32Cs around Event protos that
+    decode back to the logged tags / values / steps."""
+    import struct
+
+    from lerax_b200.callback.tensorboard import TensorBoardBackend, crc32c, masked_crc32c
+
+    assert crc32c(b"123456789") == 0xE3069283  # the CRC-32C check value
+    b = TensorBoardBackend(log_dir=tmp_path)
+    b.open("run")
+    b.log_hparams({"algorithm.num_envs": 4})
+    b.log_scalars({"episode/return": 21.5, "train/value_loss": 0.25}, step=8192)
+    b.close()
+    files = list((tmp_path / "run").iterdir())
+    assert len(files) == 1 and files[0].name.startswith("events.out.tfevents.")
+    data = files[0].read_bytes()
+
+    def varint(buf, i):
+        n = shift = 0
+        while True:
+            n |= (buf[i] & 0x7F) << shift
+            shift += 7
+            i += 1
+            if not buf[i - 1] & 0x80:
+                return n, i
+
+    def fields(buf):
+        i, out = 0, []
+        while i < len(buf):
+            k, i = varint(buf, i)
+            f, w = k >> 3, k & 7
+            if w == 0:
+                v, i = varint(buf, i)
+            elif w == 1:
+                v, i = struct.unpack("<d", buf[i:i + 8])[0], i + 8
+            elif w == 5:
+                v, i = struct.unpack("<f", buf[i:i + 4])[0], i + 4
+            else:
+                n, i = varint(buf, i)
+                v, i = buf[i:i + n], i + n
+            out.append((f, v))
+        return out
+
+    events, i = [], 0
+    while i < len(data):
+        (n,) = struct.unpack("<Q", data[i:i + 8])
+        assert struct.unpack("<I", data[i + 8:i + 12])[0] == masked_crc32c(data[i:i + 8])
+        payload = data[i + 12:i + 12 + n]
+        assert struct.unpack("<I", data[i + 12 + n:i + 16 + n])[0] == masked_crc32c(payload)
+        events.append(dict(fields(payload)))
+        i += 16 + n
+    assert events[0][3] == b"brain.Event:2" and len(events) == 4
+    scalars = {}
+    for ev in events[2:]:
+        assert ev[2] == 8192
+        val = dict(fields(dict(fields(ev[5]))[1]))
+        scalars[val[1].decode()] = val[2]
+    assert scalars == {"episode/return": 21.5, "train/value_loss": 0.25}
+    text = dict(fields(dict(fields(events[1][5]))[1]))
+    assert text[1] == b"hparams" and b"algorithm.num_envs" in dict(fields(text[8]))[8]

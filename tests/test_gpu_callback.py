@@ -122,12 +122,12 @@ def test_custom_on_step_still_rejected():
         PPO(num_envs=4, num_steps=8).consolidate_callbacks([Mine()])
 
 
-def test_ppo_with_callbacks_reference_integration(capsys):
+def test_ppo_with_callbacks_reference_integration(capsys, tmp_path):
     """tests/integration/test_ppo_callbacks.py of the reference: PPO() defaults, one LoggingCallback (not a list)
     with several backends; 512 timesteps are fewer than one iteration of the default 4 x 2048 rollout."""
     from lerax_b200 import random as jr
     from lerax_b200.algorithm import PPO
-    from lerax_b200.callback import ConsoleBackend, HistoryBackend, LoggingCallback
+    from lerax_b200.callback import ConsoleBackend, HistoryBackend, LoggingCallback, TensorBoardBackend
     from lerax_b200.env.classic_control import CartPole
     from lerax_b200.policy import MLPActorCriticPolicy
 
@@ -136,11 +136,13 @@ def test_ppo_with_callbacks_reference_integration(capsys):
     policy = MLPActorCriticPolicy(env=env, key=policy_key)
     algo = PPO()
     hist = HistoryBackend()
-    logger = LoggingCallback([hist, ConsoleBackend()], env=env, policy=policy)
+    logger = LoggingCallback([TensorBoardBackend(log_dir=tmp_path), hist, ConsoleBackend()], env=env, policy=policy)
     trained = algo.learn(env, policy, total_timesteps=512, key=learn_key, callback=logger)
     assert trained is not None and hist.records == [] and hist.name.startswith("MLPActorCriticPolicy_CartPole_")
     # one full iteration of the defaults logs one record to every backend
     trained = algo.learn(env, policy, total_timesteps=4 * 2048, key=learn_key, callback=logger)
     logger.close()
     assert len(hist.records) == 1 and hist.records[0][0] == 4 * 2048
+    runs = list(tmp_path.iterdir())  # log_dir / name / events.out.tfevents.*
+    assert len(runs) == 1 and runs[0].name == hist.name and len(list(runs[0].iterdir())) > 0
     assert "episode/return=" in capsys.readouterr().out
