@@ -13,7 +13,10 @@
  *   - Functions only ENQUEUE work on `stream` (a cudaStream_t passed as void*); none of them
  *     synchronises the host, so they are legal inside an XLA FFI handler or a CUDA graph
  *     capture.  They are re-entrant and keep no global state besides the thread-local
- *     error string.
+ *     error string and launch counter.  The ONE exception to "never allocates / never synchronises" is the
+ *     lrx_p2p_alloc / lrx_p2p_open / close / free family: CUDA IPC can only share memory the exporting process
+ *     obtained from cudaMalloc, so those four set-up calls allocate and synchronise (once per process, outside any
+ *     capture).  Test hooks (kernel-selection toggles, tensor-core self-tests) live in lerax_b200_debug.h.
  *   - Return value: LRX_OK (0) or a negative LRX_ERR_*; lrx_last_error() gives the message.
  *   - Layouts: the rollout buffer is TIME-MAJOR [T][N] (env index fastest) so that lanes of a
  *     warp touch consecutive envs; the reference's logical layout is [N][T] with flat index
@@ -213,10 +216,14 @@ int lrx_episode_stats(const float* rew, const uint8_t* done, const LrxEpisodeSta
 /* ---------------------------------------------------------------------------- GAE
  * advantage/gae.py:36-66 via buffer/rollout.py:64-79.  layout LRX_LAYOUT_TN: arrays are
  * [T][N] (kernel-native); LRX_LAYOUT_NT: [N][T] (reference-native, T contiguous).
- * ev_sums: optional double[4] receiving sum(ret), sum(ret^2), sum(adv), sum(adv^2)
- * (adv = ret - val) for explained_variance (algorithm/ppo.py:523-528). */
+ * ev_sums: optional double[LRX_GAE_EV_DOUBLES], ZERO-INITIALISED ONCE by the caller when it is allocated.
+ * ev_sums[0..3] receive sum(ret), sum(ret^2), sum(adv), sum(adv^2) (adv = ret - val) for explained_variance
+ * (algorithm/ppo.py:523-528); the rest is per-block scratch and an arrival counter that the kernel re-arms itself,
+ * so the sums are added in a fixed order (bitwise reproducible) and no memset precedes the kernel. */
 #define LRX_LAYOUT_TN 0
 #define LRX_LAYOUT_NT 1
+#define LRX_GAE_EV_BLOCKS 2048
+#define LRX_GAE_EV_DOUBLES (4 + 4 * LRX_GAE_EV_BLOCKS + 4)
 int lrx_gae(const float* rew, const float* val, const uint8_t* done, const float* last_value,
             float* adv, float* ret, int32_t N, int32_t T, float gamma, float lam, int32_t layout,
             double* ev_sums, lrx_stream_t stream);
@@ -302,47 +309,6 @@ int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* adam_m, float
                    int32_t num_batches, int64_t B, const LrxPpoHyper* h, float* stats_out,
                    int32_t* nonfinite_flag, void* workspace, size_t workspace_bytes,
                    lrx_stream_t stream);
-
-/* ------------------------------------------------------------------ diagnostics
- * Self-test of the tensor-core building blocks the fused kernels are made of (tcgen05.mma
- * kind::tf32 with the 3xTF32 split, operands in the canonical no-swizzle shared-memory
- * layout, accumulator in TMEM): D = A[M][K] * B[N][K]^T on ONE SM.  M in {64,128};
- * N multiple of 8 (16 when M = 128); K multiple of 8.  cfg_host (HOST pointer, 12 ints):
- * {mn, s_mn, s_k, lbo, sbo, kstep} for A then B -- mn = 1 stages that operand MN-major (the
- * transposed reading the weight-gradient GEMMs use), s_* are the storage strides between
- * core-matrix groups and lbo/sbo/kstep the descriptor fields, all in bytes.  split = 1 -> 3xTF32.
- * dump receives the raw accumulator [128 TMEM lanes][N].  Not part of the reference path. */
-int lrx_debug_umma_gemm(const float* A, const float* B, float* dump, int32_t M, int32_t N, int32_t K,
-                        const int32_t* cfg_host, int32_t split, lrx_stream_t stream);
-
-/* Same for the bf16x3 fp32 emulation (kind::f16, bf16 pieces x = p0+p1+p2, nprod = 1, 3 or 6
- * products kept; K multiple of 16; 2-byte elements, 8 per 16-byte chunk). */
-int lrx_debug_umma_gemm_bf16(const float* A, const float* B, float* dump, int32_t M, int32_t N, int32_t K,
-                             const int32_t* cfg_host, int32_t nprod, lrx_stream_t stream);
-
-/* Timing probe for the same MMA sequence: cycles[0] = issue, cycles[1] = issue + completion. */
-int lrx_debug_umma_time_bf16(const float* A, const float* B, float* dump, int32_t M, int32_t N, int32_t K,
-                             const int32_t* cfg_host, int32_t nprod, int32_t reps, long long* cycles,
-                             lrx_stream_t stream);
-
-/* Dispatch-rate probe: 256 back-to-back MMAs with constant descriptors over `dsplit` accumulators. */
-int lrx_debug_umma_rate(int32_t M, int32_t N, int32_t dsplit, long long* cycles, lrx_stream_t stream);
-/* Latency of tcgen05.ld from one TMEM region while n_mma MMAs accumulate into another (cycles[0..7] per load,
- * cycles[8] until the MMA batch completes).  dsplit bits 8 / 9 of lrx_debug_umma_rate select MN-major A / B. */
-int lrx_debug_tmem_ld_under_mma(int32_t n_mma, long long* cycles, lrx_stream_t stream);
-
-/* Decode of the tcgen05.ld 16x256b.x2 fragment shape: dump [128 threads][8 registers]. */
-int lrx_debug_tmem_shape_probe(float* dump, lrx_stream_t stream);
-
-/* 1 (default): default-width policies run the specialised tensor-core kernels; 0: everything runs
- * the generic-width kernels (also selectable with the environment variable LRX_DISABLE_FUSED=1). */
-void lrx_debug_set_fused(int enabled);
-/* test helper: device-to-device copy of n floats to a raw device address (an exchange slot). */
-int lrx_debug_copy_f32(float* dst, const float* src, int32_t n, lrx_stream_t stream);
-
-/* Probes of the A-operand-in-TMEM layout (mode 0) and of an M = 64 accumulator at TMEM lane 16 (mode 1):
- * dump [128 threads][16 columns] of the accumulator. */
-int lrx_debug_tmem_operand_probe(float* dump, int32_t mode, int32_t variant, int32_t M, lrx_stream_t stream);
 
 /* ------------------------------------------------------------------------- misc */
 const char* lrx_last_error(void);

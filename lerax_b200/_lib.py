@@ -21,6 +21,8 @@ LRX_MAX_NOUT = 8
 LRX_LAYOUT_TN, LRX_LAYOUT_NT = 0, 1
 LRX_P2P_HANDLE_BYTES = 64
 LRX_PPO_NSTATS = 8
+LRX_GAE_EV_BLOCKS = 2048
+LRX_GAE_EV_DOUBLES = 4 + 4 * LRX_GAE_EV_BLOCKS + 4
 
 
 class LrxEnvDesc(C.Structure):
@@ -97,7 +99,6 @@ PROTOTYPES = {
     "lrx_ppo_apply_p2p_scratch_bytes": (C.c_size_t, [_P(LrxPolicyDesc)]),
     "lrx_ppo_apply_p2p": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_uint32,
                                     _P(LrxPpoHyper), _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
-    "lrx_debug_copy_f32": (C.c_int, [_vp, _vp, C.c_int32, _vp]),
     "lrx_episode_stats": (C.c_int, [_vp, _vp, _P(LrxEpisodeStats), C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp]),
     "lrx_ppo_workspace_bytes": (C.c_size_t, [_P(LrxPolicyDesc), C.c_int64]),
     "lrx_ppo_adv_sums": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int64, _vp, _vp]),
@@ -106,6 +107,20 @@ PROTOTYPES = {
     "lrx_ppo_apply": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _vp, _P(LrxPpoHyper), _vp, _vp, _vp]),
     "lrx_ppo_update": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _P(LrxBatchView), _vp, C.c_int32,
                                  C.c_int64, _P(LrxPpoHyper), _vp, _vp, _vp, C.c_size_t, _vp]),
+    "lrx_last_error": (C.c_char_p, []),
+    "lrx_version": (C.c_int, []),
+    "lrx_launch_count": (C.c_int64, [C.c_int]),
+}
+
+
+# include/lerax_b200_debug.h: test hooks exported by the product library ...
+DEBUG_HOOKS = {
+    "lrx_debug_set_fused": (None, [C.c_int]),
+    "lrx_debug_copy_f32": (C.c_int, [_vp, _vp, C.c_int32, _vp]),
+    "lrx_debug_set_gae_chunk": (None, [C.c_int]),
+}
+# ... and the tensor-core self-tests of the separate liblerax_b200_test.so
+DEBUG_TESTS = {
     "lrx_debug_umma_gemm": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _P(C.c_int32), C.c_int32,
                                       _vp]),
     "lrx_debug_umma_gemm_bf16": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _P(C.c_int32),
@@ -115,11 +130,7 @@ PROTOTYPES = {
     "lrx_debug_umma_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "lrx_debug_tmem_ld_under_mma": (C.c_int, [C.c_int32, _vp, _vp]),
     "lrx_debug_tmem_shape_probe": (C.c_int, [_vp, _vp]),
-    "lrx_debug_set_fused": (None, [C.c_int]),
     "lrx_debug_tmem_operand_probe": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
-    "lrx_last_error": (C.c_char_p, []),
-    "lrx_version": (C.c_int, []),
-    "lrx_launch_count": (C.c_int64, [C.c_int]),
 }
 
 
@@ -142,6 +153,32 @@ def _load():
 
 
 lib = _load()
+TEST_LIB_PATH = os.path.join(HERE, "_C", "liblerax_b200_test.so")
+_debug = None
+
+
+def debug_lib():
+    """Functions of include/lerax_b200_debug.h (tests and tools only): the hooks of the product library plus the
+    self-tests of liblerax_b200_test.so, as attributes of one object."""
+    global _debug
+    if _debug is None:
+        class _Debug:
+            pass
+
+        d = _Debug()
+        for name, (res, args) in DEBUG_HOOKS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+            setattr(d, name, fn)
+        if not os.path.exists(TEST_LIB_PATH):
+            raise ImportError(f"lerax_b200: {TEST_LIB_PATH} missing; run `python -m lerax_b200.build`")
+        tl = C.CDLL(TEST_LIB_PATH)
+        for name, (res, args) in DEBUG_TESTS.items():
+            fn = getattr(tl, name)
+            fn.restype, fn.argtypes = res, args
+            setattr(d, name, fn)
+        _debug = d
+    return _debug
 
 
 def check(rc: int, what: str = "") -> None:

@@ -144,7 +144,7 @@ class PPO(AbstractAlgorithm):
 
     def _exchange(self, policy, dist):
         """The peer-memory gradient exchange of this process (None: single GPU, or NCCL fallback)."""
-        if dist is None:
+        if dist is None or getattr(self, "_force_nccl", False):
             return None
         n = policy.n_params + L.LRX_PPO_NSTATS
         if getattr(self, "_ex_key", None) != (n, dist.get_world_size()):
@@ -179,7 +179,7 @@ class PPO(AbstractAlgorithm):
             rew=torch.empty((T, N), **f32), done=torch.empty((T, N), dtype=torch.uint8, device=device),
             logp=torch.empty((T, N), **f32), val=torch.empty((T, N), **f32),
             last_value=torch.empty((N,), **f32),
-            ev_sums=torch.zeros((4,), dtype=torch.float64, device=device),
+            ev_sums=torch.zeros((L.LRX_GAE_EV_DOUBLES,), dtype=torch.float64, device=device),
             stats=torch.zeros((self.num_epochs, self.minibatches_per_epoch, L.LRX_PPO_NSTATS), **f32),
             nonfinite=torch.zeros((), dtype=torch.int32, device=device),
             workspace=torch.empty((ws_bytes,), dtype=torch.uint8, device=device),
@@ -289,7 +289,7 @@ class PPO(AbstractAlgorithm):
 
         # stats: mean over minibatches, then over epochs (ppo.py:520,551)
         s = stats.mean(dim=1).mean(dim=0)
-        ev = b["ev_sums"].clone()
+        ev = b["ev_sums"][:4].clone()
         if dist is not None:
             dist.all_reduce(ev)
         n_tot = float(self.num_envs * self.num_steps)

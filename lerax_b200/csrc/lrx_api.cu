@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "../../include/lerax_b200_debug.h"
 #include "lrx_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -25,18 +26,27 @@ extern "C" int64_t lrx_launch_count(int reset) {
   return v;
 }
 
-// Specialised tensor-core kernels on (default) / off: with 0 every call takes the generic-width
-// kernels.  Initial value from the environment variable LRX_DISABLE_FUSED=1.  Used by the tests to
-// check both implementations against each other.
+// Kernel selection for default-width policies (include/lerax_b200_debug.h): 2 = newest tensor-core kernels (default),
+// 1 = first-generation tensor-core update kernel, 0 = generic-width kernels everywhere.  Initial value from the
+// environment (LRX_FUSED=0/1/2, LRX_DISABLE_FUSED=1).  A test hook: the tests run the implementations against each other.
 static int g_fused = -1;
 int lrx_fused_enabled() {
   if (g_fused < 0) {
-    const char* e = getenv("LRX_DISABLE_FUSED");
-    g_fused = (e && e[0] == '1') ? 0 : 1;
+    const char* d = getenv("LRX_DISABLE_FUSED");
+    const char* e = getenv("LRX_FUSED");
+    g_fused = (d && d[0] == '1') ? 0 : (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
   }
   return g_fused;
 }
-extern "C" void lrx_debug_set_fused(int enabled) { g_fused = enabled ? 1 : 0; }
+extern "C" void lrx_debug_set_fused(int level) { g_fused = level < 0 ? 0 : level > 2 ? 2 : level; }
+
+int lrx_sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      n <= 0)
+    return 148;
+  return n < LRX_MAX_SMS ? n : LRX_MAX_SMS;
+}
 
 int lrx_env_state_dim(int kind) { return (kind == LRX_ENV_CARTPOLE || kind == LRX_ENV_ACROBOT) ? 4 : 2; }
 int lrx_env_obs_dim(int kind) {

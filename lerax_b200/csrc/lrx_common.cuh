@@ -35,7 +35,20 @@ void lrx_count_launch(int n = 1);
     LRX_CUDA_CHECK(cudaGetLastError());    \
   } while (0)
 
-constexpr int LRX_NUM_SMS = 148;  // B200: 2 dies x 74 SMs
+constexpr int LRX_MAX_SMS = 256;  // upper bound used to SIZE per-SM workspaces (B200 has 148)
+int lrx_sm_count();               // multiprocessors of the CURRENT device (cudaDeviceGetAttribute)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per device and kernel: `done` is a per-kernel table indexed by
+// the device ordinal (an idempotent cache, not state the results depend on)
+template <typename K>
+inline cudaError_t lrx_set_max_smem(K kernel, int bytes, bool (&done)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  return e;
+}
 
 // ------------------------------------------------------------------- policy descriptor
 struct LrxLayer {

@@ -13,178 +13,155 @@
 //    Kogge-Stone scan of the affine pairs with __shfl_down_sync.
 #include "lrx_common.cuh"
 
-template <int L>
-__global__ void __launch_bounds__(512)
-gae_tn_kernel(const float* __restrict__ rew, const float* __restrict__ val,
-              const uint8_t* __restrict__ done, const float* __restrict__ last_val,
-              float* __restrict__ adv, float* __restrict__ ret, int N, int T, float gamma,
-              float lam, double* ev_sums) {
-  __shared__ float sA[16][32], sP[16][32];
-  __shared__ double sEv[16][4];
-  const int lane = threadIdx.x, c = threadIdx.y, C = blockDim.y;
-  const int n = blockIdx.x * 32 + lane;
-  const bool live = n < N;
-  const int nl = live ? n : N - 1;
-  const float gl = gamma * lam;
-  const int seg_len = C * L;
-  const int num_seg = (T + seg_len - 1) / seg_len;
-  const float lv = last_val[nl];
-  float seg_carry = 0.f;
-  double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-
-  for (int seg = num_seg - 1; seg >= 0; --seg) {
-    const int t0 = seg * seg_len + c * L;
-    float r[L], v[L + 1], nd[L];
-#pragma unroll
-    for (int i = 0; i < L; ++i) {
-      const int t = t0 + i;
-      const bool ok = t < T;
-      const size_t off = (size_t)(ok ? t : T - 1) * N + nl;
-      r[i] = ok ? rew[off] : 0.f;
-      v[i] = ok ? val[off] : lv;
-      nd[i] = ok ? 1.0f - (float)done[off] : 1.0f;
-    }
-    v[L] = (t0 + L < T) ? val[(size_t)(t0 + L) * N + nl] : lv;
-
-    float a = 0.f, p = 1.f;
-    float A[L], P[L];
-#pragma unroll
-    for (int i = L - 1; i >= 0; --i) {
-      const bool ok = t0 + i < T;
-      const float delta = ok ? r[i] + gamma * v[i + 1] * nd[i] - v[i] : 0.f;
-      const float disc = ok ? gl * nd[i] : 1.f;
-      a = delta + disc * a;
-      p = disc * p;
-      A[i] = a;
-      P[i] = p;
-    }
-    sA[c][lane] = a;
-    sP[c][lane] = p;
-    __syncthreads();
-    float carry = seg_carry;
-    for (int cc = C - 1; cc > c; --cc) carry = sA[cc][lane] + sP[cc][lane] * carry;
-#pragma unroll
-    for (int i = 0; i < L; ++i) {
-      const int t = t0 + i;
-      if (t < T && live) {
-        const float Ai = A[i] + P[i] * carry;
-        const float Ri = Ai + v[i];
-        const size_t off = (size_t)t * N + n;
-        adv[off] = Ai;
-        ret[off] = Ri;
-        e0 += Ri; e1 += (double)Ri * Ri; e2 += Ai; e3 += (double)Ai * Ai;
-      }
-    }
-    float cr = carry;
-    for (int cc = c; cc >= 0; --cc) cr = sA[cc][lane] + sP[cc][lane] * cr;
-    seg_carry = cr;
-    __syncthreads();
+// Explained-variance sums (algorithm/ppo.py:523-528) without atomics: every block stores its four partial sums in
+// ev[4 + 4 * block], the last block to arrive (ticket at ev[LRX_GAE_EV_DOUBLES - 1]) adds them in block order and
+// re-arms the ticket, so the result is bitwise reproducible and no memset launch precedes the kernel.
+__device__ __forceinline__ void ev_block_finish(double* ev, const double (*sEv)[4], int C, int tid) {
+  __shared__ bool last;
+  if (tid < 4) {
+    double s = 0;
+    for (int cc = 0; cc < C; ++cc) s += sEv[cc][tid];
+    ev[4 + 4 * (size_t)blockIdx.x + tid] = s;
   }
-
-  if (ev_sums) {
-    e0 = warp_sum(e0); e1 = warp_sum(e1); e2 = warp_sum(e2); e3 = warp_sum(e3);
-    if (lane == 0) { sEv[c][0] = e0; sEv[c][1] = e1; sEv[c][2] = e2; sEv[c][3] = e3; }
-    __syncthreads();
-    if (c == 0 && lane < 4) {
-      double s = 0;
-      for (int cc = 0; cc < C; ++cc) s += sEv[cc][lane];
-      atomicAdd(ev_sums + lane, s);
-    }
+  __threadfence();
+  __syncthreads();
+  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(ev + LRX_GAE_EV_DOUBLES - 1);
+  if (tid == 0) last = atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (tid < 4) {
+    double s = 0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(ev + 4 + 4 * (size_t)b + tid);
+    ev[tid] = s;
   }
+  if (tid == 0) *ticket = 0ull;
 }
 
-// Two adjacent envs per lane (float2 / uchar2 accesses: 256-byte rows per warp, half the
-// instructions); requires N even.  Same chunked affine scan as gae_tn_kernel.
-template <int L>
-__global__ void __launch_bounds__(512)
-gae_tn2_kernel(const float* __restrict__ rew, const float* __restrict__ val,
-               const uint8_t* __restrict__ done, const float* __restrict__ last_val,
-               float* __restrict__ adv, float* __restrict__ ret, int N, int T, float gamma,
-               float lam, double* ev_sums) {
-  __shared__ float2 sA[16][32], sP[16][32];
+// EPL adjacent envs per lane (EPL = 1: 128-byte rows per warp; 2: float2 / uchar2, 256-byte rows; 4: float4 /
+// uchar4, 512-byte rows), C warps own C consecutive chunks of L steps held in registers; chunk summaries (a, p) of
+// the affine maps are exchanged through shared memory.  Strips of 32 * EPL envs are walked with a grid stride so the
+// launch can be sized to one resident wave.  EPL > 1 needs N % EPL == 0 and EPL*4-byte aligned planes.
+template <int EPL> struct GaeVec;
+template <> struct GaeVec<1> { using F = float; using U = uint8_t; };
+template <> struct GaeVec<2> { using F = float2; using U = uchar2; };
+template <> struct GaeVec<4> { using F = float4; using U = uchar4; };
+
+template <int L, int EPL, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+gae_tn_kernel(const float* __restrict__ rew, const float* __restrict__ val, const uint8_t* __restrict__ done,
+              const float* __restrict__ last_val, float* __restrict__ adv, float* __restrict__ ret, int N, int T,
+              float gamma, float lam, double* ev_sums) {
+  using F = typename GaeVec<EPL>::F;
+  using U = typename GaeVec<EPL>::U;
+  __shared__ float sA[16][32 * EPL], sP[16][32 * EPL];
   __shared__ double sEv[16][4];
   const int lane = threadIdx.x, c = threadIdx.y, C = blockDim.y;
-  const int n = (blockIdx.x * 32 + lane) * 2;
-  const bool live = n < N;
-  const int nl = live ? n : N - 2;
   const float gl = gamma * lam;
   const int seg_len = C * L;
   const int num_seg = (T + seg_len - 1) / seg_len;
-  const float2 lv = *reinterpret_cast<const float2*>(last_val + nl);
-  float2 seg_carry = make_float2(0.f, 0.f);
+  const int n_strips = (N + 32 * EPL - 1) / (32 * EPL);
   double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
 
-  for (int seg = num_seg - 1; seg >= 0; --seg) {
-    const int t0 = seg * seg_len + c * L;
-    float2 r[L], v[L + 1], nd[L];
+  for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
+    const int n = (strip * 32 + lane) * EPL;
+    const bool live = n < N;
+    const int nl = live ? n : N - EPL;
+    float lv[EPL];
+    {
+      const F x = *reinterpret_cast<const F*>(last_val + nl);
 #pragma unroll
-    for (int i = 0; i < L; ++i) {
-      const int t = t0 + i;
-      const bool ok = t < T;
-      const size_t off = (size_t)(ok ? t : T - 1) * N + nl;
-      r[i] = ok ? *reinterpret_cast<const float2*>(rew + off) : make_float2(0.f, 0.f);
-      v[i] = ok ? *reinterpret_cast<const float2*>(val + off) : lv;
-      const uchar2 d = ok ? *reinterpret_cast<const uchar2*>(done + off) : make_uchar2(0, 0);
-      nd[i] = make_float2(1.0f - (float)d.x, 1.0f - (float)d.y);
+      for (int e = 0; e < EPL; ++e) lv[e] = reinterpret_cast<const float*>(&x)[e];
     }
-    v[L] = (t0 + L < T) ? *reinterpret_cast<const float2*>(val + (size_t)(t0 + L) * N + nl) : lv;
+    float seg_carry[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) seg_carry[e] = 0.f;
 
-    float2 a = make_float2(0.f, 0.f), p = make_float2(1.f, 1.f);
-    float2 A[L], P[L];
+    for (int seg = num_seg - 1; seg >= 0; --seg) {
+      const int t0 = seg * seg_len + c * L;
+      float r[L][EPL], v[L + 1][EPL], nd[L][EPL];
 #pragma unroll
-    for (int i = L - 1; i >= 0; --i) {
-      const bool ok = t0 + i < T;
-      const float dx = ok ? r[i].x + gamma * v[i + 1].x * nd[i].x - v[i].x : 0.f;
-      const float dy = ok ? r[i].y + gamma * v[i + 1].y * nd[i].y - v[i].y : 0.f;
-      const float cx = ok ? gl * nd[i].x : 1.f, cy = ok ? gl * nd[i].y : 1.f;
-      a.x = dx + cx * a.x; a.y = dy + cy * a.y;
-      p.x = cx * p.x; p.y = cy * p.y;
-      A[i] = a;
-      P[i] = p;
-    }
-    sA[c][lane] = a;
-    sP[c][lane] = p;
-    __syncthreads();
-    float2 carry = seg_carry;
-    for (int cc = C - 1; cc > c; --cc) {
-      const float2 qa = sA[cc][lane], qp = sP[cc][lane];
-      carry.x = qa.x + qp.x * carry.x;
-      carry.y = qa.y + qp.y * carry.y;
-    }
-    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;  // <= 2L terms per chunk in fp32, then fp64
+      for (int i = 0; i < L; ++i) {
+        const int t = t0 + i;
+        const bool ok = t < T;
+        const size_t off = (size_t)(ok ? t : T - 1) * N + nl;
+        const F rr = *reinterpret_cast<const F*>(rew + off);
+        const F vv = *reinterpret_cast<const F*>(val + off);
+        const U dd = *reinterpret_cast<const U*>(done + off);
 #pragma unroll
-    for (int i = 0; i < L; ++i) {
-      const int t = t0 + i;
-      if (t < T && live) {
-        const float2 Ai = make_float2(A[i].x + P[i].x * carry.x, A[i].y + P[i].y * carry.y);
-        const float2 Ri = make_float2(Ai.x + v[i].x, Ai.y + v[i].y);
-        const size_t off = (size_t)t * N + n;
-        *reinterpret_cast<float2*>(adv + off) = Ai;
-        *reinterpret_cast<float2*>(ret + off) = Ri;
-        f0 += Ri.x + Ri.y; f1 = fmaf(Ri.x, Ri.x, fmaf(Ri.y, Ri.y, f1));
-        f2 += Ai.x + Ai.y; f3 = fmaf(Ai.x, Ai.x, fmaf(Ai.y, Ai.y, f3));
+        for (int e = 0; e < EPL; ++e) {
+          r[i][e] = ok ? reinterpret_cast<const float*>(&rr)[e] : 0.f;
+          v[i][e] = ok ? reinterpret_cast<const float*>(&vv)[e] : lv[e];
+          nd[i][e] = ok ? 1.0f - (float)reinterpret_cast<const uint8_t*>(&dd)[e] : 1.0f;
+        }
       }
+      {
+        const bool ok = t0 + L < T;
+        const F vv = *reinterpret_cast<const F*>(val + (size_t)(ok ? t0 + L : T - 1) * N + nl);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) v[L][e] = ok ? reinterpret_cast<const float*>(&vv)[e] : lv[e];
+      }
+      float a[EPL], p[EPL], A[L][EPL], P[L][EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { a[e] = 0.f; p[e] = 1.f; }
+#pragma unroll
+      for (int i = L - 1; i >= 0; --i) {
+        const bool ok = t0 + i < T;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const float delta = ok ? r[i][e] + gamma * v[i + 1][e] * nd[i][e] - v[i][e] : 0.f;
+          const float disc = ok ? gl * nd[i][e] : 1.f;
+          a[e] = delta + disc * a[e];
+          p[e] = disc * p[e];
+          A[i][e] = a[e];
+          P[i][e] = p[e];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { sA[c][lane * EPL + e] = a[e]; sP[c][lane * EPL + e] = p[e]; }
+      __syncthreads();
+      float carry[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) carry[e] = seg_carry[e];
+      for (int cc = C - 1; cc > c; --cc) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) carry[e] = sA[cc][lane * EPL + e] + sP[cc][lane * EPL + e] * carry[e];
+      }
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;  // <= EPL * L terms per chunk in fp32, then fp64
+#pragma unroll
+      for (int i = 0; i < L; ++i) {
+        const int t = t0 + i;
+        if (t < T && live) {
+          F Ao, Ro;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            const float Ai = A[i][e] + P[i][e] * carry[e];
+            const float Ri = Ai + v[i][e];
+            reinterpret_cast<float*>(&Ao)[e] = Ai;
+            reinterpret_cast<float*>(&Ro)[e] = Ri;
+            f0 += Ri; f1 = fmaf(Ri, Ri, f1); f2 += Ai; f3 = fmaf(Ai, Ai, f3);
+          }
+          const size_t off = (size_t)t * N + n;
+          *reinterpret_cast<F*>(adv + off) = Ao;
+          *reinterpret_cast<F*>(ret + off) = Ro;
+        }
+      }
+      e0 += f0; e1 += f1; e2 += f2; e3 += f3;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        float cr = carry[e];
+        for (int cc = c; cc >= 0; --cc) cr = sA[cc][lane * EPL + e] + sP[cc][lane * EPL + e] * cr;
+        seg_carry[e] = cr;
+      }
+      __syncthreads();
     }
-    e0 += f0; e1 += f1; e2 += f2; e3 += f3;
-    float2 cr = carry;
-    for (int cc = c; cc >= 0; --cc) {
-      const float2 qa = sA[cc][lane], qp = sP[cc][lane];
-      cr.x = qa.x + qp.x * cr.x;
-      cr.y = qa.y + qp.y * cr.y;
-    }
-    seg_carry = cr;
-    __syncthreads();
   }
 
   if (ev_sums) {
     e0 = warp_sum(e0); e1 = warp_sum(e1); e2 = warp_sum(e2); e3 = warp_sum(e3);
     if (lane == 0) { sEv[c][0] = e0; sEv[c][1] = e1; sEv[c][2] = e2; sEv[c][3] = e3; }
     __syncthreads();
-    if (c == 0 && lane < 4) {
-      double s = 0;
-      for (int cc = 0; cc < C; ++cc) s += sEv[cc][lane];
-      atomicAdd(ev_sums + lane, s);
-    }
+    ev_block_finish(ev_sums, sEv, C, threadIdx.y * 32 + threadIdx.x);
   }
 }
 
@@ -193,54 +170,63 @@ gae_nt_kernel(const float* __restrict__ rew, const float* __restrict__ val,
               const uint8_t* __restrict__ done, const float* __restrict__ last_val,
               float* __restrict__ adv, float* __restrict__ ret, int N, int T, float gamma,
               float lam, double* ev_sums) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (env >= N) return;  // whole warp exits together
+  __shared__ double sEv[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const float gl = gamma * lam;
-  const size_t base_off = (size_t)env * T;
-  const float lv = last_val[env];
-  float carry = 0.f;
   double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-  for (int base = ((T - 1) / 32) * 32; base >= 0; base -= 32) {
-    const int t = base + lane;
-    const bool ok = t < T;
-    float v = 0.f, a = 0.f, b = 1.f;
-    if (ok) {
-      v = val[base_off + t];
-      const float vn = (t + 1 < T) ? val[base_off + t + 1] : lv;
-      const float nd = 1.0f - (float)done[base_off + t];
-      a = rew[base_off + t] + gamma * vn * nd - v;
-      b = gl * nd;
-    }
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const float a2 = __shfl_down_sync(0xffffffffu, a, o);
-      const float b2 = __shfl_down_sync(0xffffffffu, b, o);
-      if (lane + o < 32) {
-        a = a + b * a2;
-        b = b * b2;
+  for (int env = blockIdx.x * warps + warp; env < N; env += gridDim.x * warps) {  // warp-uniform
+    const size_t base_off = (size_t)env * T;
+    const float lv = last_val[env];
+    float carry = 0.f;
+    for (int base = ((T - 1) / 32) * 32; base >= 0; base -= 32) {
+      const int t = base + lane;
+      const bool ok = t < T;
+      float v = 0.f, a = 0.f, b = 1.f;
+      if (ok) {
+        v = val[base_off + t];
+        const float vn = (t + 1 < T) ? val[base_off + t + 1] : lv;
+        const float nd = 1.0f - (float)done[base_off + t];
+        a = rew[base_off + t] + gamma * vn * nd - v;
+        b = gl * nd;
       }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float a2 = __shfl_down_sync(0xffffffffu, a, o);
+        const float b2 = __shfl_down_sync(0xffffffffu, b, o);
+        if (lane + o < 32) {
+          a = a + b * a2;
+          b = b * b2;
+        }
+      }
+      const float Ai = a + b * carry;
+      if (ok) {
+        const float Ri = Ai + v;
+        adv[base_off + t] = Ai;
+        ret[base_off + t] = Ri;
+        e0 += Ri; e1 += (double)Ri * Ri; e2 += Ai; e3 += (double)Ai * Ai;
+      }
+      carry = __shfl_sync(0xffffffffu, Ai, 0);
     }
-    const float Ai = a + b * carry;
-    if (ok) {
-      const float Ri = Ai + v;
-      adv[base_off + t] = Ai;
-      ret[base_off + t] = Ri;
-      e0 += Ri; e1 += (double)Ri * Ri; e2 += Ai; e3 += (double)Ai * Ai;
-    }
-    carry = __shfl_sync(0xffffffffu, Ai, 0);
   }
   if (ev_sums) {
     e0 = warp_sum(e0); e1 = warp_sum(e1); e2 = warp_sum(e2); e3 = warp_sum(e3);
-    if (lane == 0) {
-      atomicAdd(ev_sums + 0, e0); atomicAdd(ev_sums + 1, e1);
-      atomicAdd(ev_sums + 2, e2); atomicAdd(ev_sums + 3, e3);
-    }
+    if (lane == 0) { sEv[warp][0] = e0; sEv[warp][1] = e1; sEv[warp][2] = e2; sEv[warp][3] = e3; }
+    __syncthreads();
+    ev_block_finish(ev_sums, sEv, warps, threadIdx.x);
   }
 }
 
-static int g_gae_chunk = 0;  // 0 = automatic; tools/gae_time.py sweeps it
-extern "C" void lrx_debug_set_gae_chunk(int L) { g_gae_chunk = L; }
+// tools/gae_time.py sweeps the launch shape: knob = MINB * 1000000 + EPL * 10000 + L * 100 + C (0 = automatic):
+// MINB resident blocks per SM asked of the compiler (register cap), EPL envs per lane, L steps per thread, C warps.
+static int g_gae_knob = 0;
+extern "C" void lrx_debug_set_gae_chunk(int knob) { g_gae_knob = knob; }
+
+template <int L, int EPL, int MAXT, int MINB>
+static void launch_gae_tn(int C, int grid, cudaStream_t s, const float* rew, const float* val, const uint8_t* done,
+                          const float* last_value, float* adv, float* ret, int N, int T, float gamma, float lam,
+                          double* ev_sums) {
+  gae_tn_kernel<L, EPL, MAXT, MINB><<<grid, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
+}
 
 extern "C" int lrx_gae(const float* rew, const float* val, const uint8_t* done,
                        const float* last_value, float* adv, float* ret, int32_t N, int32_t T,
@@ -250,39 +236,44 @@ extern "C" int lrx_gae(const float* rew, const float* val, const uint8_t* done,
   LRX_REQUIRE(layout == LRX_LAYOUT_TN || layout == LRX_LAYOUT_NT, LRX_ERR_INVALID_ARG,
               "lrx_gae: unknown layout %d", layout);
   cudaStream_t s = (cudaStream_t)stream;
-  if (ev_sums) LRX_CUDA_CHECK(cudaMemsetAsync(ev_sums, 0, 4 * sizeof(double), s));
-  if (N == 0 || T == 0) return LRX_OK;
+  if (N == 0 || T == 0) {
+    if (ev_sums) LRX_CUDA_CHECK(cudaMemsetAsync(ev_sums, 0, 4 * sizeof(double), s));
+    return LRX_OK;
+  }
   LRX_REQUIRE(rew && val && done && last_value && adv && ret, LRX_ERR_INVALID_ARG, "lrx_gae: NULL pointer");
   if (layout == LRX_LAYOUT_TN) {
-    const int blocks = (N + 31) / 32;
-    const int Lsel = g_gae_chunk > 0 ? g_gae_chunk : 24;
-    if (T >= 64 && (N % 2) == 0 && N >= 64 && (Lsel == 8 || Lsel == 28 || Lsel == 24)) {
-      const int blocks2 = (N / 2 + 31) / 32;
-      if (Lsel == 24) {
-        int C = (T + 3) / 4;
-        if (C > 16) C = 16;
-        gae_tn2_kernel<4><<<blocks2, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
-      } else {
-        int C = (T + 7) / 8;
-        if (C > 16) C = 16;
-        gae_tn2_kernel<8><<<blocks2, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
-      }
-    } else if (T >= 64 && Lsel == 16) {
-      int C = (T + 15) / 16;
-      if (C > 16) C = 16;
-      gae_tn_kernel<16><<<blocks, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
-    } else if (T >= 64 && (Lsel == 8 || Lsel == 18)) {
-      int C = (T + 7) / 8;
-      if (C > 16) C = 16;
-      gae_tn_kernel<8><<<blocks, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
-    } else {
-      int C = (T + 3) / 4;
-      if (C > 16) C = 16;
-      gae_tn_kernel<4><<<blocks, dim3(32, C), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
+    // vector width: all planes (and every row t * N of them) must be aligned to the access size
+    auto aligned = [&](int epl) {
+      const uintptr_t m = (uintptr_t)rew | (uintptr_t)val | (uintptr_t)adv | (uintptr_t)ret | (uintptr_t)last_value;
+      return N % epl == 0 && (m & (uintptr_t)(4 * epl - 1)) == 0 && ((uintptr_t)done & (uintptr_t)(epl - 1)) == 0;
+    };
+    int epl = 2, L = 4, C = 8, minb = 4;
+    if (g_gae_knob > 0) {
+      minb = g_gae_knob / 1000000; epl = (g_gae_knob / 10000) % 100; L = (g_gae_knob / 100) % 100; C = g_gae_knob % 100;
     }
+    if (N < 64 * epl) epl = 1;
+    while (epl > 1 && !aligned(epl)) epl >>= 1;
+    if (C > 16) C = 16;
+    while (C > 1 && (C - 1) * L >= T) --C;  // no warp without a step
+    const int n_strips = (N + 32 * epl - 1) / (32 * epl);
+    const int grid = n_strips < LRX_GAE_EV_BLOCKS ? n_strips : LRX_GAE_EV_BLOCKS;
+    bool launched = false;
+#define LRX_GAE_CASE(LL, EE, MT, MB)                                                                                  \
+  if (!launched && L == LL && epl == EE && C * 32 <= MT && (minb == MB || g_gae_knob == 0)) {                          \
+    launch_gae_tn<LL, EE, MT, MB>(C, grid, s, rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);        \
+    launched = true;                                                                                                  \
+  }
+    LRX_GAE_CASE(4, 2, 256, 4) LRX_GAE_CASE(4, 2, 256, 5) LRX_GAE_CASE(4, 2, 256, 3) LRX_GAE_CASE(4, 2, 512, 2)
+    LRX_GAE_CASE(2, 2, 256, 6) LRX_GAE_CASE(2, 2, 512, 3) LRX_GAE_CASE(8, 2, 256, 3) LRX_GAE_CASE(8, 2, 512, 1)
+    LRX_GAE_CASE(4, 1, 256, 6) LRX_GAE_CASE(4, 1, 512, 2) LRX_GAE_CASE(2, 1, 256, 8) LRX_GAE_CASE(8, 1, 256, 4)
+    LRX_GAE_CASE(4, 4, 256, 3) LRX_GAE_CASE(4, 4, 256, 2) LRX_GAE_CASE(2, 4, 256, 4) LRX_GAE_CASE(2, 4, 512, 2)
+    LRX_REQUIRE(launched, LRX_ERR_INVALID_ARG, "lrx_gae: unsupported launch shape L=%d epl=%d C=%d minb=%d", L, epl, C, minb);
+#undef LRX_GAE_CASE
   } else {
     const int warps = 8;
-    gae_nt_kernel<<<(N + warps - 1) / warps, warps * 32, 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
+    int grid = (N + warps - 1) / warps;
+    if (grid > LRX_GAE_EV_BLOCKS) grid = LRX_GAE_EV_BLOCKS;
+    gae_nt_kernel<<<grid, warps * 32, 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);
   }
   LRX_LAUNCH_CHECK();
   return LRX_OK;

@@ -369,7 +369,7 @@ extern "C" int lrx_policy_forward(const LrxPolicyDesc* pol, const float* params,
   LRX_REQUIRE(smem <= 227 * 1024, LRX_ERR_UNSUPPORTED, "policy too wide for shared memory (%zu B)", smem);
   LRX_CUDA_CHECK(cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks = (B + warps * 32 - 1) / (warps * 32);
-  if (blocks > LRX_NUM_SMS * 8) blocks = LRX_NUM_SMS * 8;
+  if (blocks > lrx_sm_count() * 8) blocks = lrx_sm_count() * 8;
   policy_forward_kernel<<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(tab, params, obs, value, head, B,
                                                                            pol->obs_dim, pol->n_out);
   LRX_LAUNCH_CHECK();
@@ -411,7 +411,7 @@ extern "C" int lrx_rollout(const LrxEnvDesc* env, const LrxPolicyDesc* pol, cons
   PolicyTable tab = lrx_make_table(*pol);
   int warps = warps_for_smem(tab, 8, 96 * 1024);
   // spread the envs over all SMs before stacking warps into a block
-  while (warps > 1 && (N + warps * 32 - 1) / (warps * 32) < LRX_NUM_SMS) warps >>= 1;
+  while (warps > 1 && (N + warps * 32 - 1) / (warps * 32) < lrx_sm_count()) warps >>= 1;
   size_t smem = (size_t)warps * (2 * tab.max_width + tab.feat) * 32 * sizeof(float);
   LRX_REQUIRE(smem <= 227 * 1024, LRX_ERR_UNSUPPORTED, "policy too wide for shared memory (%zu B)", smem);
   int blocks = (N + warps * 32 - 1) / (warps * 32);

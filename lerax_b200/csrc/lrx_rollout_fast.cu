@@ -368,11 +368,8 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_tc_kernel(const __grid_con
 
 template <int KIND>
 int launch_tc(const RolloutArgs& a, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    LRX_CUDA_CHECK(cudaFuncSetAttribute(rollout_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
-  }
+  static bool attr_set[64];  // per kernel instantiation and device
+  LRX_CUDA_CHECK(lrx_set_max_smem(rollout_tc_kernel<KIND>, (int)SMEM_BYTES, attr_set));
   rollout_tc_kernel<KIND><<<(a.N + ENVS - 1) / ENVS, THREADS, SMEM_BYTES, stream>>>(a);
   return LRX_OK;
 }

@@ -885,8 +885,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_fused_kernel(const __grid
 }
 
 struct FusedWorkspace {
-  float* partial;        // [LRX_NUM_SMS][P_pad]
-  double* loss_partial;  // [LRX_NUM_SMS][8]
+  float* partial;        // [LRX_MAX_SMS][P_pad]
+  double* loss_partial;  // [LRX_MAX_SMS][8]
   size_t P_pad, total;
 };
 size_t align_up_(size_t x, size_t al) { return (x + al - 1) / al * al; }
@@ -896,9 +896,9 @@ FusedWorkspace carve_fused(const LrxPolicyDesc& pol, void* base) {
   char* b = (char*)base;
   size_t off = 0;
   w.partial = (float*)(b ? b + off : nullptr);
-  off += align_up_((size_t)LRX_NUM_SMS * w.P_pad * 4, 256);
+  off += align_up_((size_t)LRX_MAX_SMS * w.P_pad * 4, 256);
   w.loss_partial = (double*)(b ? b + off : nullptr);
-  off += align_up_((size_t)LRX_NUM_SMS * 8 * sizeof(double), 256);
+  off += align_up_((size_t)LRX_MAX_SMS * 8 * sizeof(double), 256);
   w.total = off;
   return w;
 }
@@ -941,15 +941,13 @@ int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxB
   a.n_out = pol->n_out;
   a.is_box = pol->is_box;
   a.lo = tc::layer_offsets(*pol);
-  const int grid = a.n_tiles < LRX_NUM_SMS ? a.n_tiles : LRX_NUM_SMS;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    LRX_CUDA_CHECK(cudaFuncSetAttribute(ppo_grad_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
-  }
+  const int sms = lrx_sm_count();
+  const int grid = a.n_tiles < sms ? a.n_tiles : sms;
+  static bool set0[64], set1[64], set2[64], set3[64];
+  LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_fused_kernel<0>, (int)SMEM_BYTES, set0));
+  LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_fused_kernel<1>, (int)SMEM_BYTES, set1));
+  LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_fused_kernel<2>, (int)SMEM_BYTES, set2));
+  LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_fused_kernel<3>, (int)SMEM_BYTES, set3));
   switch (pol->n_out) {
     case 1: ppo_grad_fused_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
     case 2: ppo_grad_fused_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;

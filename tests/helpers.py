@@ -96,12 +96,12 @@ def run_gae(rew, val, done, last, gamma, lam, layout="TN", want_ev=False):
     r, v, d, lv = dev(rew.astype(np.float32)), dev(val.astype(np.float32)), dev(done.astype(np.uint8)), dev(
         np.asarray(last, np.float32).reshape(N))
     adv, ret = torch.empty_like(r), torch.empty_like(r)
-    ev = torch.zeros(4, dtype=torch.float64, device="cuda") if want_ev else None
+    ev = torch.zeros(L.LRX_GAE_EV_DOUBLES, dtype=torch.float64, device="cuda") if want_ev else None
     L.check(L.lib.lrx_gae(L.ptr(r), L.ptr(v), L.ptr(d), L.ptr(lv), L.ptr(adv), L.ptr(ret), N, T, float(gamma),
                           float(lam), lay, L.ptr(ev), L.stream_ptr()), "lrx_gae")
     torch.cuda.synchronize()
     if want_ev:
-        return adv.cpu().numpy(), ret.cpu().numpy(), ev.cpu().numpy()
+        return adv.cpu().numpy(), ret.cpu().numpy(), ev[:4].cpu().numpy()
     return adv.cpu().numpy(), ret.cpu().numpy()
 
 

@@ -28,7 +28,7 @@ def main():
         x = torch.randn(n, generator=g, device=dev)
         slot = ex.next_slot()
         # what lrx_ppo_grad does: write the local partial into the own slot
-        L.check(L.lib.lrx_debug_copy_f32(slot, L.ptr(x), n, L.stream_ptr()), "copy")
+        L.check(L.debug_lib().lrx_debug_copy_f32(slot, L.ptr(x), n, L.stream_ptr()), "copy")
         ex.allreduce(out)
         ref = x.clone()
         dist.all_reduce(ref)

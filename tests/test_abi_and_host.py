@@ -34,6 +34,25 @@ def test_library_exports_every_declared_symbol():
     assert L.lib.lrx_version() == 100
 
 
+def test_debug_header_symbols_exported_and_separate():
+    """include/lerax_b200_debug.h: the toggles come from the product library, the tensor-core self-tests from the separate
+    liblerax_b200_test.so -- and the product library does not carry them."""
+    from lerax_b200 import _lib as L
+
+    src = open(os.path.join(ROOT, "include", "lerax_b200_debug.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(lrx_debug_[a-z_0-9]+)\s*\(", src)))
+    assert declared == sorted(list(L.DEBUG_HOOKS) + list(L.DEBUG_TESTS))
+    raw = ctypes.CDLL(L.LIB_PATH)
+    for name in L.DEBUG_HOOKS:
+        assert hasattr(raw, name)
+    for name in L.DEBUG_TESTS:
+        assert not hasattr(raw, name), f"{name} must not ship in the product library"
+    dbg = L.debug_lib()
+    for name in declared:
+        assert hasattr(dbg, name)
+
+
 def test_struct_sizes_match_header_layout():
     from lerax_b200 import _lib as L
 

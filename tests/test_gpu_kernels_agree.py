@@ -19,8 +19,8 @@ KINDS = ["cartpole", "pendulum", "acrobot", "mountain_car", "continuous_mountain
 def fused_toggle():
     from lerax_b200 import _lib as L
 
-    yield L.lib.lrx_debug_set_fused
-    L.lib.lrx_debug_set_fused(1)
+    yield L.debug_lib().lrx_debug_set_fused
+    L.debug_lib().lrx_debug_set_fused(1)
 
 
 @pytest.mark.parametrize("kind", KINDS)

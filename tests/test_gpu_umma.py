@@ -33,7 +33,7 @@ def _run(fn, M, N, K, cfg, flag, seed=0):
     dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
     dump = torch.full((128, N), float("nan"), device="cuda")
     arr = (C.c_int32 * 12)(*cfg)
-    L.check(getattr(L.lib, fn)(L.ptr(dA), L.ptr(dB), L.ptr(dump), M, N, K, arr, flag, L.stream_ptr()), fn)
+    L.check(getattr(L.debug_lib(), fn)(L.ptr(dA), L.ptr(dB), L.ptr(dump), M, N, K, arr, flag, L.stream_ptr()), fn)
     torch.cuda.synchronize()
     d = dump.cpu().numpy()
     if M == 64:  # row m lives in TMEM lane (m % 16) + 32 * (m // 16)

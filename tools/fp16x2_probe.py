@@ -12,7 +12,7 @@ def run(A, B, nprod):
     dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
     dump = torch.zeros(128, N, device="cuda")
     arr = (C.c_int32 * 12)(*(kmaj(M) + kmaj(N)))
-    L.check(L.lib.lrx_debug_umma_gemm_bf16(L.ptr(dA), L.ptr(dB), L.ptr(dump), M, N, K, arr, nprod, L.stream_ptr()))
+    L.check(L.debug_lib().lrx_debug_umma_gemm_bf16(L.ptr(dA), L.ptr(dB), L.ptr(dump), M, N, K, arr, nprod, L.stream_ptr()))
     torch.cuda.synchronize()
     return dump.cpu().numpy()
 

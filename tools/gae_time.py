@@ -1,20 +1,48 @@
-"""GAE kernel time vs steps-per-thread chunk (run on a B200)."""
-import sys, os, torch, ctypes as C
+"""GAE kernel time vs launch shape (run on a B200): knob = EPL * 10000 + L * 100 + C  (envs per lane, steps per
+thread, warps per block).  Cold-L2 timing: a 512 MB buffer is rewritten between launches; the event pair brackets
+only the GAE launch."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lerax_b200 import _lib as L
-L.lib.lrx_debug_set_gae_chunk.argtypes = [C.c_int]
-for T, N in ((128, 65536), (512, 65536), (128, 1 << 20)):
+
+dbg = L.debug_lib()
+shapes = [(128, 65536), (512, 65536), (128, 1 << 20), (128, 16384), (128, 4096)]
+knobs = [0] + [e * 10000 + l * 100 + c for e in (1, 2, 4) for l in (2, 4, 8) for c in (4, 8, 16) if not (e == 4 and l == 8)]
+if len(sys.argv) > 1:
+    knobs = [int(x) for x in sys.argv[1].split(",")]
+flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+for T, N in shapes:
     r = torch.randn(T, N, device="cuda"); v = torch.randn(T, N, device="cuda")
     d = (torch.rand(T, N, device="cuda") < 0.02).to(torch.uint8); lv = torch.randn(N, device="cuda")
-    adv = torch.empty_like(r); ret = torch.empty_like(r); ev = torch.zeros(4, dtype=torch.float64, device="cuda")
-    for chunk in (16, 18, 8, 24):  # 16/18: one env per lane, 16/8 steps; 8/24: two envs per lane, 8/4 steps
-        L.lib.lrx_debug_set_gae_chunk(chunk)
-        for with_ev in (True, False):
-            f = lambda: L.check(L.lib.lrx_gae(L.ptr(r), L.ptr(v), L.ptr(d), L.ptr(lv), L.ptr(adv), L.ptr(ret), N, T, 0.99, 0.95, 0, L.ptr(ev) if with_ev else None, L.stream_ptr()))
-            for _ in range(3): f()
+    adv = torch.empty_like(r); ret = torch.empty_like(r)
+    ev = torch.zeros(L.LRX_GAE_EV_DOUBLES, dtype=torch.float64, device="cuda")
+    best = None
+    for knob in knobs:
+        dbg.lrx_debug_set_gae_chunk(knob)
+        f = lambda: L.check(L.lib.lrx_gae(L.ptr(r), L.ptr(v), L.ptr(d), L.ptr(lv), L.ptr(adv), L.ptr(ret), N, T, 0.99, 0.95, 0, L.ptr(ev), L.stream_ptr()))
+        for _ in range(3):
+            f()
+        reps, tot = 10, 0.0
+        for _ in range(reps):
+            flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); e0.record()
-            for _ in range(20): f()
-            e1.record(); torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 20
-            print(f"T={T} N={N} chunk={chunk} ev={with_ev}: {ms*1000:7.1f} us  {T*N*17/ms/1e6:7.0f} GB/s")
+            e0.record(); f(); e1.record(); torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        cold = tot / reps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(20):
+            f()
+        e1.record(); torch.cuda.synchronize()
+        warm = e0.elapsed_time(e1) / 20
+        gbs = T * N * 17 / cold / 1e6
+        if best is None or gbs > best[1]:
+            best = (knob, gbs)
+        print(f"T={T} N={N} knob={knob:6d}: cold {cold*1000:7.1f} us {gbs:6.0f} GB/s ({gbs/6553:.2f})   back-to-back {warm*1000:7.1f} us {T*N*17/warm/1e6:6.0f} GB/s", flush=True)
+    print(f"== T={T} N={N}: best knob {best[0]} {best[1]:.0f} GB/s")
+dbg.lrx_debug_set_gae_chunk(0)

@@ -7,7 +7,7 @@ from lerax_b200 import _lib as L
 for n in (0, 16, 256, 10016, 10256, -16, -256):
     cyc = torch.zeros(16, dtype=torch.int64, device="cuda")
     for _ in range(2):
-        L.check(L.lib.lrx_debug_tmem_ld_under_mma(n, L.ptr(cyc), L.stream_ptr()))
+        L.check(L.debug_lib().lrx_debug_tmem_ld_under_mma(n, L.ptr(cyc), L.stream_ptr()))
     torch.cuda.synchronize()
     c = cyc.cpu().numpy()
     if n >= 10000:

@@ -4,7 +4,7 @@ from lerax_b200 import _lib as L
 np.set_printoptions(linewidth=220)
 def run(mode, variant, M):
     d = torch.full((128, 16), float("nan"), device="cuda")
-    L.check(L.lib.lrx_debug_tmem_operand_probe(L.ptr(d), mode, variant, M, L.stream_ptr())); torch.cuda.synchronize()
+    L.check(L.debug_lib().lrx_debug_tmem_operand_probe(L.ptr(d), mode, variant, M, L.stream_ptr())); torch.cuda.synchronize()
     return d.cpu().numpy()
 for M in (128, 64):
     d = run(0, 0, M)

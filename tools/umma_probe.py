@@ -11,7 +11,7 @@ def run(M, N, K, cfg, A, B, split=1):
     dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
     dump = torch.full((128, N), float("nan"), device="cuda")
     arr = (C.c_int32 * 12)(*cfg)
-    L.check(L.lib.lrx_debug_umma_gemm(L.ptr(dA), L.ptr(dB), L.ptr(dump), M, N, K, arr, split, L.stream_ptr()))
+    L.check(L.debug_lib().lrx_debug_umma_gemm(L.ptr(dA), L.ptr(dB), L.ptr(dump), M, N, K, arr, split, L.stream_ptr()))
     torch.cuda.synchronize()
     return dump.cpu().numpy()
 

@@ -9,7 +9,7 @@ for a_mn, b_mn in ((0, 0), (0, 1), (1, 0), (1, 1)):
             if M == 128 and N % 16: continue
             for ds in (1, 4):
                 cyc = torch.zeros(2, dtype=torch.int64, device="cuda")
-                L.check(L.lib.lrx_debug_umma_rate(M, N, ds | (a_mn << 8) | (b_mn << 9), L.ptr(cyc), L.stream_ptr()))
+                L.check(L.debug_lib().lrx_debug_umma_rate(M, N, ds | (a_mn << 8) | (b_mn << 9), L.ptr(cyc), L.stream_ptr()))
                 torch.cuda.synchronize()
                 c = cyc.cpu().numpy() / 256.0
                 print(f"A {'MN' if a_mn else 'K '}-major B {'MN' if b_mn else 'K '}-major M={M:3d} N={N:2d} accumulators={ds}: "

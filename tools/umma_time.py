@@ -12,7 +12,7 @@ def t(M, N, K, ca, cb, nprod=6, reps=64, dsplit=1):
     A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda")
     dump = torch.zeros(128, N, device="cuda"); cyc = torch.zeros(2, dtype=torch.int64, device="cuda")
     arr = (C.c_int32 * 12)(*(ca + cb))
-    L.check(L.lib.lrx_debug_umma_time_bf16(L.ptr(A), L.ptr(B), L.ptr(dump), M, N, K, arr, nprod | (dsplit << 8), reps, L.ptr(cyc), L.stream_ptr()))
+    L.check(L.debug_lib().lrx_debug_umma_time_bf16(L.ptr(A), L.ptr(B), L.ptr(dump), M, N, K, arr, nprod | (dsplit << 8), reps, L.ptr(cyc), L.stream_ptr()))
     torch.cuda.synchronize()
     n = reps * (K // 16) * nprod
     c = cyc.cpu().numpy()
