@@ -18,21 +18,33 @@
 // re-arms the ticket, so the result is bitwise reproducible and no memset launch precedes the kernel.
 __device__ __forceinline__ void ev_block_finish(double* ev, const double (*sEv)[4], int C, int tid) {
   __shared__ bool last;
+  __shared__ double red[64][4];
   if (tid < 4) {
     double s = 0;
     for (int cc = 0; cc < C; ++cc) s += sEv[cc][tid];
     ev[4 + 4 * (size_t)blockIdx.x + tid] = s;
+    __threadfence();  // only the partial sums need to be visible before the ticket; the adv / ret stores drain on their own
   }
-  __threadfence();
   __syncthreads();
   unsigned long long* ticket = reinterpret_cast<unsigned long long*>(ev + LRX_GAE_EV_DOUBLES - 1);
   if (tid == 0) last = atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1;
   __syncthreads();
-  if (!last) return;
+  if (!last) return;  // block-uniform
   __threadfence();
+  // fixed order: `parts` threads per quantity each add every parts-th block partial, then the parts in order
+  const int nthreads = blockDim.x * blockDim.y;
+  const int parts = nthreads >= 256 ? 64 : nthreads / 4;
+  if (tid < 4 * parts) {
+    const int k = tid & 3, part = tid >> 2;
+    double s = 0;
+#pragma unroll 8
+    for (unsigned b = part; b < gridDim.x; b += parts) s += __ldcg(ev + 4 + 4 * (size_t)b + k);
+    red[part][k] = s;
+  }
+  __syncthreads();
   if (tid < 4) {
     double s = 0;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(ev + 4 + 4 * (size_t)b + tid);
+    for (int p = 0; p < parts; ++p) s += red[p][tid];
     ev[tid] = s;
   }
   if (tid == 0) *ticket = 0ull;
@@ -247,7 +259,9 @@ extern "C" int lrx_gae(const float* rew, const float* val, const uint8_t* done,
       const uintptr_t m = (uintptr_t)rew | (uintptr_t)val | (uintptr_t)adv | (uintptr_t)ret | (uintptr_t)last_value;
       return N % epl == 0 && (m & (uintptr_t)(4 * epl - 1)) == 0 && ((uintptr_t)done & (uintptr_t)(epl - 1)) == 0;
     };
-    int epl = 2, L = 4, C = 8, minb = 4;
+    // tools/gae_time.py sweep on B200 (profiles/r2_gae.md): two envs per lane, four steps per thread, <= 48 registers (five
+    // 256-thread blocks per SM); four warps per block, eight once the buffer is far larger than one wave
+    int epl = 2, L = 4, C = ((long long)N * T >= (1ll << 26)) ? 8 : 4, minb = 5;
     if (g_gae_knob > 0) {
       minb = g_gae_knob / 1000000; epl = (g_gae_knob / 10000) % 100; L = (g_gae_knob / 100) % 100; C = g_gae_knob % 100;
     }
@@ -259,14 +273,17 @@ extern "C" int lrx_gae(const float* rew, const float* val, const uint8_t* done,
     const int grid = n_strips < LRX_GAE_EV_BLOCKS ? n_strips : LRX_GAE_EV_BLOCKS;
     bool launched = false;
 #define LRX_GAE_CASE(LL, EE, MT, MB)                                                                                  \
-  if (!launched && L == LL && epl == EE && C * 32 <= MT && (minb == MB || g_gae_knob == 0)) {                          \
+  if (!launched && L == LL && epl == EE && C * 32 <= MT && (minb == MB || any_minb)) {                                 \
     launch_gae_tn<LL, EE, MT, MB>(C, grid, s, rew, val, done, last_value, adv, ret, N, T, gamma, lam, ev_sums);        \
     launched = true;                                                                                                  \
   }
-    LRX_GAE_CASE(4, 2, 256, 4) LRX_GAE_CASE(4, 2, 256, 5) LRX_GAE_CASE(4, 2, 256, 3) LRX_GAE_CASE(4, 2, 512, 2)
-    LRX_GAE_CASE(2, 2, 256, 6) LRX_GAE_CASE(2, 2, 512, 3) LRX_GAE_CASE(8, 2, 256, 3) LRX_GAE_CASE(8, 2, 512, 1)
-    LRX_GAE_CASE(4, 1, 256, 6) LRX_GAE_CASE(4, 1, 512, 2) LRX_GAE_CASE(2, 1, 256, 8) LRX_GAE_CASE(8, 1, 256, 4)
-    LRX_GAE_CASE(4, 4, 256, 3) LRX_GAE_CASE(4, 4, 256, 2) LRX_GAE_CASE(2, 4, 256, 4) LRX_GAE_CASE(2, 4, 512, 2)
+    for (int pass = 0; pass < 2 && !launched; ++pass) {  // the requested register cap first, then any instantiation
+      const bool any_minb = pass == 1 && (g_gae_knob == 0 || minb == 0);
+      LRX_GAE_CASE(4, 2, 256, 5) LRX_GAE_CASE(4, 2, 256, 4) LRX_GAE_CASE(4, 2, 256, 3) LRX_GAE_CASE(4, 2, 512, 2)
+      LRX_GAE_CASE(2, 2, 256, 6) LRX_GAE_CASE(2, 2, 512, 3) LRX_GAE_CASE(8, 2, 256, 3) LRX_GAE_CASE(8, 2, 512, 1)
+      LRX_GAE_CASE(4, 1, 256, 6) LRX_GAE_CASE(4, 1, 512, 2) LRX_GAE_CASE(2, 1, 256, 8) LRX_GAE_CASE(8, 1, 256, 4)
+      LRX_GAE_CASE(4, 4, 256, 3) LRX_GAE_CASE(4, 4, 256, 2) LRX_GAE_CASE(2, 4, 256, 4) LRX_GAE_CASE(2, 4, 512, 2)
+    }
     LRX_REQUIRE(launched, LRX_ERR_INVALID_ARG, "lrx_gae: unsupported launch shape L=%d epl=%d C=%d minb=%d", L, epl, C, minb);
 #undef LRX_GAE_CASE
   } else {

@@ -700,6 +700,22 @@ int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxB
                        const int32_t* idx, int64_t B, int64_t B_global, const double* adv_sums,
                        const LrxPpoHyper* h, float* gradbuf, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream, bool* handled, const LrxApplyArgs* apply);
+int lrx_ppo_grad_tc128(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,
+                       int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, float* gradbuf,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled,
+                       const LrxApplyArgs* apply);
+// Default-width policies: second-generation tensor-core kernel (lrx_update_tc128.cu), else the first-generation one
+// (lrx_update_fused.cu); `handled` stays false for other widths (or with the kernels switched off).
+static int lrx_ppo_grad_tensor(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,
+                               int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, float* gradbuf,
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled,
+                               const LrxApplyArgs* apply) {
+  int rc = lrx_ppo_grad_tc128(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, stream,
+                              handled, apply);
+  if (rc || *handled) return rc;
+  return lrx_ppo_grad_fused(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, stream,
+                            handled, apply);
+}
 
 extern "C" int lrx_ppo_grad(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf,
                             const int32_t* idx, int64_t B, int64_t B_global, const double* adv_sums,
@@ -716,7 +732,7 @@ extern "C" int lrx_ppo_grad(const LrxPolicyDesc* pol, const float* params, const
   cudaStream_t s = (cudaStream_t)stream;
 
   bool handled = false;
-  rc = lrx_ppo_grad_fused(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, s, &handled, nullptr);
+  rc = lrx_ppo_grad_tensor(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, s, &handled, nullptr);
   if (rc) return rc;
   if (handled) return LRX_OK;
 
@@ -900,8 +916,8 @@ extern "C" int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* ad
     bool handled = false;
     ap.stats_out = stats_out + (size_t)b * LRX_PPO_NSTATS;
     LRX_REQUIRE(!h->normalize_advantages || adv_sums, LRX_ERR_INVALID_ARG, "adv_sums missing");
-    rc = lrx_ppo_grad_fused(pol, params, buf, idx + (size_t)b * B, B, B, adv_sums + 2 * b, h, gradbuf, workspace,
-                            tail.adv_sums_off, (cudaStream_t)stream, &handled, &ap);
+    rc = lrx_ppo_grad_tensor(pol, params, buf, idx + (size_t)b * B, B, B, adv_sums + 2 * b, h, gradbuf, workspace,
+                             tail.adv_sums_off, (cudaStream_t)stream, &handled, &ap);
     if (rc) return rc;
     if (handled) continue;
     rc = lrx_ppo_grad(pol, params, buf, idx + (size_t)b * B, B, B, adv_sums + 2 * b, h, gradbuf, workspace,

@@ -1,0 +1,830 @@
+// Fused PPO minibatch gradient for the default MLPActorCriticPolicy widths on the tensor cores, second generation:
+// 128-row tiles (UMMA M = 128), fp32 emulated with TWO bf16 pieces (lrx_tc2.cuh), accumulators in TMEM.
+//
+// Reference: algorithm/ppo.py:396-469 (ppo_loss + filter_value_and_grad) over the gathered minibatch of
+// buffer/base_buffer.py:90-103 -- the same contract as lrx_update_fused.cu (first generation: 64-row tiles, three
+// pieces), which stays selectable with lrx_debug_set_fused(1) and is checked against this kernel in the tests.
+//
+// Why this shape.  The first-generation kernel was bound by a serial chain per tile -- critical MMA group -> commit
+// -> tcgen05.ld -> epilogue -> CTA barrier, eleven times -- with one 64-row tile in flight and six bf16 MMAs per fp32
+// product (profiles/r1_ppo_grad_fused.md).  The update's contract is 1e-4 (BASELINE.json north_star), not the
+// rollout's 1e-5, so two round-to-nearest pieces and three products are enough (~3e-6 rms per dot product): half the
+// MMAs and two thirds of the shared memory, which buys a 128-row tile.  The chain is walked once per 128 rows instead
+// of once per 64, an M = 128 MMA costs 48 clk against 2 x 32 for two M = 64 ones, and every epilogue thread owns one
+// ROW (TMEM lane = row, 16 consecutive columns: 32x32b loads, 16-byte operand stores).
+// Bias gradients ride on the weight-gradient GEMMs: the activation operand carries a constant ones column, so
+// dW^T = dY^T [X | 1] has the bias gradient as its last accumulator column (no separate reduction, no extra MMA).
+//
+// One persistent CTA per SM: 16 epilogue warps (warp w: TMEM quadrant w & 3 = rows 32q .. 32q+31, column group
+// w >> 2 = 16 of a layer's 64 columns) + 1 issuer warp.  Per tile:
+//   gather rows (cp.async) -> encoder layer 0 (FMA) -> enc1 -> enc2 -> value head -> value loss -> value head bwd ->
+//   action head -> policy loss -> action head bwd -> encoder bwd,
+// weight gradients accumulated in TMEM across all tiles of the CTA and flushed once as a per-CTA partial
+// (reduce_partials_kernel sums the partials in a fixed order and applies clip + Adam).
+#include <stdlib.h>
+
+#include "lrx_common.cuh"
+#include "lrx_policy.cuh"
+#include "lrx_tc2.cuh"
+
+namespace {
+
+constexpr int ROWS = 128;              // rows per tile = UMMA M
+constexpr int WORKERS = 512;           // 16 epilogue warps
+constexpr int THREADS = WORKERS + 32;  // + warp 16: issues every tcgen05.mma (converged, one elected lane)
+
+// ---- shared memory map (bytes).  A c-group (8 columns) of an R-row matrix is R * 16 bytes.
+constexpr uint32_t CG = ROWS * 16;  // 2048: c-group of a 128-row activation matrix
+constexpr uint32_t OFF_W1 = 0;                       // [64][64]  hi 8192 | lo 8192
+constexpr uint32_t OFF_W2 = OFF_W1 + 16384;          // [16][64]  hi 2048 | lo 2048
+constexpr uint32_t OFF_WV0 = OFF_W2 + 4096;          // [64][16]  hi 2048 | lo 2048
+constexpr uint32_t OFF_WV1 = OFF_WV0 + 4096;         // [64][64]
+constexpr uint32_t OFF_WA0 = OFF_WV1 + 16384;        // [64][16]
+constexpr uint32_t OFF_WA1 = OFF_WA0 + 4096;         // [16][64]
+constexpr uint32_t OFF_XOBS = OFF_WA1 + 4096;        // [128][8 obs | ones, 0 x 7]: hi 2 c-groups, lo 1 c-group
+constexpr uint32_t OFF_XH1 = OFF_XOBS + 3 * CG;      // [128][64 | ones]: hi 9 c-groups, lo 8
+constexpr uint32_t OFF_XH2 = OFF_XH1 + 17 * CG;      // [128][64]: hi 8, lo 8 (also d(loss)/d(h1) at the end of a tile)
+constexpr uint32_t OFF_XF = OFF_XH2 + 16 * CG;       // [128][16 | ones]: hi 3, lo 2
+constexpr uint32_t OFF_XB1 = OFF_XF + 5 * CG;        // [128][64 | ones]: head layer-1 activations (value, then action)
+constexpr uint32_t OFF_DY64 = OFF_XB1 + 17 * CG;     // [128][64]: current upstream gradient
+constexpr uint32_t OFF_DY16 = OFF_DY64 + 16 * CG;    // [128][16]
+// fp32 staging (no MMA operand): gathered row data of the NEXT tile (cp.async destinations; single-buffered, the gather
+// is issued after the tile's last read of them): observations [128][8], five 32-bit planes [5][128] -- return, old
+// value, action bits, old log-prob, advantage --, valid flags [128] u8.
+constexpr int R_RET = 0, R_VAL = 1, R_ACT = 2, R_LOGP = 3, R_ADV = 4, R_PLANES = 5;
+constexpr uint32_t OFF_OBS32 = OFF_DY16 + 4 * CG;
+constexpr uint32_t OFF_PLANES = OFF_OBS32 + ROWS * 8 * 4;
+constexpr uint32_t OFF_VALID = OFF_PLANES + R_PLANES * ROWS * 4;
+constexpr uint32_t OFF_F32 = OFF_VALID + ROWS;                    // fp32 biases etc. (tc::F_COUNT floats)
+constexpr uint32_t OFF_VPART = OFF_F32 + tc::F_RESERVE * 4;       // [4 column groups][128 rows] partial value dot products
+constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ROWS * 4;           // 3 mbarriers, TMEM slot
+constexpr uint32_t OFF_IDX = OFF_MISC + 64;                       // minibatch indices of the tile after the one being gathered
+constexpr uint32_t SMEM_BYTES = OFF_IDX + ROWS * 4;
+static_assert(SMEM_BYTES <= 227 * 1024, "tc128 update kernel exceeds shared memory");
+static_assert(tc::F_COUNT <= tc::F_RESERVE, "fp32 parameter block too small");
+
+// ---- TMEM columns (fp32).  M = 128 accumulators use all 128 lanes; the M = 64 weight-gradient accumulators use
+// lanes 0-15 of every 32-lane quadrant (output unit j at lane 32 * (j / 16) + j % 16).
+constexpr uint32_t C_D0 = 0;       // 64: layer outputs
+constexpr uint32_t C_D1 = 64;      // 64: action head layer-1 pre-activations (issued with the value head's)
+constexpr uint32_t C_DF = 128;     // 16: d(features), summed over both heads
+constexpr uint32_t C_G0 = 144;     // enc0  dW^T [64 out][8 in | bias | 0 x 7]
+constexpr uint32_t C_G1 = 160;     // enc1  dW^T [64][64 | bias, 0 x 7]
+constexpr uint32_t C_G2 = 232;     // enc2  dW   [64 in][16 out]
+constexpr uint32_t C_GV0 = 248;    // v0    dW^T [64][16 | bias, 0 x 7]
+constexpr uint32_t C_GV1 = 272;    // v1    dW^T [64][64 | bias, 0 x 7]
+constexpr uint32_t C_GA0 = 344;    // a0    dW^T [64][16 | bias, 0 x 7]
+constexpr uint32_t C_GA1 = 368;    // a1    dW   [64 in][16 out]
+constexpr uint32_t TMEM_COLS = 512;
+
+struct Tc128Args {
+  const float* params;
+  LrxBatchView buf;
+  const int32_t* idx;
+  long long B;
+  double B_global;
+  const double* adv_sums;
+  LrxPpoHyper h;
+  float* partial;           // [gridDim.x][partial_stride]
+  long long partial_stride;
+  double* loss_partial;     // [gridDim.x][8]
+  int n_tiles;
+  int obs_dim, n_out, is_box;
+  tc::LayerOffsets lo;
+};
+
+__device__ __forceinline__ void tie_weights_f(float a, float b, float& wa, float& wb) {
+  wa = a < b ? 1.f : (a == b ? 0.5f : 0.f);  // JAX: d min(a,b) splits ties 1/2-1/2
+  wb = 1.f - wa;
+}
+__device__ __forceinline__ float clip_grad_f(float x, float lo, float hi) {
+  return (x > lo && x < hi) ? 1.f : ((x == lo || x == hi) ? 0.5f : 0.f);
+}
+
+// Sum over the 32 lanes of 16 per-lane values, scattered: afterwards v[0] of lane L is the warp-wide sum of element
+// (L >> 1) & 15 (both lanes of a pair hold the same sum).  16 shuffles instead of 80 for sixteen full reductions.
+__device__ __forceinline__ float reduce_scatter16(float* v, int lane) {
+#pragma unroll
+  for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < half) {
+        const float send = up ? v[j] : v[j + half];
+        const float keep = up ? v[j + half] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// NOUT: number of action-head outputs when known at compile time (1 = scalar Box, 2 = CartPole, 3 = Acrobot /
+// MountainCar); 0 = read it from the arguments (up to LRX_MAX_NOUT).
+template <int NOUT>
+__global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid_constant__ Tc128Args a) {
+  constexpr int NO = NOUT ? NOUT : LRX_MAX_NOUT;
+  const int n_out = NOUT ? NOUT : a.n_out;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
+  const bool worker = warp < WORKERS / 32;  // warp-uniform
+  const int q = warp & 3, g = worker ? (warp >> 2) : 0;
+  const int m = q * 32 + lane;  // row of the tile owned by this thread
+  const bool g0 = worker && (g == 0);  // row-owner warps: per-row loss arithmetic
+  const int cg = g * 16;               // first column of this thread's group in a 64-wide layer
+  float* fp = reinterpret_cast<float*>(smem + OFF_F32);
+  float* vpart = reinterpret_cast<float*>(smem + OFF_VPART);
+  uint64_t* barA = reinterpret_cast<uint64_t*>(smem + OFF_MISC);      // critical GEMM(s) of a step done
+  uint64_t* barB = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 8);  // background GEMMs of a step done
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 16);
+  uint64_t* barL = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 24);  // every epilogue warp has done its TMEM loads
+  int* idx_s = reinterpret_cast<int*>(smem + OFF_IDX);
+  float* obs_s = reinterpret_cast<float*>(smem + OFF_OBS32);
+  float* rows_s = reinterpret_cast<float*>(smem + OFF_PLANES);
+  uint8_t* valid_s = smem + OFF_VALID;
+
+  const tc2::Mat W1{smem + OFF_W1, 64, 8192}, W2{smem + OFF_W2, 16, 2048};
+  const tc2::Mat WV0{smem + OFF_WV0, 64, 2048}, WV1{smem + OFF_WV1, 64, 8192};
+  const tc2::Mat WA0{smem + OFF_WA0, 64, 2048}, WA1{smem + OFF_WA1, 16, 2048};
+  const tc2::Mat XOBS{smem + OFF_XOBS, ROWS, 2 * CG};
+  const tc2::Mat XH1{smem + OFF_XH1, ROWS, 9 * CG}, XH2{smem + OFF_XH2, ROWS, 8 * CG};
+  const tc2::Mat DH1 = XH2;  // d(loss)/d(h1) of a tile reuses the XH2 buffer (see the last two steps of a tile)
+  const tc2::Mat XF{smem + OFF_XF, ROWS, 3 * CG}, XB1{smem + OFF_XB1, ROWS, 9 * CG};
+  const tc2::Mat DY64{smem + OFF_DY64, ROWS, 8 * CG}, DY16{smem + OFF_DY16, ROWS, 2 * CG};
+
+  // ------------------------------------------------------------------ one-time staging
+  tc2::stage_weight(a.params + a.lo.w[tc::L_ENC1], 64, 64, 64, W1, tid, THREADS);
+  tc2::stage_weight(a.params + a.lo.w[tc::L_ENC2], 16, 64, 64, W2, tid, THREADS);
+  tc2::stage_weight(a.params + a.lo.w[tc::L_V0], 64, 16, 16, WV0, tid, THREADS);
+  tc2::stage_weight(a.params + a.lo.w[tc::L_V1], 64, 64, 64, WV1, tid, THREADS);
+  tc2::stage_weight(a.params + a.lo.w[tc::L_A0], 64, 16, 16, WA0, tid, THREADS);
+  tc2::stage_weight(a.params + a.lo.w[tc::L_A1], 16, 64, 64, WA1, tid, THREADS);
+  tc::stage_f32(a.params, a.lo, n_out, a.obs_dim, fp, tid, THREADS);
+  if (tid < ROWS) {  // the constant ones columns (bf16 1.0 = 0x3F80 in element 0 of the extra c-group)
+    const uint4 one = make_uint4(0x00003F80u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(XOBS.ptr + 1 * CG + tid * 16) = one;
+    *reinterpret_cast<uint4*>(XH1.ptr + 8 * CG + tid * 16) = one;
+    *reinterpret_cast<uint4*>(XF.ptr + 2 * CG + tid * 16) = one;
+    *reinterpret_cast<uint4*>(XB1.ptr + 8 * CG + tid * 16) = one;
+  }
+  if (tid == 0) {
+    umma::mbar_init(barA, 1);
+    umma::mbar_init(barB, 1);
+    umma::mbar_init(barL, WORKERS / 32);
+    umma::fence_mbar_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tslot, TMEM_COLS);
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tb = *tslot;
+  const uint32_t tw = umma::tmem_addr(tb, q * 32, 0);  // this warp's quadrant
+  if (worker) {
+    float z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0.f;
+    for (int c = g * 128; c < g * 128 + 128; c += 16) umma::tmem_st16(tw + c, z);
+    umma::tmem_st_wait();
+  }
+
+  // One step = the epilogue warps publish their shared-memory operands, the issuer warp enqueues the step's CRITICAL
+  // GEMM(s) (the result the next epilogue consumes) and commits barA, then the BACKGROUND GEMMs (weight gradients
+  // accumulating in TMEM) and commits barB where something must know that they are done.  See lrx_update_fused.cu for
+  // the measurements behind track_bg / after_loads (tcgen05.ld does not overtake queued MMAs; a commit costs ~300 clk).
+  uint32_t phA = 0, phB = 0, phL = 0;
+  bool pendA = false, pendB = false, pendL = false;
+  auto wait_crit = [&]() {
+    if (pendA) {
+      umma::mbar_wait(barA, phA);
+      phA ^= 1u;
+      pendA = false;
+      umma::tc_fence_after();
+    }
+  };
+  auto wait_bg = [&]() {
+    if (pendB) {
+      umma::mbar_wait(barB, phB);
+      phB ^= 1u;
+      pendB = false;
+      umma::tc_fence_after();
+    }
+  };
+  auto signal_loaded = [&]() {  // epilogue warps, after tcgen05.wait::ld (or with nothing to load)
+    if (pendL) {
+      pendL = false;
+      umma::tc_fence_before();
+      if (lane == 0) umma::mbar_arrive(barL);
+    }
+  };
+  auto step_impl = [&](auto&& crit, auto&& bg, bool track_bg, bool after_loads = false) {
+    if (worker) {
+      signal_loaded();
+      wait_crit();
+      wait_bg();
+      umma::fence_async_smem();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (!worker) {
+      umma::tc_fence_after();
+      const bool leader = umma::elect_one();
+      crit(leader);
+      if (leader) umma::mma_commit(barA);
+      if (after_loads) {
+        umma::mbar_wait(barL, phL);
+        phL ^= 1u;
+        umma::tc_fence_after();
+      }
+      bg(leader);
+      if (track_bg && leader) umma::mma_commit(barB);
+      __syncwarp();
+    } else {
+      pendA = true;
+      pendB = track_bg;
+      pendL = after_loads;
+    }
+  };
+  auto step_late = [&](auto&& crit, auto&& bg) { step_impl(crit, bg, false, true); };
+  auto step = [&](auto&& crit, auto&& bg) { step_impl(crit, bg, false); };
+  auto step_track = [&](auto&& crit, auto&& bg) { step_impl(crit, bg, true); };
+  auto none = [](bool) {};
+
+  const LrxPpoHyper h = a.h;
+  const float invB = (float)(1.0 / a.B_global);
+  float adv_mean = 0.f, adv_den = 1.f;
+  if (h.normalize_advantages) {
+    const double mean = a.adv_sums[0] / a.B_global;
+    double var = a.adv_sums[1] / a.B_global - mean * mean;
+    var = var > 0 ? var : 0;
+    adv_mean = (float)mean;
+    adv_den = (float)sqrt(var) + 1.1920928955078125e-07f;  // + finfo(float32).eps   (ppo.py:424-427)
+  }
+  float log_std = 0.f, scale = 1.f, log_scale = 0.f;
+  if (a.is_box) {
+    log_std = __ldg(a.params + a.lo.log_std);
+    scale = expf(log_std);
+    log_scale = logf(scale);
+  }
+  // per-thread loss statistics: one row per tile, at most a few dozen tiles per launch -> fp32 here, fp64 across threads
+  float s_kl = 0, s_pol = 0, s_val = 0, s_ent = 0, s_dls = 0, s_bad = 0;
+
+  // ---- epilogue building blocks: this thread's row m, columns cg .. cg+15 of a 64-wide layer
+  auto store_row16 = [&](const tc2::Mat& dst, const float* v, bool need_bg) {
+    uint32_t hw[8], lw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tc2::split2(v[2 * i], v[2 * i + 1], hw[i], lw[i]);
+    if (need_bg) wait_bg();
+    uint8_t* d = dst.ptr + (uint32_t)(2 * g) * CG + (uint32_t)m * 16u;
+    *reinterpret_cast<uint4*>(d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(d + CG) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    *reinterpret_cast<uint4*>(d + dst.lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    *reinterpret_cast<uint4*>(d + dst.lo_off + CG) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+  };
+  auto add_bias_relu = [&](float* v, const float* bias, uint32_t& mask) {
+    const float4* bp = reinterpret_cast<const float4*>(bias + cg);  // warp-uniform address: broadcast
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = bp[i];
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+    mask = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (v[j] > 0.f) mask |= (1u << j);
+      v[j] = fmaxf(v[j], 0.f);
+    }
+  };
+  // layer output -> + bias -> ReLU (16-bit mask recorded) -> operand X
+  auto fwd64 = [&](uint32_t col, const float* bias, const tc2::Mat& dst, uint32_t& mask) {
+    wait_crit();
+    float v[16];
+    umma::tmem_ld16(tw + col + cg, v);
+    umma::tmem_ld_wait();
+    signal_loaded();
+    add_bias_relu(v, bias, mask);
+    store_row16(dst, v, false);
+  };
+  // dX masked by the ReLU of the layer that produced X -> operand dY
+  auto bwd64 = [&](uint32_t col, uint32_t mask, const tc2::Mat& dst, bool need_bg) {
+    wait_crit();
+    float v[16];
+    umma::tmem_ld16(tw + col + cg, v);
+    umma::tmem_ld_wait();
+    signal_loaded();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = ((mask >> j) & 1u) ? v[j] : 0.f;
+    store_row16(dst, v, need_bg);
+  };
+  // 16-wide layer outputs (features, d(features)): every column group takes 4 of the 16 columns of its rows
+  float bs_e2[4] = {0.f, 0.f, 0.f, 0.f};  // encoder output layer's bias gradient: columns 4g..4g+3 over this thread's rows
+  auto quarter16 = [&](uint32_t col, const float* bias, const tc2::Mat& dst, bool sum_cols) {
+    wait_crit();
+    float v[4];
+    umma::tmem_ld4(tw + col + 4 * g, v);
+    umma::tmem_ld_wait();
+    signal_loaded();
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += bias[4 * g + j];
+    }
+    if (sum_cols) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bs_e2[j] += v[j];
+    }
+    tc2::store4(dst, 4 * g, m, v);
+  };
+
+  // ---- row gather (buffer/base_buffer.py:90-103): cp.async straight into shared staging, one lane of column group 2
+  // per row, one tile ahead; the minibatch index two tiles ahead.  No register is the destination of a global load in
+  // the tile loop (lrx_update_fused.cu: such a load cost 9 %).
+  auto cp_async4 = [](void* dst, const void* src, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(umma::smem_u32(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+  };
+  auto cp_async16 = [](void* dst, const void* src, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(umma::smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+  };
+  auto tile_row_ok = [&](int t) { return t < a.n_tiles && (long long)t * ROWS + m < a.B; };
+  auto gather_rows = [&](int i, bool ok) {  // buffer row i (zeros when !ok) -> this lane's staging slot m
+    const int n = i / a.buf.T, t = i - n * a.buf.T;
+    const size_t src = ok ? (size_t)t * a.buf.N + n : 0;
+    cp_async4(rows_s + R_RET * ROWS + m, a.buf.ret + src, ok);
+    cp_async4(rows_s + R_VAL * ROWS + m, (h.clip_value_loss ? a.buf.val : a.buf.ret) + src, ok && h.clip_value_loss);
+    cp_async4(rows_s + R_ACT * ROWS + m, (const int32_t*)a.buf.act + src, ok);
+    cp_async4(rows_s + R_LOGP * ROWS + m, a.buf.logp + src, ok);
+    cp_async4(rows_s + R_ADV * ROWS + m, a.buf.adv + src, ok);  // raw; normalised where it is used
+    const float* op = a.buf.obs + src * a.obs_dim;
+    if (a.obs_dim == 4) {  // one 16-byte copy (CartPole)
+      cp_async16(obs_s + m * 8, op, ok);
+      *reinterpret_cast<float4*>(obs_s + m * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cp_async4(obs_s + m * 8 + k, op + (k < a.obs_dim ? k : 0), ok && k < a.obs_dim);
+    }
+    valid_s[m] = ok ? 1 : 0;
+  };
+  auto gather_idx = [&](int t) {  // minibatch indices of tile t -> idx_s
+    const bool ok = tile_row_ok(t);
+    cp_async4(idx_s + m, a.idx + (ok ? (long long)t * ROWS + m : 0), ok);
+  };
+  auto gather_commit = []() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+  auto gather_wait = []() { asm volatile("cp.async.wait_group 0;" ::: "memory"); };
+  const bool gatherer = worker && g == 2;
+  if (gatherer) {  // first tile: the only register load of an index
+    const int t0 = (int)blockIdx.x;
+    const bool ok = tile_row_ok(t0);
+    const int i = ok ? __ldg(a.idx + (long long)t0 * ROWS + m) : 0;
+    gather_rows(i, ok);
+    gather_idx(t0 + (int)gridDim.x);
+    gather_commit();
+    gather_wait();
+  }
+  __syncthreads();
+
+  // gradients kept in registers across the tiles of the CTA
+  float gw_v2 = 0.f, gb_v2 = 0.f;  // value output layer (64 -> 1): dW of column cg + (lane >> 1) % 16 over this warp's rows; db
+  float gm_w[NO], gm_b[NO];        // action_dist.mapping (16 -> n_out): dW[o][(lane >> 1) % 16], db[o] (row-owner warps)
+#pragma unroll
+  for (int o2 = 0; o2 < NO; ++o2) gm_w[o2] = gm_b[o2] = 0.f;
+
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const bool valid_m = valid_s[m] != 0;  // this thread's row is a real row of the minibatch
+
+    // ---------------------------------------------------------------- encoder layer 0 (d <= 8 inputs) on the FMA pipe
+    uint32_t mk_h1 = 0, mk_h2 = 0, mk_b1 = 0, mk_b2 = 0;
+    if (worker) {
+      float x[8];
+      {
+        const float4 lo4 = *reinterpret_cast<const float4*>(obs_s + m * 8), hi4 = *reinterpret_cast<const float4*>(obs_s + m * 8 + 4);
+        x[0] = lo4.x; x[1] = lo4.y; x[2] = lo4.z; x[3] = lo4.w; x[4] = hi4.x; x[5] = hi4.y; x[6] = hi4.z; x[7] = hi4.w;
+      }
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 wa = *reinterpret_cast<const float4*>(fp + tc::F_W0 + (cg + j) * 8);  // warp-uniform: broadcast
+        float acc = fmaf(wa.w, x[3], fmaf(wa.z, x[2], fmaf(wa.y, x[1], wa.x * x[0])));
+        if (a.obs_dim > 4) {
+          const float4 wb = *reinterpret_cast<const float4*>(fp + tc::F_W0 + (cg + j) * 8 + 4);
+          acc = fmaf(wb.w, x[7], fmaf(wb.z, x[6], fmaf(wb.y, x[5], fmaf(wb.x, x[4], acc))));
+        }
+        v[j] = acc;
+      }
+      add_bias_relu(v, fp + tc::F_B0, mk_h1);
+      store_row16(XH1, v, true);  // waits for the previous tile's last GEMMs (they read XH1 / XH2 / XOBS)
+      if (g0) {
+        float z8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) z8[k] = k < a.obs_dim ? x[k] : 0.f;
+        tc2::store8(XOBS, 0, m, z8);  // lo piece: c-group 0 only (XOBS.lo_off = 2 c-groups)
+      }
+    }
+    step([&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D0, XH1, W1, ROWS, 64, 64, 4, 0u); }, none);
+    if (worker) fwd64(C_D0, fp + tc::F_B1, XH2, mk_h2);
+    step([&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D0, XH2, W2, ROWS, 16, 16, 4, 0u); }, none);
+    if (worker) quarter16(C_D0, fp + tc::F_B2, XF, false);
+
+    // ---------------------------------------------------------------- value head forward
+    step([&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D0, XF, WV0, ROWS, 64, 64, 1, 0u); },
+         [&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D1, XF, WA0, ROWS, 64, 64, 1, 0u); });  // action head layer 1, consumed later
+    if (worker) fwd64(C_D0, fp + tc::F_BV0, XB1, mk_b1);
+    step([&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D0, XB1, WV1, ROWS, 64, 64, 4, 0u); }, none);
+    float xb2[16];  // value layer-2 activations of this thread's row and column group
+    if (worker) {
+      wait_crit();
+      umma::tmem_ld16(tw + C_D0 + cg, xb2);
+      umma::tmem_ld_wait();
+      add_bias_relu(xb2, fp + tc::F_BV1, mk_b2);
+      const float4* wp = reinterpret_cast<const float4*>(fp + tc::F_WV2 + cg);
+      float pr = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 w = wp[i];
+        pr = fmaf(w.w, xb2[4 * i + 3], fmaf(w.z, xb2[4 * i + 2], fmaf(w.y, xb2[4 * i + 1], fmaf(w.x, xb2[4 * i], pr))));
+      }
+      vpart[g * ROWS + m] = pr;
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- value loss (ppo.py:435-451) and its backward
+    bool bad = false;
+    if (worker) {
+      const float value = (((fp[tc::F_BV2] + vpart[m]) + vpart[ROWS + m]) + vpart[2 * ROWS + m]) + vpart[3 * ROWS + m];
+      const float ret_r = rows_s[R_RET * ROWS + m], vold_r = rows_s[R_VAL * ROWS + m];
+      float dv = 0.f, sv = 0.f;  // d loss / d value of this row (0 past the minibatch) and its squared-error statistic
+      if (valid_m) {
+        const float c = h.clip_coefficient;
+        const float e1 = value - ret_r;
+        float dvl;
+        if (h.clip_value_loss) {
+          const float dvo = value - vold_r;
+          const float clipped = vold_r + lrx_clipf(dvo, -c, c);
+          const float e2 = clipped - ret_r;
+          const float q1 = e1 * e1, q2 = e2 * e2;
+          sv = fminf(q1, q2);
+          float u1, u2;
+          tie_weights_f(q1, q2, u1, u2);
+          dvl = invB * (u1 * e1 + u2 * e2 * clip_grad_f(dvo, -c, c));
+        } else {
+          sv = e1 * e1;
+          dvl = invB * e1;
+        }
+        dv = h.value_loss_coefficient * dvl;
+      }
+      if (g0 && valid_m) {
+        bad = !isfinite(value);
+        s_val += sv;
+        gb_v2 += dv;
+      }
+      // value output layer (64 -> 1) on the FMA pipe: dW[c] += h2[r][c] dv[r] (reduced over the warp's rows), dX = dv W
+      float t16[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t16[j] = xb2[j] * dv;
+      gw_v2 += reduce_scatter16(t16, lane);
+      const float4* wp = reinterpret_cast<const float4*>(fp + tc::F_WV2 + cg);
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 w = wp[i];
+        v[4 * i] = dv * w.x; v[4 * i + 1] = dv * w.y; v[4 * i + 2] = dv * w.z; v[4 * i + 3] = dv * w.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ((mk_b2 >> j) & 1u) ? v[j] : 0.f;
+      store_row16(DY64, v, false);
+    }
+    step_track([&](bool ld) { tc2::gemm<false, true>(ld, tb + C_D0, DY64, WV1, ROWS, 64, 64, 4, 0u); },      // dX = dY W
+               [&](bool ld) { tc2::gemm<true, true>(ld, tb + C_GV1, DY64, XB1, 64, 72, 64, 8, 1u); });        // [dW^T | db] += dY^T [X | 1]
+    if (worker) {
+      bwd64(C_D0, mk_b1, DY64, true);  // the background GEMM reads DY64 and XB1
+      // -------------------------------------------------------------- action head forward
+      fwd64(C_D1, fp + tc::F_BA0, XB1, mk_b1);
+    }
+    // background, issued once the action head's output has been loaded from TMEM: d(features) from the value head and
+    // the value layer-0 weight gradient run under the policy-loss arithmetic
+    step_late([&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D0, XB1, WA1, ROWS, 16, 16, 4, 0u); },
+              [&](bool ld) {
+                tc2::gemm<false, true>(ld, tb + C_DF, DY64, WV0, ROWS, 16, 16, 4, 0u);
+                tc2::gemm<true, true>(ld, tb + C_GV0, DY64, XF, 64, 24, 16, 8, 1u);
+              });
+    if (g0) {
+      float a2[16];
+      wait_crit();
+      umma::tmem_ld16(tw + C_D0, a2);
+      umma::tmem_ld_wait();
+      signal_loaded();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a2[j] += fp[tc::F_BA1 + j];
+      // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261) on the FMA pipe
+      float head[NO];
+#pragma unroll
+      for (int o2 = 0; o2 < NO; ++o2) {
+        float sacc = fp[tc::F_BMAP + o2];
+        if (o2 < n_out) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sacc = fmaf(fp[tc::F_WMAP + o2 * 16 + i], a2[i], sacc);
+        }
+        head[o2] = sacc;
+      }
+
+      // -------------------------------------------------------------- policy loss (ppo.py:405-434,452-467)
+      float dhead[NO];
+#pragma unroll
+      for (int o2 = 0; o2 < NO; ++o2) dhead[o2] = 0.f;
+      if (valid_m) {
+        const int act_raw = reinterpret_cast<const int*>(rows_s)[R_ACT * ROWS + m];  // fp32 (Box) or int32 (Discrete) bits
+        const float logp_old = rows_s[R_LOGP * ROWS + m], A = rows_s[R_ADV * ROWS + m];
+        float logp, entropy, z_n = 0.f;
+        float lp[NO], pr[NO];
+        if (a.is_box) {
+          const float loc = head[0];
+          z_n = (__int_as_float(act_raw) - loc) / scale;
+          logp = -0.5f * (z_n * z_n) - (LRX_HALF_LOG_2PI + log_scale);
+          entropy = 0.5f + LRX_HALF_LOG_2PI + log_scale;
+        } else {
+#pragma unroll
+          for (int j = 0; j < NO; ++j) lp[j] = j < n_out ? head[j] : 0.f;
+          log_softmax_n<NO>(lp, n_out);
+          logp = 0.f;
+          entropy = 0.f;
+#pragma unroll
+          for (int j = 0; j < NO; ++j) {
+            if (j < n_out) {
+              pr[j] = expf(lp[j]);
+              entropy -= pr[j] * lp[j];
+              if (j == act_raw) logp = lp[j];
+            }
+          }
+        }
+        bad = bad || !(isfinite(logp) && isfinite(entropy));  // ppo.py:413-417
+        if (bad) s_bad += 1.0f;
+        const float log_ratio = logp - logp_old;
+        const float ratio = expf(log_ratio);
+        s_kl += ratio - log_ratio;
+        const float c = h.clip_coefficient, lo = 1.f - c, hi = 1.f + c;
+        const float An = h.normalize_advantages ? (A - adv_mean) / adv_den : A;  // ppo.py:424-427
+        float dlogp;
+        if (h.surrogate == 1) {  // A2C / REINFORCE: -mean(logp * A)   (a2c.py:401, reinforce.py:391)
+          s_pol += logp * An;
+          dlogp = -invB * An;
+        } else {
+          const float s1 = An * ratio, s2 = An * lrx_clipf(ratio, lo, hi);
+          s_pol += fminf(s1, s2);
+          float w1, w2;
+          tie_weights_f(s1, s2, w1, w2);
+          dlogp = -invB * (w1 * An * ratio + w2 * An * clip_grad_f(ratio, lo, hi) * ratio);
+        }
+        s_ent += entropy;
+        const float ch = h.entropy_loss_coefficient;
+        if (a.is_box) {
+          dhead[0] = dlogp * z_n / scale;
+          s_dls += dlogp * (z_n * z_n - 1.0f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < NO; ++j) {
+            if (j < n_out) {
+              const float dH = -pr[j] * (lp[j] + entropy);
+              dhead[j] = dlogp * ((j == act_raw ? 1.f : 0.f) - pr[j]) + (-ch * invB) * dH;
+            }
+          }
+        }
+      }
+      // -------------------------------------------------------------- action head backward (mapping, FMA)
+      {
+        float d16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int o2 = 0; o2 < NO; ++o2)
+            if (o2 < n_out) sacc = fmaf(dhead[o2], fp[tc::F_WMAP + o2 * 16 + i], sacc);
+          d16[i] = sacc;
+        }
+        tc2::store8(DY16, 0, m, d16);
+        tc2::store8(DY16, 1, m, d16 + 8);
+      }
+      // mapping layer gradients: dW[o][i] += dhead[r][o] a2[r][i], db[o] += dhead[r][o] over the warp's 32 rows
+#pragma unroll
+      for (int o2 = 0; o2 < NO; ++o2) {
+        if (o2 < n_out) {
+          float t16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t16[i] = dhead[o2] * a2[i];
+          gm_w[o2] += reduce_scatter16(t16, lane);
+          gm_b[o2] += warp_sum(dhead[o2]);
+        }
+      }
+    }
+    step([&](bool ld) { tc2::gemm<false, true>(ld, tb + C_D0, DY16, WA1, ROWS, 64, 64, 1, 0u); },        // dX = dY16 W_a1 (K = 16 outputs)
+         [&](bool ld) { tc2::gemm<true, true>(ld, tb + C_GA1, XB1, DY16, 64, 16, 16, 8, 1u); });           // dW[in][out] += X^T dY
+    if (worker) bwd64(C_D0, mk_b1, DY64, false);  // this step's background GEMM does not read DY64
+    // every read of this tile's gathered rows is behind the barrier of the step above: fetch the next tile's
+    if (gatherer) {
+      gather_rows(idx_s[m], tile_row_ok(tile + (int)gridDim.x));
+      gather_idx(tile + 2 * (int)gridDim.x);
+      gather_commit();
+    }
+    step([&](bool ld) { tc2::gemm<false, true>(ld, tb + C_DF, DY64, WA0, ROWS, 16, 16, 4, 1u); },        // d(features) += action head
+         [&](bool ld) { tc2::gemm<true, true>(ld, tb + C_GA0, DY64, XF, 64, 24, 16, 8, 1u); });
+
+    // ---------------------------------------------------------------- encoder backward
+    if (worker) quarter16(C_DF, nullptr, DY16, true);                    // background reads DY64 / XF only
+    step([&](bool ld) { tc2::gemm<false, true>(ld, tb + C_D0, DY16, W2, ROWS, 64, 64, 1, 0u); },
+         [&](bool ld) { tc2::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 16, 8, 1u); });
+    if (worker) bwd64(C_D0, mk_h2, DY64, false);  // background reads XH2 / DY16 only
+    step([&](bool ld) { tc2::gemm<false, true>(ld, tb + C_D0, DY64, W1, ROWS, 64, 64, 4, 0u); },
+         [&](bool ld) { tc2::gemm<true, true>(ld, tb + C_G1, DY64, XH1, 64, 72, 64, 8, 1u); });
+    // d(h1) goes into the XH2 buffer, dead since the GEMMs of the step before (ordered before this step's critical
+    // GEMM) read it: no wait for this step's weight-gradient GEMM, which still reads DY64 and XH1
+    if (worker) bwd64(C_D0, mk_h1, DH1, false);
+    // the next tile's rows have had three steps to arrive; the barrier of the step below publishes them
+    if (gatherer) gather_wait();
+    step_track(none, [&](bool ld) {
+      tc2::gemm<true, true>(ld, tb + C_G0, DH1, XOBS, 64, 16, 8, 8, 1u);  // [dW^T | db]: obs c-group + the ones c-group
+    });  // its commit also covers the GEMM on XH1 of the step before: waited for before XH1 / XH2 / XOBS are rewritten
+  }
+  if (worker) {
+    wait_crit();
+    wait_bg();
+  }
+
+  // ------------------------------------------------------------------ flush the gradient partial
+  float* part = a.partial + (size_t)blockIdx.x * a.partial_stride;
+  const tc::LayerOffsets& lo = a.lo;
+  const bool low = lane < 16;          // M = 64 accumulators: output / input unit mo at lanes 0-15 of the quadrant
+  const int mo = q * 16 + (lane & 15);
+  // dW^T accumulators: TMEM row = output unit, columns = inputs, then the bias gradient at column bias_col
+  auto flush_T = [&](uint32_t col, int in_real, int in_pad, int bias_col, int layer) {
+    for (int c0 = 0; c0 < in_pad; c0 += 8) {
+      float v[8];
+      umma::tmem_ld8(tw + col + c0, v);
+      umma::tmem_ld_wait();
+      if (low) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < in_real) part[lo.w[layer] + mo * in_real + c0 + j] = v[j];
+      }
+    }
+    float v[8];
+    umma::tmem_ld8(tw + col + bias_col, v);
+    umma::tmem_ld_wait();
+    if (low) part[lo.b[layer] + mo] = v[0];
+  };
+  // dW accumulators: TMEM row = input unit, columns = outputs (their biases come from registers)
+  auto flush_N = [&](uint32_t col, int in_real, int out_real, int out_pad, int layer) {
+    for (int c0 = 0; c0 < out_pad; c0 += 8) {
+      float v[8];
+      umma::tmem_ld8(tw + col + c0, v);
+      umma::tmem_ld_wait();
+      if (low) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < out_real && mo < in_real) part[lo.w[layer] + (c0 + j) * in_real + mo] = v[j];
+      }
+    }
+  };
+  umma::tc_fence_after();
+  if (worker && g == 0) { flush_T(C_G0, a.obs_dim, 8, 8, tc::L_ENC0); flush_N(C_G2, 64, 16, 16, tc::L_ENC2); }
+  if (worker && g == 1) flush_T(C_G1, 64, 64, 64, tc::L_ENC1);
+  if (worker && g == 2) { flush_T(C_GV1, 64, 64, 64, tc::L_V1); flush_T(C_GV0, 16, 16, 16, tc::L_V0); }
+  if (worker && g == 3) { flush_T(C_GA0, 16, 16, 16, tc::L_A0); flush_N(C_GA1, 64, 16, 16, tc::L_A1); }
+
+  // ------------------------------------------------------------------ register-held gradients (fixed order)
+  __syncthreads();  // every GEMM is done and waited for: the activation buffers are free
+  {
+    float* sh = reinterpret_cast<float*>(smem + OFF_XH1);
+    float* s_wv2 = sh;                 // [4 quadrants][64 columns]
+    float* s_bv2 = s_wv2 + 256;        // [4 quadrants]
+    float* s_e2 = s_bv2 + 4;           // [4 quadrants][16 columns]
+    float* s_mw = s_e2 + 64;           // [4 quadrants][NO][16]
+    float* s_mb = s_mw + 4 * LRX_MAX_NOUT * 16;  // [4 quadrants][NO]
+    if (worker) {
+      if ((lane & 1) == 0) s_wv2[q * 64 + cg + (lane >> 1)] = gw_v2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = warp_sum(bs_e2[j]);
+        if (lane == 0) s_e2[q * 16 + 4 * g + j] = x;
+      }
+      if (g0) {
+        const float x = warp_sum(gb_v2);
+        if (lane == 0) s_bv2[q] = x;
+#pragma unroll
+        for (int o2 = 0; o2 < NO; ++o2) {
+          if (o2 < n_out) {
+            if ((lane & 1) == 0) s_mw[(q * LRX_MAX_NOUT + o2) * 16 + (lane >> 1)] = gm_w[o2];
+            if (lane == 0) s_mb[q * LRX_MAX_NOUT + o2] = gm_b[o2];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    auto sum4 = [](const float* p, int stride) { return ((p[0] + p[stride]) + p[2 * stride]) + p[3 * stride]; };
+    if (tid < 64) part[lo.w[tc::L_V2] + tid] = sum4(s_wv2 + tid, 64);
+    if (tid == 64) part[lo.b[tc::L_V2]] = sum4(s_bv2, 1);
+    if (tid >= 96 && tid < 112) part[lo.b[tc::L_ENC2] + tid - 96] = sum4(s_e2 + tid - 96, 16);
+    if (tid >= 128 && tid < 128 + 16 * LRX_MAX_NOUT) {
+      const int o2 = (tid - 128) >> 4, i2 = (tid - 128) & 15;
+      if (o2 < n_out) part[lo.w[tc::L_MAP] + o2 * 16 + i2] = sum4(s_mw + o2 * 16 + i2, LRX_MAX_NOUT * 16);
+    }
+    if (tid >= 256 && tid < 256 + LRX_MAX_NOUT && tid - 256 < n_out)
+      part[lo.b[tc::L_MAP] + tid - 256] = sum4(s_mb + tid - 256, LRX_MAX_NOUT);
+    if (tid >= 288 && tid < 304) {  // db_a1 = W_map^T db_map (the layers are linear in between)
+      const int i2 = tid - 288;
+      float sacc = 0.f;
+      for (int o2 = 0; o2 < n_out; ++o2) sacc = fmaf(sum4(s_mb + o2, LRX_MAX_NOUT), fp[tc::F_WMAP + o2 * 16 + i2], sacc);
+      part[lo.b[tc::L_A1] + i2] = sacc;
+    }
+  }
+
+  // ------------------------------------------------------------------ loss statistics (fixed order)
+  __syncthreads();
+  double* shd = reinterpret_cast<double*>(smem + OFF_DY64);  // [6][4 warps]
+  double v6[6] = {(double)s_kl, (double)s_pol, (double)s_val, (double)s_ent, (double)s_dls, (double)s_bad};
+  if (g0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      v6[k] = warp_sum(v6[k]);
+      if (lane == 0) shd[k * 4 + q] = v6[k];
+    }
+  }
+  __syncthreads();
+  if (tid < 6) {
+    double s = 0;
+    for (int w = 0; w < 4; ++w) s += shd[tid * 4 + w];
+    a.loss_partial[(size_t)blockIdx.x * 8 + tid] = s;
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tb, TMEM_COLS);
+}
+
+struct FusedWorkspace {
+  float* partial;        // [LRX_MAX_SMS][P_pad]
+  double* loss_partial;  // [LRX_MAX_SMS][8]
+  size_t P_pad, total;
+};
+size_t align_up_(size_t x, size_t al) { return (x + al - 1) / al * al; }
+FusedWorkspace carve_fused(const LrxPolicyDesc& pol, void* base) {
+  FusedWorkspace w{};
+  w.P_pad = align_up_((size_t)pol.n_params + LRX_PPO_NSTATS, 32);
+  char* b = (char*)base;
+  size_t off = 0;
+  w.partial = (float*)(b ? b + off : nullptr);
+  off += align_up_((size_t)LRX_MAX_SMS * w.P_pad * 4, 256);
+  w.loss_partial = (double*)(b ? b + off : nullptr);
+  off += align_up_((size_t)LRX_MAX_SMS * 8 * sizeof(double), 256);
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+// defined in lrx_update.cu
+struct LrxApplyArgs;
+void lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
+                                int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
+                                const LrxApplyArgs* apply, cudaStream_t s);
+
+// Same workspace layout as the first-generation kernel (lrx_fused_workspace_bytes covers both).
+int lrx_ppo_grad_tc128(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,
+                       int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, float* gradbuf,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled,
+                       const LrxApplyArgs* apply) {
+  *handled = false;
+  if (!tc::is_default_policy(*pol) || lrx_fused_enabled() < 2) return LRX_OK;
+  FusedWorkspace w = carve_fused(*pol, workspace);
+  LRX_REQUIRE(workspace_bytes >= w.total, LRX_ERR_INVALID_ARG, "lrx_ppo_grad: workspace too small for the fused path");
+  Tc128Args a{};
+  a.params = params;
+  a.buf = *buf;
+  a.idx = idx;
+  a.B = B;
+  a.B_global = (double)B_global;
+  a.adv_sums = adv_sums;
+  a.h = *h;
+  a.partial = w.partial;
+  a.partial_stride = (long long)w.P_pad;
+  a.loss_partial = w.loss_partial;
+  a.n_tiles = (int)((B + ROWS - 1) / ROWS);
+  a.obs_dim = pol->obs_dim;
+  a.n_out = pol->n_out;
+  a.is_box = pol->is_box;
+  a.lo = tc::layer_offsets(*pol);
+  const int sms = lrx_sm_count();
+  const int grid = a.n_tiles < sms ? a.n_tiles : sms;
+  static bool set0[64], set1[64], set2[64], set3[64];
+  LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_tc128_kernel<0>, (int)SMEM_BYTES, set0));
+  LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_tc128_kernel<1>, (int)SMEM_BYTES, set1));
+  LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_tc128_kernel<2>, (int)SMEM_BYTES, set2));
+  LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_tc128_kernel<3>, (int)SMEM_BYTES, set3));
+  switch (pol->n_out) {
+    case 1: ppo_grad_tc128_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
+    case 2: ppo_grad_tc128_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
+    case 3: ppo_grad_tc128_kernel<3><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
+    default: ppo_grad_tc128_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
+  }
+  LRX_LAUNCH_CHECK();
+  lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid, a.lo.log_std,
+                             h->entropy_loss_coefficient, (double)B_global, gradbuf, apply, stream);
+  LRX_LAUNCH_CHECK();
+  *handled = true;
+  return LRX_OK;
+}

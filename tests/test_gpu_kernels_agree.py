@@ -19,8 +19,8 @@ KINDS = ["cartpole", "pendulum", "acrobot", "mountain_car", "continuous_mountain
 def fused_toggle():
     from lerax_b200 import _lib as L
 
-    yield L.debug_lib().lrx_debug_set_fused
-    L.debug_lib().lrx_debug_set_fused(1)
+    yield L.debug_lib().lrx_debug_set_fused  # 2: newest tensor-core kernels, 1: first-generation update kernel, 0: generic
+    L.debug_lib().lrx_debug_set_fused(2)
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -30,7 +30,7 @@ def test_rollout_tensor_core_vs_generic(kind, mes, fused_toggle):
     oenv, spec, params, env, pol, rng, y0 = setup(kind, N=N, mes=mes)
     na, ru = noise_for(spec, rng, T, N, oenv.state_dim)
     t0, sc0 = np.zeros(N, np.float32), np.zeros(N, np.int32)
-    fused_toggle(1)
+    fused_toggle(2)
     a = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, na, ru)
     fused_toggle(0)
     b = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, na, ru)
@@ -47,13 +47,14 @@ def test_rollout_tensor_core_vs_generic(kind, mes, fused_toggle):
         H.assert_close(a[name], b[name], 1e-4, drift, name)
 
 
+@pytest.mark.parametrize("level", [2, 1])
 @pytest.mark.parametrize("kind", KINDS)
-def test_gradient_tensor_core_vs_generic(kind, fused_toggle):
-    T, N, B = 40, 33, 1000  # 15 full 64-row tiles + a ragged one
+def test_gradient_tensor_core_vs_generic(kind, level, fused_toggle):
+    T, N, B = 40, 33, 1000  # 7 full 128-row tiles (15 of 64 rows for the first-generation kernel) + a ragged one
     spec, params, pol, rng, flat, buf = synthetic_buffer(kind, T, N, seed=21)
     hp = OU.Hyper(clip_value_loss=True, entropy_loss_coefficient=0.01)
     idx = rng.permutation(T * N)[:B].astype(np.int32)
-    fused_toggle(1)
+    fused_toggle(level)
     ga, _ = H.run_grad(pol, buf, idx, hp)
     ga2, _ = H.run_grad(pol, buf, idx, hp)
     np.testing.assert_array_equal(ga, ga2)  # deterministic (fixed-order reductions)
@@ -106,16 +107,18 @@ def test_full_size_properties():
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("level", [2, 1])
 @pytest.mark.parametrize("kind", ["cartpole", "pendulum", "mountain_car"])
-def test_gradient_many_tiles_per_cta_vs_generic(kind, fused_toggle):
-    """Every CTA of the fused kernel walks two or three tiles (row staging double buffer, buffer reuse across tiles,
-    a ragged last tile); the generic layer-by-layer kernels are the independent implementation."""
-    T, N = 64, 400
-    B = 64 * 148 * 2 + 37
+def test_gradient_many_tiles_per_cta_vs_generic(kind, level, fused_toggle):
+    """Every CTA of the fused kernel walks two or three tiles (row staging reuse, buffer reuse across tiles, a ragged
+    last tile); the generic layer-by-layer kernels are the independent implementation."""
+    rows = 128 if level == 2 else 64
+    T, N = 64, 400 * rows // 64
+    B = rows * 148 * 2 + 37
     spec, params, pol, rng, flat, buf = synthetic_buffer(kind, T, N, seed=5)
     hp = OU.Hyper(clip_value_loss=True, entropy_loss_coefficient=0.01)
     idx = rng.permutation(T * N)[:B].astype(np.int32)
-    fused_toggle(1)
+    fused_toggle(level)
     ga, _ = H.run_grad(pol, buf, idx, hp)
     ga2, _ = H.run_grad(pol, buf, idx, hp)
     np.testing.assert_array_equal(ga, ga2)

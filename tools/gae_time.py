@@ -12,7 +12,11 @@ from lerax_b200 import _lib as L
 
 dbg = L.debug_lib()
 shapes = [(128, 65536), (512, 65536), (128, 1 << 20), (128, 16384), (128, 4096)]
-knobs = [0] + [e * 10000 + l * 100 + c for e in (1, 2, 4) for l in (2, 4, 8) for c in (4, 8, 16) if not (e == 4 and l == 8)]
+# (MINB, EPL, L) instantiations of lrx_gae.cu x warps per block
+shapes_k = [(4, 2, 4), (5, 2, 4), (3, 2, 4), (2, 2, 4), (6, 2, 2), (3, 2, 2), (3, 2, 8), (1, 2, 8), (6, 1, 4), (2, 1, 4), (8, 1, 2),
+            (4, 1, 8), (3, 4, 4), (2, 4, 4), (4, 4, 2), (2, 4, 2)]
+knobs = [0] + [m * 1000000 + e * 10000 + l * 100 + c for (m, e, l) in shapes_k for c in (4, 8, 16)
+               if c * 32 <= (512 if (m, e, l) in ((2, 2, 4), (3, 2, 2), (1, 2, 8), (2, 1, 4), (2, 4, 2)) else 256)]
 if len(sys.argv) > 1:
     knobs = [int(x) for x in sys.argv[1].split(",")]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
@@ -43,6 +47,6 @@ for T, N in shapes:
         gbs = T * N * 17 / cold / 1e6
         if best is None or gbs > best[1]:
             best = (knob, gbs)
-        print(f"T={T} N={N} knob={knob:6d}: cold {cold*1000:7.1f} us {gbs:6.0f} GB/s ({gbs/6553:.2f})   back-to-back {warm*1000:7.1f} us {T*N*17/warm/1e6:6.0f} GB/s", flush=True)
+        print(f"T={T} N={N} knob={knob:8d}: cold {cold*1000:7.1f} us {gbs:6.0f} GB/s ({gbs/6553:.2f})   back-to-back {warm*1000:7.1f} us {T*N*17/warm/1e6:6.0f} GB/s", flush=True)
     print(f"== T={T} N={N}: best knob {best[0]} {best[1]:.0f} GB/s")
 dbg.lrx_debug_set_gae_chunk(0)
