@@ -24,6 +24,9 @@ void lrx_debug_set_fused(int level);
 /* GAE launch shape for lrx_gae(LRX_LAYOUT_TN): knob = EPL * 10000 + L * 100 + C (envs per lane, steps per thread,
  * warps per block); 0 = automatic.  tools/gae_time.py sweeps it. */
 void lrx_debug_set_gae_chunk(int knob);
+/* Cycle profile of ppo_grad_tc128_kernel: with a device buffer of 64 int64 set, CTA 0 accumulates the cycles between
+ * consecutive step marks of row-owner thread 0 (slots 1..16) and of the issuer warp (slots 33..48); NULL switches it off. */
+void lrx_debug_set_tc128_prof(long long* device_buffer_64);
 /* device-to-device copy of n floats to a raw device address (an exchange slot of lrx_p2p_*). */
 int lrx_debug_copy_f32(float* dst, const float* src, int32_t n, lrx_stream_t stream);
 

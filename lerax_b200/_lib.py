@@ -21,6 +21,7 @@ LRX_MAX_NOUT = 8
 LRX_LAYOUT_TN, LRX_LAYOUT_NT = 0, 1
 LRX_P2P_HANDLE_BYTES = 64
 LRX_PPO_NSTATS = 8
+LRX_PACKED_FLOATS = 16
 LRX_GAE_EV_BLOCKS = 2048
 LRX_GAE_EV_DOUBLES = 4 + 4 * LRX_GAE_EV_BLOCKS + 4
 
@@ -70,7 +71,7 @@ class LrxEpisodeStats(C.Structure):
 
 class LrxBatchView(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("act", C.c_void_p), ("logp", C.c_void_p), ("val", C.c_void_p),
-                ("ret", C.c_void_p), ("adv", C.c_void_p), ("N", C.c_int32), ("T", C.c_int32)]
+                ("ret", C.c_void_p), ("adv", C.c_void_p), ("N", C.c_int32), ("T", C.c_int32), ("packed", C.c_void_p)]
 
 
 _P = C.POINTER
@@ -101,6 +102,7 @@ PROTOTYPES = {
                                     _P(LrxPpoHyper), _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "lrx_episode_stats": (C.c_int, [_vp, _vp, _P(LrxEpisodeStats), C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp]),
     "lrx_ppo_workspace_bytes": (C.c_size_t, [_P(LrxPolicyDesc), C.c_int64]),
+    "lrx_ppo_pack_rows": (C.c_int, [_P(LrxBatchView), C.c_int32, C.c_int32, _vp, _vp]),
     "lrx_ppo_adv_sums": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int64, _vp, _vp]),
     "lrx_ppo_grad": (C.c_int, [_P(LrxPolicyDesc), _vp, _P(LrxBatchView), _vp, C.c_int64, C.c_int64, _vp,
                                _P(LrxPpoHyper), _vp, _vp, C.c_size_t, _vp]),
@@ -118,6 +120,7 @@ DEBUG_HOOKS = {
     "lrx_debug_set_fused": (None, [C.c_int]),
     "lrx_debug_copy_f32": (C.c_int, [_vp, _vp, C.c_int32, _vp]),
     "lrx_debug_set_gae_chunk": (None, [C.c_int]),
+    "lrx_debug_set_tc128_prof": (None, [_vp]),
 }
 # ... and the tensor-core self-tests of the separate liblerax_b200_test.so
 DEBUG_TESTS = {

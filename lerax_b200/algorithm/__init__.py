@@ -185,6 +185,8 @@ class PPO(AbstractAlgorithm):
             workspace=torch.empty((ws_bytes,), dtype=torch.uint8, device=device),
             gradbuf=torch.zeros((policy.n_params + L.LRX_PPO_NSTATS,), **f32),
             adv_sums=torch.zeros((self.minibatches_per_epoch, 2), dtype=torch.float64, device=device),
+            # row-major copy of the buffer for the minibatch gather of the tensor-core update kernel (default widths)
+            packed=(torch.empty((T * N, L.LRX_PACKED_FLOATS), **f32) if (d <= 8 and policy.is_default_widths()) else None),
         )
         return self._bufs
 
@@ -240,7 +242,7 @@ class PPO(AbstractAlgorithm):
         b = self._bufs
         assert b is not None, "collect_rollout must run before train"
         pol_d = policy.desc()
-        view = buffer.view()
+        view = buffer.view(packed=b.get("packed"))
         B_global = self.batch_size
         B_local = B_global // world
         if B_local * world != B_global:

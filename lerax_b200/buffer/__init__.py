@@ -90,9 +90,18 @@ class RolloutBuffer(AbstractBuffer):
         out.states, out.action_masks = self.states, self.action_masks
         return out
 
-    def view(self) -> L.LrxBatchView:
-        return L.LrxBatchView(L.ptr(self._obs), L.ptr(self._act), L.ptr(self._logp), L.ptr(self._val),
-                              L.ptr(self._ret), L.ptr(self._adv), self.num_envs, self.num_steps)
+    def view(self, packed=None) -> L.LrxBatchView:
+        """`packed`: optional [N*T, LRX_PACKED_FLOATS] float32 workspace; when given, the row-major copy of the buffer
+        (lrx_ppo_pack_rows: one 64-byte record per row in reference order) is written and the view carries it, so the
+        update's minibatch gather touches one line per row."""
+        v = L.LrxBatchView(L.ptr(self._obs), L.ptr(self._act), L.ptr(self._logp), L.ptr(self._val),
+                           L.ptr(self._ret), L.ptr(self._adv), self.num_envs, self.num_steps, None)
+        if packed is not None:
+            d = int(self._obs.shape[-1])
+            L.check(L.lib.lrx_ppo_pack_rows(v, d, int(self._act.dtype.is_floating_point), L.ptr(packed), L.stream_ptr()),
+                    "lrx_ppo_pack_rows")
+            v.packed = L.ptr(packed)
+        return v
 
     def batch_indices(self, batch_size: int, *, key=None):
         """base_buffer.py:64-88: permutation of N*T trimmed to a multiple of batch_size,

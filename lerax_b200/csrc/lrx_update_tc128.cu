@@ -48,14 +48,16 @@ constexpr uint32_t OFF_XF = OFF_XH2 + 16 * CG;       // [128][16 | ones]: hi 3, 
 constexpr uint32_t OFF_XB1 = OFF_XF + 5 * CG;        // [128][64 | ones]: head layer-1 activations (value, then action)
 constexpr uint32_t OFF_DY64 = OFF_XB1 + 17 * CG;     // [128][64]: current upstream gradient
 constexpr uint32_t OFF_DY16 = OFF_DY64 + 16 * CG;    // [128][16]
-// fp32 staging (no MMA operand): gathered row data of the NEXT tile (cp.async destinations; single-buffered, the gather
-// is issued after the tile's last read of them): observations [128][8], five 32-bit planes [5][128] -- return, old
-// value, action bits, old log-prob, advantage --, valid flags [128] u8.
+// fp32 staging (no MMA operand): gathered row data (cp.async destinations).  Observations [128][8]: single-buffered (a
+// tile reads them only at its top, the gather of the next tile is issued later).  Five 32-bit planes [5][128] -- return,
+// old value, action bits, old log-prob, advantage -- and the valid flags [128] u8: double-buffered, because the gather
+// is issued under the policy loss, which still reads the current tile's.
 constexpr int R_RET = 0, R_VAL = 1, R_ACT = 2, R_LOGP = 3, R_ADV = 4, R_PLANES = 5;
 constexpr uint32_t OFF_OBS32 = OFF_DY16 + 4 * CG;
 constexpr uint32_t OFF_PLANES = OFF_OBS32 + ROWS * 8 * 4;
-constexpr uint32_t OFF_VALID = OFF_PLANES + R_PLANES * ROWS * 4;
-constexpr uint32_t OFF_F32 = OFF_VALID + ROWS;                    // fp32 biases etc. (tc::F_COUNT floats)
+constexpr uint32_t PLANES_BYTES = R_PLANES * ROWS * 4;
+constexpr uint32_t OFF_VALID = OFF_PLANES + 2 * PLANES_BYTES;
+constexpr uint32_t OFF_F32 = OFF_VALID + 2 * ROWS;                    // fp32 biases etc. (tc::F_COUNT floats)
 constexpr uint32_t OFF_VPART = OFF_F32 + tc::F_RESERVE * 4;       // [4 column groups][128 rows] partial value dot products
 constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ROWS * 4;           // 3 mbarriers, TMEM slot
 constexpr uint32_t OFF_IDX = OFF_MISC + 64;                       // minibatch indices of the tile after the one being gathered
@@ -91,6 +93,7 @@ struct Tc128Args {
   int n_tiles;
   int obs_dim, n_out, is_box;
   tc::LayerOffsets lo;
+  long long* prof;  // test hook (lrx_debug_set_tc128_prof): per-step cycle totals of CTA 0, thread 0 and the issuer
 };
 
 __device__ __forceinline__ void tie_weights_f(float a, float b, float& wa, float& wb) {
@@ -140,8 +143,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
   uint64_t* barL = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 24);  // every epilogue warp has done its TMEM loads
   int* idx_s = reinterpret_cast<int*>(smem + OFF_IDX);
   float* obs_s = reinterpret_cast<float*>(smem + OFF_OBS32);
+  // current (read by this tile) and next (being gathered) staging buffers; swapped at the end of a tile
   float* rows_s = reinterpret_cast<float*>(smem + OFF_PLANES);
+  float* rows_n = rows_s + PLANES_BYTES / 4;
   uint8_t* valid_s = smem + OFF_VALID;
+  uint8_t* valid_n = valid_s + ROWS;
 
   const tc2::Mat W1{smem + OFF_W1, 64, 8192}, W2{smem + OFF_W2, 16, 2048};
   const tc2::Mat WV0{smem + OFF_WV0, 64, 2048}, WV1{smem + OFF_WV1, 64, 8192};
@@ -188,6 +194,19 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
     umma::tmem_st_wait();
   }
 
+  // profiling marks (only with the debug hook set): slot k accumulates the cycles between mark k-1 and mark k of row-owner
+  // thread 0 (slots 0..31) and of the issuer's lane 0 (slots 32..63)
+  long long prof_last = 0;
+  int prof_step = 1;
+  const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && (tid == 0 || tid == WORKERS);
+  auto mark = [&](int k) {
+    if (prof_on) {
+      const long long t = clock64();
+      if (k > 0) a.prof[(tid == 0 ? 0 : 32) + k] += t - prof_last;
+      prof_last = t;
+    }
+  };
+
   // One step = the epilogue warps publish their shared-memory operands, the issuer warp enqueues the step's CRITICAL
   // GEMM(s) (the result the next epilogue consumes) and commits barA, then the BACKGROUND GEMMs (weight gradients
   // accumulating in TMEM) and commits barB where something must know that they are done.  See lrx_update_fused.cu for
@@ -225,7 +244,13 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
       umma::fence_async_smem();
     }
     umma::tc_fence_before();
+    long long tbar = 0;
+    if (prof_on) tbar = clock64();
     __syncthreads();
+    if (prof_on) {  // slots 17..31 (thread 0) / 49..63 (issuer): cycles spent waiting at the barrier of step 1, 2, ..
+      a.prof[(tid == 0 ? 16 : 48) + prof_step] += clock64() - tbar;
+      ++prof_step;
+    }
     if (!worker) {
       umma::tc_fence_after();
       const bool leader = umma::elect_one();
@@ -249,7 +274,6 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
   auto step = [&](auto&& crit, auto&& bg) { step_impl(crit, bg, false); };
   auto step_track = [&](auto&& crit, auto&& bg) { step_impl(crit, bg, true); };
   auto none = [](bool) {};
-
   const LrxPpoHyper h = a.h;
   const float invB = (float)(1.0 / a.B_global);
   float adv_mean = 0.f, adv_den = 1.f;
@@ -335,8 +359,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
     tc2::store4(dst, 4 * g, m, v);
   };
 
-  // ---- row gather (buffer/base_buffer.py:90-103): cp.async straight into shared staging, one lane of column group 2
-  // per row, one tile ahead; the minibatch index two tiles ahead.  No register is the destination of a global load in
+  // ---- row gather (buffer/base_buffer.py:90-103): cp.async straight into shared staging, one tile ahead; the
+  // minibatch index two tiles ahead.  No register is the destination of a global load in
   // the tile loop (lrx_update_fused.cu: such a load cost 9 %).
   auto cp_async4 = [](void* dst, const void* src, bool ok) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(umma::smem_u32(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
@@ -344,51 +368,77 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
   auto cp_async16 = [](void* dst, const void* src, bool ok) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(umma::smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
   };
-  auto tile_row_ok = [&](int t) { return t < a.n_tiles && (long long)t * ROWS + m < a.B; };
-  auto gather_rows = [&](int i, bool ok) {  // buffer row i (zeros when !ok) -> this lane's staging slot m
+  auto tile_row_ok = [&](int t, int r) { return t < a.n_tiles && (long long)t * ROWS + r < a.B; };
+  auto gather_row = [&](int r, int i, bool ok) {  // buffer row i (zeros when !ok) -> staging slot r
+    if (a.buf.packed != nullptr) {
+      // row-major record (lrx_ppo_pack_rows): one 64-byte line per row instead of one sector per plane
+      const float* rec = a.buf.packed + (ok ? (size_t)i * LRX_PACKED_FLOATS : 0);
+      cp_async16(obs_s + r * 8, rec, ok);
+      cp_async16(obs_s + r * 8 + 4, rec + 4, ok);
+      cp_async4(rows_n + R_ACT * ROWS + r, rec + 8, ok);
+      cp_async4(rows_n + R_LOGP * ROWS + r, rec + 9, ok);
+      cp_async4(rows_n + R_VAL * ROWS + r, rec + 10, ok && h.clip_value_loss);
+      cp_async4(rows_n + R_RET * ROWS + r, rec + 11, ok);
+      cp_async4(rows_n + R_ADV * ROWS + r, rec + 12, ok);  // raw; normalised where it is used
+      valid_n[r] = ok ? 1 : 0;
+      return;
+    }
     const int n = i / a.buf.T, t = i - n * a.buf.T;
     const size_t src = ok ? (size_t)t * a.buf.N + n : 0;
-    cp_async4(rows_s + R_RET * ROWS + m, a.buf.ret + src, ok);
-    cp_async4(rows_s + R_VAL * ROWS + m, (h.clip_value_loss ? a.buf.val : a.buf.ret) + src, ok && h.clip_value_loss);
-    cp_async4(rows_s + R_ACT * ROWS + m, (const int32_t*)a.buf.act + src, ok);
-    cp_async4(rows_s + R_LOGP * ROWS + m, a.buf.logp + src, ok);
-    cp_async4(rows_s + R_ADV * ROWS + m, a.buf.adv + src, ok);  // raw; normalised where it is used
+    cp_async4(rows_n + R_RET * ROWS + r, a.buf.ret + src, ok);
+    cp_async4(rows_n + R_VAL * ROWS + r, (h.clip_value_loss ? a.buf.val : a.buf.ret) + src, ok && h.clip_value_loss);
+    cp_async4(rows_n + R_ACT * ROWS + r, (const int32_t*)a.buf.act + src, ok);
+    cp_async4(rows_n + R_LOGP * ROWS + r, a.buf.logp + src, ok);
+    cp_async4(rows_n + R_ADV * ROWS + r, a.buf.adv + src, ok);  // raw; normalised where it is used
     const float* op = a.buf.obs + src * a.obs_dim;
     if (a.obs_dim == 4) {  // one 16-byte copy (CartPole)
-      cp_async16(obs_s + m * 8, op, ok);
-      *reinterpret_cast<float4*>(obs_s + m * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      cp_async16(obs_s + r * 8, op, ok);
+      *reinterpret_cast<float4*>(obs_s + r * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) cp_async4(obs_s + m * 8 + k, op + (k < a.obs_dim ? k : 0), ok && k < a.obs_dim);
+      for (int k = 0; k < 8; ++k) cp_async4(obs_s + r * 8 + k, op + (k < a.obs_dim ? k : 0), ok && k < a.obs_dim);
     }
-    valid_s[m] = ok ? 1 : 0;
+    valid_n[r] = ok ? 1 : 0;
   };
-  auto gather_idx = [&](int t) {  // minibatch indices of tile t -> idx_s
-    const bool ok = tile_row_ok(t);
-    cp_async4(idx_s + m, a.idx + (ok ? (long long)t * ROWS + m : 0), ok);
+  // Column group 2's warps gather, one lane per row, right after the barrier of the policy-loss step, during which
+  // they have nothing else to do: the DRAM latency of the copies runs under the row-owner warps' loss arithmetic.  (The
+  // first fence.proxy.async any warp of the CTA executes after the copies were issued waits for them to land -- its
+  // MEMBAR drains the CTA's outstanding LDGSTS -- so they must be issued early in a long step, not late: measured with
+  // tools/tc128_prof.py, 1.7 k cycles per tile.)
+  auto gather_tile = [&](int t_next, int t_after, bool first) {
+    const bool ok = tile_row_ok(t_next, m);
+    const int i = first ? (ok ? __ldg(a.idx + (long long)t_next * ROWS + m) : 0) : idx_s[m];
+    gather_row(m, i, ok);
+    const bool ok2 = tile_row_ok(t_after, m);  // minibatch index of the tile after: read only by this lane, next time
+    cp_async4(idx_s + m, a.idx + (ok2 ? (long long)t_after * ROWS + m : 0), ok2);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto gather_commit = []() { asm volatile("cp.async.commit_group;" ::: "memory"); };
   auto gather_wait = []() { asm volatile("cp.async.wait_group 0;" ::: "memory"); };
+  auto swap_staging = [&]() {
+    float* t = rows_s; rows_s = rows_n; rows_n = t;
+    uint8_t* u = valid_s; valid_s = valid_n; valid_n = u;
+  };
   const bool gatherer = worker && g == 2;
-  if (gatherer) {  // first tile: the only register load of an index
-    const int t0 = (int)blockIdx.x;
-    const bool ok = tile_row_ok(t0);
-    const int i = ok ? __ldg(a.idx + (long long)t0 * ROWS + m) : 0;
-    gather_rows(i, ok);
-    gather_idx(t0 + (int)gridDim.x);
-    gather_commit();
+  if (gatherer) {  // first tile: the only register loads of indices
+    gather_tile((int)blockIdx.x, (int)blockIdx.x + (int)gridDim.x, true);
     gather_wait();
   }
+  swap_staging();  // what was gathered as "next" is the first tile's "current"
   __syncthreads();
 
   // gradients kept in registers across the tiles of the CTA
   float gw_v2 = 0.f, gb_v2 = 0.f;  // value output layer (64 -> 1): dW of column cg + (lane >> 1) % 16 over this warp's rows; db
-  float gm_w[NO], gm_b[NO];        // action_dist.mapping (16 -> n_out): dW[o][(lane >> 1) % 16], db[o] (row-owner warps)
+  // action_dist.mapping (16 -> n_out): dW[o][4 (lane % 4) + c] over this lane's rows (lane / 4 of every tile's octet), db[o]
+  float gm_w[NO][4], gm_b[NO];
 #pragma unroll
-  for (int o2 = 0; o2 < NO; ++o2) gm_w[o2] = gm_b[o2] = 0.f;
+  for (int o2 = 0; o2 < NO; ++o2) gm_w[o2][0] = gm_w[o2][1] = gm_w[o2][2] = gm_w[o2][3] = gm_b[o2] = 0.f;
 
+  mark(0);
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    mark(14);
+    prof_step = 1;
     const bool valid_m = valid_s[m] != 0;  // this thread's row is a real row of the minibatch
+    mark(0);
 
     // ---------------------------------------------------------------- encoder layer 0 (d <= 8 inputs) on the FMA pipe
     uint32_t mk_h1 = 0, mk_h2 = 0, mk_b1 = 0, mk_b2 = 0;
@@ -418,15 +468,19 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
         tc2::store8(XOBS, 0, m, z8);  // lo piece: c-group 0 only (XOBS.lo_off = 2 c-groups)
       }
     }
+    mark(1);
     step([&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D0, XH1, W1, ROWS, 64, 64, 4, 0u); }, none);
     if (worker) fwd64(C_D0, fp + tc::F_B1, XH2, mk_h2);
+    mark(2);
     step([&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D0, XH2, W2, ROWS, 16, 16, 4, 0u); }, none);
     if (worker) quarter16(C_D0, fp + tc::F_B2, XF, false);
 
+    mark(3);
     // ---------------------------------------------------------------- value head forward
     step([&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D0, XF, WV0, ROWS, 64, 64, 1, 0u); },
          [&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D1, XF, WA0, ROWS, 64, 64, 1, 0u); });  // action head layer 1, consumed later
     if (worker) fwd64(C_D0, fp + tc::F_BV0, XB1, mk_b1);
+    mark(4);
     step([&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D0, XB1, WV1, ROWS, 64, 64, 4, 0u); }, none);
     float xb2[16];  // value layer-2 activations of this thread's row and column group
     if (worker) {
@@ -445,8 +499,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
     }
     __syncthreads();
 
+    mark(5);
     // ---------------------------------------------------------------- value loss (ppo.py:435-451) and its backward
-    bool bad = false;
     if (worker) {
       const float value = (((fp[tc::F_BV2] + vpart[m]) + vpart[ROWS + m]) + vpart[2 * ROWS + m]) + vpart[3 * ROWS + m];
       const float ret_r = rows_s[R_RET * ROWS + m], vold_r = rows_s[R_VAL * ROWS + m];
@@ -471,7 +525,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
         dv = h.value_loss_coefficient * dvl;
       }
       if (g0 && valid_m) {
-        bad = !isfinite(value);
+        if (!isfinite(value)) s_bad += 1.0f;  // ppo.py:413-417 (a row with a non-finite log-prob too counts twice: only > 0 matters)
         s_val += sv;
         gb_v2 += dv;
       }
@@ -491,6 +545,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
       for (int j = 0; j < 16; ++j) v[j] = ((mk_b2 >> j) & 1u) ? v[j] : 0.f;
       store_row16(DY64, v, false);
     }
+    mark(6);
     step_track([&](bool ld) { tc2::gemm<false, true>(ld, tb + C_D0, DY64, WV1, ROWS, 64, 64, 4, 0u); },      // dX = dY W
                [&](bool ld) { tc2::gemm<true, true>(ld, tb + C_GV1, DY64, XB1, 64, 72, 64, 8, 1u); });        // [dW^T | db] += dY^T [X | 1]
     if (worker) {
@@ -498,6 +553,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
       // -------------------------------------------------------------- action head forward
       fwd64(C_D1, fp + tc::F_BA0, XB1, mk_b1);
     }
+    mark(7);
     // background, issued once the action head's output has been loaded from TMEM: d(features) from the value head and
     // the value layer-0 weight gradient run under the policy-loss arithmetic
     step_late([&](bool ld) { tc2::gemm<false, false>(ld, tb + C_D0, XB1, WA1, ROWS, 16, 16, 4, 0u); },
@@ -505,33 +561,58 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
                 tc2::gemm<false, true>(ld, tb + C_DF, DY64, WV0, ROWS, 16, 16, 4, 0u);
                 tc2::gemm<true, true>(ld, tb + C_GV0, DY64, XF, 64, 24, 16, 8, 1u);
               });
-    if (g0) {
-      float a2[16];
-      wait_crit();
-      umma::tmem_ld16(tw + C_D0, a2);
-      umma::tmem_ld_wait();
-      signal_loaded();
+    // the next tile's rows, fetched under the policy loss (the longest step): observations into the single staging
+    // buffer (dead since the tile top), the per-row planes into the buffers this tile does not read
+    if (gatherer) gather_tile(tile + (int)gridDim.x, tile + 2 * (int)gridDim.x, false);
+    if (worker) {
+      // ------------------------------------------------------------ action head output, policy loss and their backward,
+      // on ALL sixteen warps: four lanes per row.  Left to the four row-owner warps (one per scheduler, no latency
+      // hiding) this was the longest step of a tile -- ~800 dependent instructions, 4.5 k cycles (tools/tc128_prof.py).
+      // Warp (q, g) serves rows 32q + 8g .. + 7; lane = 4 * (row % 8) + p holds features 4p .. 4p + 3 of its row.
+      const int p4 = lane & 3, rl = 8 * g + (lane >> 2), rr = 32 * q + rl;
+      float x[4];
+      {
+        float a2[16];
+        wait_crit();
+        umma::tmem_ld16(tw + C_D0, a2);  // lane l: row 32q + l, all 16 features
+        umma::tmem_ld_wait();
+        signal_loaded();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) a2[j] += fp[tc::F_BA1 + j];
-      // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261) on the FMA pipe
-      float head[NO];
+        for (int c = 0; c < 4; ++c) {
+          const float v0 = __shfl_sync(0xffffffffu, a2[c], rl), v1 = __shfl_sync(0xffffffffu, a2[4 + c], rl);
+          const float v2 = __shfl_sync(0xffffffffu, a2[8 + c], rl), v3 = __shfl_sync(0xffffffffu, a2[12 + c], rl);
+          x[c] = p4 == 0 ? v0 : (p4 == 1 ? v1 : (p4 == 2 ? v2 : v3));
+        }
+        const float4 b4 = *reinterpret_cast<const float4*>(fp + tc::F_BA1 + 4 * p4);
+        x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
+      }
+      // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261) on the FMA pipe: partial over this lane's four
+      // features, then the row's four lanes are summed (all four end up with the logits / loc)
+      float head[NO], wm[NO][4];
 #pragma unroll
       for (int o2 = 0; o2 < NO; ++o2) {
-        float sacc = fp[tc::F_BMAP + o2];
+        float sacc = 0.f;
         if (o2 < n_out) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) sacc = fmaf(fp[tc::F_WMAP + o2 * 16 + i], a2[i], sacc);
+          const float4 w4 = *reinterpret_cast<const float4*>(fp + tc::F_WMAP + o2 * 16 + 4 * p4);
+          wm[o2][0] = w4.x; wm[o2][1] = w4.y; wm[o2][2] = w4.z; wm[o2][3] = w4.w;
+          sacc = fmaf(w4.w, x[3], fmaf(w4.z, x[2], fmaf(w4.y, x[1], w4.x * x[0])));
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+          sacc += fp[tc::F_BMAP + o2];
+        } else {
+          wm[o2][0] = wm[o2][1] = wm[o2][2] = wm[o2][3] = 0.f;
         }
         head[o2] = sacc;
       }
 
-      // -------------------------------------------------------------- policy loss (ppo.py:405-434,452-467)
+      // -------------------------------------------------------------- policy loss (ppo.py:405-434,452-467), computed by
+      // the row's four lanes alike; lane p = 0 keeps the statistics
       float dhead[NO];
 #pragma unroll
       for (int o2 = 0; o2 < NO; ++o2) dhead[o2] = 0.f;
-      if (valid_m) {
-        const int act_raw = reinterpret_cast<const int*>(rows_s)[R_ACT * ROWS + m];  // fp32 (Box) or int32 (Discrete) bits
-        const float logp_old = rows_s[R_LOGP * ROWS + m], A = rows_s[R_ADV * ROWS + m];
+      if (valid_s[rr] != 0) {
+        const int act_raw = reinterpret_cast<const int*>(rows_s)[R_ACT * ROWS + rr];  // fp32 (Box) or int32 (Discrete) bits
+        const float logp_old = rows_s[R_LOGP * ROWS + rr], A = rows_s[R_ADV * ROWS + rr];
         float logp, entropy, z_n = 0.f;
         float lp[NO], pr[NO];
         if (a.is_box) {
@@ -554,29 +635,27 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
             }
           }
         }
-        bad = bad || !(isfinite(logp) && isfinite(entropy));  // ppo.py:413-417
-        if (bad) s_bad += 1.0f;
+        const bool bad_p = !(isfinite(logp) && isfinite(entropy));  // ppo.py:413-417
         const float log_ratio = logp - logp_old;
         const float ratio = expf(log_ratio);
-        s_kl += ratio - log_ratio;
         const float c = h.clip_coefficient, lo = 1.f - c, hi = 1.f + c;
         const float An = h.normalize_advantages ? (A - adv_mean) / adv_den : A;  // ppo.py:424-427
-        float dlogp;
+        float dlogp, spol;
         if (h.surrogate == 1) {  // A2C / REINFORCE: -mean(logp * A)   (a2c.py:401, reinforce.py:391)
-          s_pol += logp * An;
+          spol = logp * An;
           dlogp = -invB * An;
         } else {
           const float s1 = An * ratio, s2 = An * lrx_clipf(ratio, lo, hi);
-          s_pol += fminf(s1, s2);
+          spol = fminf(s1, s2);
           float w1, w2;
           tie_weights_f(s1, s2, w1, w2);
           dlogp = -invB * (w1 * An * ratio + w2 * An * clip_grad_f(ratio, lo, hi) * ratio);
         }
-        s_ent += entropy;
         const float ch = h.entropy_loss_coefficient;
+        float sdls = 0.f;
         if (a.is_box) {
           dhead[0] = dlogp * z_n / scale;
-          s_dls += dlogp * (z_n * z_n - 1.0f);
+          sdls = dlogp * (z_n * z_n - 1.0f);
         } else {
 #pragma unroll
           for (int j = 0; j < NO; ++j) {
@@ -586,66 +665,70 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
             }
           }
         }
-      }
-      // -------------------------------------------------------------- action head backward (mapping, FMA)
-      {
-        float d16[16];
+        if (p4 == 0) {
+          if (bad_p) s_bad += 1.0f;
+          s_kl += ratio - log_ratio;
+          s_pol += spol;
+          s_ent += entropy;
+          s_dls += sdls;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+          for (int o2 = 0; o2 < NO; ++o2) gm_b[o2] += dhead[o2];
+        }
+      }
+      // -------------------------------------------------------------- action head backward (mapping, FMA): this lane's
+      // four columns of d(a2), and its share of the mapping layer's weight gradient dW[o][4p + c] += dhead[o] a2[4p + c]
+      {
+        float d4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
           float sacc = 0.f;
 #pragma unroll
-          for (int o2 = 0; o2 < NO; ++o2)
-            if (o2 < n_out) sacc = fmaf(dhead[o2], fp[tc::F_WMAP + o2 * 16 + i], sacc);
-          d16[i] = sacc;
+          for (int o2 = 0; o2 < NO; ++o2) {
+            if (o2 < n_out) {
+              sacc = fmaf(dhead[o2], wm[o2][c], sacc);
+              gm_w[o2][c] = fmaf(dhead[o2], x[c], gm_w[o2][c]);
+            }
+          }
+          d4[c] = sacc;
         }
-        tc2::store8(DY16, 0, m, d16);
-        tc2::store8(DY16, 1, m, d16 + 8);
-      }
-      // mapping layer gradients: dW[o][i] += dhead[r][o] a2[r][i], db[o] += dhead[r][o] over the warp's 32 rows
-#pragma unroll
-      for (int o2 = 0; o2 < NO; ++o2) {
-        if (o2 < n_out) {
-          float t16[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) t16[i] = dhead[o2] * a2[i];
-          gm_w[o2] += reduce_scatter16(t16, lane);
-          gm_b[o2] += warp_sum(dhead[o2]);
-        }
+        tc2::store4(DY16, 4 * p4, rr, d4);
       }
     }
+    mark(8);
     step([&](bool ld) { tc2::gemm<false, true>(ld, tb + C_D0, DY16, WA1, ROWS, 64, 64, 1, 0u); },        // dX = dY16 W_a1 (K = 16 outputs)
          [&](bool ld) { tc2::gemm<true, true>(ld, tb + C_GA1, XB1, DY16, 64, 16, 16, 8, 1u); });           // dW[in][out] += X^T dY
     if (worker) bwd64(C_D0, mk_b1, DY64, false);  // this step's background GEMM does not read DY64
-    // every read of this tile's gathered rows is behind the barrier of the step above: fetch the next tile's
-    if (gatherer) {
-      gather_rows(idx_s[m], tile_row_ok(tile + (int)gridDim.x));
-      gather_idx(tile + 2 * (int)gridDim.x);
-      gather_commit();
-    }
+    mark(9);
     step([&](bool ld) { tc2::gemm<false, true>(ld, tb + C_DF, DY64, WA0, ROWS, 16, 16, 4, 1u); },        // d(features) += action head
          [&](bool ld) { tc2::gemm<true, true>(ld, tb + C_GA0, DY64, XF, 64, 24, 16, 8, 1u); });
 
     // ---------------------------------------------------------------- encoder backward
     if (worker) quarter16(C_DF, nullptr, DY16, true);                    // background reads DY64 / XF only
+    mark(10);
     step([&](bool ld) { tc2::gemm<false, true>(ld, tb + C_D0, DY16, W2, ROWS, 64, 64, 1, 0u); },
          [&](bool ld) { tc2::gemm<true, true>(ld, tb + C_G2, XH2, DY16, 64, 16, 16, 8, 1u); });
     if (worker) bwd64(C_D0, mk_h2, DY64, false);  // background reads XH2 / DY16 only
+    mark(11);
     step([&](bool ld) { tc2::gemm<false, true>(ld, tb + C_D0, DY64, W1, ROWS, 64, 64, 4, 0u); },
          [&](bool ld) { tc2::gemm<true, true>(ld, tb + C_G1, DY64, XH1, 64, 72, 64, 8, 1u); });
     // d(h1) goes into the XH2 buffer, dead since the GEMMs of the step before (ordered before this step's critical
     // GEMM) read it: no wait for this step's weight-gradient GEMM, which still reads DY64 and XH1
     if (worker) bwd64(C_D0, mk_h1, DH1, false);
+    mark(12);
     // the next tile's rows have had three steps to arrive; the barrier of the step below publishes them
     if (gatherer) gather_wait();
     step_track(none, [&](bool ld) {
       tc2::gemm<true, true>(ld, tb + C_G0, DH1, XOBS, 64, 16, 8, 8, 1u);  // [dW^T | db]: obs c-group + the ones c-group
     });  // its commit also covers the GEMM on XH1 of the step before: waited for before XH1 / XH2 / XOBS are rewritten
+    mark(13);
+    swap_staging();
   }
   if (worker) {
     wait_crit();
     wait_bg();
   }
 
+  mark(15);
   // ------------------------------------------------------------------ flush the gradient partial
   float* part = a.partial + (size_t)blockIdx.x * a.partial_stride;
   const tc::LayerOffsets& lo = a.lo;
@@ -694,8 +777,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
     float* s_wv2 = sh;                 // [4 quadrants][64 columns]
     float* s_bv2 = s_wv2 + 256;        // [4 quadrants]
     float* s_e2 = s_bv2 + 4;           // [4 quadrants][16 columns]
-    float* s_mw = s_e2 + 64;           // [4 quadrants][NO][16]
-    float* s_mb = s_mw + 4 * LRX_MAX_NOUT * 16;  // [4 quadrants][NO]
+    float* s_mw = s_e2 + 64;           // [16 warps][NO][16]
+    float* s_mb = s_mw + 16 * LRX_MAX_NOUT * 16;  // [16 warps][NO]
     if (worker) {
       if ((lane & 1) == 0) s_wv2[q * 64 + cg + (lane >> 1)] = gw_v2;
 #pragma unroll
@@ -706,51 +789,66 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
       if (g0) {
         const float x = warp_sum(gb_v2);
         if (lane == 0) s_bv2[q] = x;
+      }
+      // mapping layer: reduce over the warp's eight row slots (lanes with equal lane % 4), one slot per warp
 #pragma unroll
-        for (int o2 = 0; o2 < NO; ++o2) {
-          if (o2 < n_out) {
-            if ((lane & 1) == 0) s_mw[(q * LRX_MAX_NOUT + o2) * 16 + (lane >> 1)] = gm_w[o2];
-            if (lane == 0) s_mb[q * LRX_MAX_NOUT + o2] = gm_b[o2];
+      for (int o2 = 0; o2 < NO; ++o2) {
+        if (o2 < n_out) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float x = gm_w[o2][c];
+            x += __shfl_xor_sync(0xffffffffu, x, 4);
+            x += __shfl_xor_sync(0xffffffffu, x, 8);
+            x += __shfl_xor_sync(0xffffffffu, x, 16);
+            if (lane < 4) s_mw[(warp * LRX_MAX_NOUT + o2) * 16 + 4 * lane + c] = x;
           }
+          const float xb = warp_sum(gm_b[o2]);
+          if (lane == 0) s_mb[warp * LRX_MAX_NOUT + o2] = xb;
         }
       }
     }
     __syncthreads();
     auto sum4 = [](const float* p, int stride) { return ((p[0] + p[stride]) + p[2 * stride]) + p[3 * stride]; };
+    auto sum16 = [](const float* p, int stride) {
+      float t = 0.f;
+      for (int w = 0; w < 16; ++w) t += p[w * stride];  // warp order: fixed
+      return t;
+    };
     if (tid < 64) part[lo.w[tc::L_V2] + tid] = sum4(s_wv2 + tid, 64);
     if (tid == 64) part[lo.b[tc::L_V2]] = sum4(s_bv2, 1);
     if (tid >= 96 && tid < 112) part[lo.b[tc::L_ENC2] + tid - 96] = sum4(s_e2 + tid - 96, 16);
     if (tid >= 128 && tid < 128 + 16 * LRX_MAX_NOUT) {
       const int o2 = (tid - 128) >> 4, i2 = (tid - 128) & 15;
-      if (o2 < n_out) part[lo.w[tc::L_MAP] + o2 * 16 + i2] = sum4(s_mw + o2 * 16 + i2, LRX_MAX_NOUT * 16);
+      if (o2 < n_out) part[lo.w[tc::L_MAP] + o2 * 16 + i2] = sum16(s_mw + o2 * 16 + i2, LRX_MAX_NOUT * 16);
     }
     if (tid >= 256 && tid < 256 + LRX_MAX_NOUT && tid - 256 < n_out)
-      part[lo.b[tc::L_MAP] + tid - 256] = sum4(s_mb + tid - 256, LRX_MAX_NOUT);
+      part[lo.b[tc::L_MAP] + tid - 256] = sum16(s_mb + tid - 256, LRX_MAX_NOUT);
     if (tid >= 288 && tid < 304) {  // db_a1 = W_map^T db_map (the layers are linear in between)
       const int i2 = tid - 288;
       float sacc = 0.f;
-      for (int o2 = 0; o2 < n_out; ++o2) sacc = fmaf(sum4(s_mb + o2, LRX_MAX_NOUT), fp[tc::F_WMAP + o2 * 16 + i2], sacc);
+      for (int o2 = 0; o2 < n_out; ++o2) sacc = fmaf(sum16(s_mb + o2, LRX_MAX_NOUT), fp[tc::F_WMAP + o2 * 16 + i2], sacc);
       part[lo.b[tc::L_A1] + i2] = sacc;
     }
   }
 
   // ------------------------------------------------------------------ loss statistics (fixed order)
   __syncthreads();
-  double* shd = reinterpret_cast<double*>(smem + OFF_DY64);  // [6][4 warps]
+  double* shd = reinterpret_cast<double*>(smem + OFF_DY64);  // [6][16 warps]
   double v6[6] = {(double)s_kl, (double)s_pol, (double)s_val, (double)s_ent, (double)s_dls, (double)s_bad};
-  if (g0) {
+  if (worker) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       v6[k] = warp_sum(v6[k]);
-      if (lane == 0) shd[k * 4 + q] = v6[k];
+      if (lane == 0) shd[k * 16 + warp] = v6[k];
     }
   }
   __syncthreads();
   if (tid < 6) {
     double s = 0;
-    for (int w = 0; w < 4; ++w) s += shd[tid * 4 + w];
+    for (int w = 0; w < 16; ++w) s += shd[tid * 16 + w];
     a.loss_partial[(size_t)blockIdx.x * 8 + tid] = s;
   }
+  mark(16);
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tb, TMEM_COLS);
@@ -783,6 +881,9 @@ void lrx_launch_reduce_partials(const float* partial, int splits, long long stri
                                 int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
                                 const LrxApplyArgs* apply, cudaStream_t s);
 
+static long long* g_tc128_prof = nullptr;  // test hook, include/lerax_b200_debug.h
+extern "C" void lrx_debug_set_tc128_prof(long long* device_buffer_64) { g_tc128_prof = device_buffer_64; }
+
 // Same workspace layout as the first-generation kernel (lrx_fused_workspace_bytes covers both).
 int lrx_ppo_grad_tc128(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,
                        int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, float* gradbuf,
@@ -808,6 +909,7 @@ int lrx_ppo_grad_tc128(const LrxPolicyDesc* pol, const float* params, const LrxB
   a.n_out = pol->n_out;
   a.is_box = pol->is_box;
   a.lo = tc::layer_offsets(*pol);
+  a.prof = g_tc128_prof;
   const int sms = lrx_sm_count();
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;
   static bool set0[64], set1[64], set2[64], set3[64];

@@ -98,6 +98,12 @@ class MLPActorCriticPolicy(AbstractActorCriticPolicy):
                 d.relu[c][i] = r
         return d
 
+    def is_default_widths(self) -> bool:
+        """mlp.py:64-78 defaults (encoder d->64->64->16, value head 16->64->64->1, action head 16->64->16->n_out, d <= 8):
+        the shapes the specialised tensor-core kernels serve."""
+        d, n = self.obs_dim, self.n_out
+        return d <= 8 and tuple(self._dims) == ((d, 64, 64, 16), (16, 64, 64, 1), (16, 64, 16, n))
+
     def with_params(self, params) -> "MLPActorCriticPolicy":
         new = object.__new__(MLPActorCriticPolicy)
         new.__dict__.update(self.__dict__)

@@ -61,7 +61,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(L.LrxRng) == 16
     assert ctypes.sizeof(L.LrxRolloutOut) == 10 * 8
     assert ctypes.sizeof(L.LrxPpoHyper) == 8 * 4 + 3 * 4
-    assert ctypes.sizeof(L.LrxBatchView) == 6 * 8 + 8
+    assert ctypes.sizeof(L.LrxBatchView) == 6 * 8 + 8 + 8
 
 
 def test_argument_validation_without_gpu():

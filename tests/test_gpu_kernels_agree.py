@@ -147,3 +147,29 @@ def test_permutation_is_a_bijection(n):
         # no structure a minibatch would notice: first-quarter mean index close to n/2
         q = out[: n // 4].double().mean().item()
         assert abs(q - (n - 1) / 2) < 0.05 * n
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "acrobot", "pendulum"])
+def test_packed_rows_gather_equals_plane_gather(kind):
+    """LrxBatchView.packed (lrx_ppo_pack_rows: one 64-byte record per row, reference order) vs the gather from the
+    [T][N] planes: same rows, same arithmetic -> bit-identical gradients."""
+    import torch
+
+    from lerax_b200 import _lib as L
+
+    T, N, B = 48, 50, 2000
+    spec, params, pol, rng, flat, buf = synthetic_buffer(kind, T, N, seed=17)
+    # the record of row i = n*T + t holds exactly the planes' values at (t, n)
+    rec = buf.packed.cpu().numpy().reshape(N, T, L.LRX_PACKED_FLOATS)
+    np.testing.assert_array_equal(rec[:, :, :spec.obs_dim], np.swapaxes(buf.t["obs"].cpu().numpy(), 0, 1))
+    np.testing.assert_array_equal(rec[:, :, spec.obs_dim:8], 0)
+    for k, name in ((9, "logp"), (10, "val"), (11, "ret"), (12, "adv")):
+        np.testing.assert_array_equal(rec[:, :, k], buf.t[name].cpu().numpy().T)
+    np.testing.assert_array_equal(rec[:, :, 8].view(np.int32), buf.t["act"].cpu().numpy().T.view(np.int32))
+    hp = OU.Hyper(clip_value_loss=True, entropy_loss_coefficient=0.01)
+    idx = rng.permutation(T * N)[:B].astype(np.int32)
+    ga, _ = H.run_grad(pol, buf, idx, hp)
+    buf.view.packed = None
+    gb, _ = H.run_grad(pol, buf, idx, hp)
+    np.testing.assert_array_equal(ga, gb)
+    torch.cuda.synchronize()

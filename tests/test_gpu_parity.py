@@ -299,7 +299,8 @@ def test_one_ppo_update_matches_oracle(kind):
     p1, st, log = OU.train(spec, params.copy(), OU.AdamState.init(params), flat, idx, hp)
     gp, gm, gv, cnt, stats, flag = H.run_update(pol, buf, idx, hp)
     assert cnt == nb and flag == 0
-    H.assert_close(gp, p1, 1e-4, 1e-6, "params after one epoch")
+    tol, tight = H.adam_conditioned_tolerance(spec, params, flat, idx, hp)
+    H.assert_params_close(gp, p1, tol, tight, "params after one epoch")
     H.assert_close(gm, st.m, 1e-3, 1e-7, "adam mu")
     H.assert_close(gv, st.v, 1e-3, 1e-10, "adam nu")
     s = stats[0].mean(axis=0)
@@ -341,6 +342,7 @@ def test_nonfinite_flag_and_skip():
     import torch
 
     buf.t["obs"][0, 0, 0] = float("inf")
+    buf.pack()  # the row-major copy follows the planes
     idx = np.arange(T * N, dtype=np.int32).reshape(1, 1, -1)
     gp, gm, gv, cnt, stats, flag = H.run_update(pol, buf, idx, OU.Hyper())
     assert flag == 1 and cnt == 0

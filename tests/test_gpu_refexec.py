@@ -117,11 +117,10 @@ def test_ppo_train(case, h):
     hp = case.hyper(h, learning_rate=1e-3)
     gp, gm, gv, cnt, stats, flag = H.run_update(pol, H.DeviceBuffer(**case.planes()), case.train_idx(), hp)
     assert flag == 0 and cnt == int(fx[f"train_count_{h}"])
-    # six Adam steps of 1e-3: a parameter whose gradient is round-off sized moves by a sign-dependent fraction of a step,
-    # so the bar is 1e-4 relative + 5 % of ONE step, and all but a handful of parameters meet the tight 1e-5
-    want = fx[f"train_params_{h}"]
-    H.assert_close(gp, want, 1e-4, 5e-5, "parameters after PPO.train")
-    assert (np.abs(gp - want) > 1e-5 + 1e-4 * np.abs(want)).mean() < 1e-3
+    # north_star's 1e-4 on parameters, plus -- for the handful of parameters whose gradient is cancellation noise -- what
+    # the gradient bar allows through Adam's normalised step (helpers.adam_conditioned_tolerance)
+    tol, tight = H.adam_conditioned_tolerance(case.spec, case.params, case.flat(), case.train_idx(), hp, atol=1e-5)
+    H.assert_params_close(gp, fx[f"train_params_{h}"], tol, tight, "parameters after PPO.train")
     if h == 0:
         H.assert_close(gm, fx["train_mu_0"], 1e-3, 1e-5 * np.abs(fx["train_mu_0"]).max(), "adam mu")
         H.assert_close(gv, fx["train_nu_0"], 2e-3, 1e-5 * np.abs(fx["train_nu_0"]).max(), "adam nu")
