@@ -312,10 +312,13 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
       const float4 b = bp[i];
       v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
     }
+    // ReLU + its mask in two instructions per element: the sign bits are funnel-shifted into `mask` (element j ends up at
+    // bit 15 - j, 1 = negative pre-activation = no gradient).  A pre-activation of exactly +0 passes its (zero-measure)
+    // gradient where jax.nn.relu would not.
     mask = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      if (v[j] > 0.f) mask |= (1u << j);
+      mask = __funnelshift_l(__float_as_uint(v[j]), mask, 1);
       v[j] = fmaxf(v[j], 0.f);
     }
   };
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
     umma::tmem_ld_wait();
     signal_loaded();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = ((mask >> j) & 1u) ? v[j] : 0.f;
+    for (int j = 0; j < 16; ++j) v[j] = ((mask >> (15 - j)) & 1u) ? 0.f : v[j];
     store_row16(dst, v, need_bg);
   };
   // 16-wide layer outputs (features, d(features)): every column group takes 4 of the 16 columns of its rows
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
         v[4 * i] = dv * w.x; v[4 * i + 1] = dv * w.y; v[4 * i + 2] = dv * w.z; v[4 * i + 3] = dv * w.w;
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = ((mk_b2 >> j) & 1u) ? v[j] : 0.f;
+      for (int j = 0; j < 16; ++j) v[j] = ((mk_b2 >> (15 - j)) & 1u) ? 0.f : v[j];
       store_row16(DY64, v, false);
     }
     mark(6);
