@@ -21,7 +21,9 @@ class GradientExchange:
         self.seq = 0
 
     def _seq32(self) -> int:
-        return (self.seq - 1) % 0xFFFFFFFF + 1  # 1 .. 2^32 - 1, never 0 (0 = nothing published yet)
+        # 1 .. 2^32 - 2, never 0 (0 = nothing published yet), with an EVEN period: consecutive exchanges always alternate
+        # between the two slots (seq & 1), also across the wrap
+        return (self.seq - 1) % 0xFFFFFFFE + 1
 
     def next_slot(self) -> int:
         """Device address the next lrx_ppo_grad writes its gradbuf to."""

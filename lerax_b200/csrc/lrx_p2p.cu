@@ -16,7 +16,7 @@ namespace {
 
 __global__ void p2p_allreduce_kernel(char* const* __restrict__ peers, int rank, int world, size_t slot_b,
                                      float* __restrict__ out, int n, uint32_t seq, int* __restrict__ error_flag) {
-  p2p::publish_and_wait(peers, rank, world, seq, blockIdx.x == 0, error_flag);
+  if (!p2p::publish_and_wait(peers, rank, world, seq, blockIdx.x == 0, error_flag)) return;  // `out` is left untouched
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     out[i] = p2p::peer_sum(peers, world, slot_b, seq, i);
 }

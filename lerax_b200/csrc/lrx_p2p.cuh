@@ -25,9 +25,11 @@ __device__ __forceinline__ float ld_volatile_f32(const float* p) {
 }
 
 // Block-wide: (one thread of ONE block, `publisher`) publish seq in the own flag, then wait until every peer's flag
-// has reached seq.  Ends with __syncthreads().  A peer that does not arrive within ~10 s sets *error_flag.
-__device__ __forceinline__ void publish_and_wait(char* const* peers, int rank, int world, uint32_t seq, bool publisher,
+// has reached seq.  Ends with a block barrier; returns false (for every thread of the block) when a peer did not arrive
+// within ~10 s: *error_flag is set and the caller must NOT consume the slots (they may be stale or half written).
+__device__ __forceinline__ bool publish_and_wait(char* const* peers, int rank, int world, uint32_t seq, bool publisher,
                                                  int* error_flag) {
+  int timed_out = 0;
   if (publisher && threadIdx.x == 0) {
     __threadfence_system();  // the gradient kernel's stores to the own slot (earlier launch) before the flag
     st_release_sys(reinterpret_cast<uint32_t*>(peers[rank]), seq);
@@ -38,19 +40,30 @@ __device__ __forceinline__ void publish_and_wait(char* const* peers, int rank, i
     while ((int32_t)(ld_acquire_sys(flag) - seq) < 0) {
       if (clock64() - t0 > 20000000000LL) {  // a peer is gone -- report instead of hanging the GPU
         *error_flag = 1;
+        timed_out = 1;
         break;
       }
       __nanosleep(100);
     }
   }
-  __syncthreads();
+  return __syncthreads_or(timed_out) == 0;
 }
 
-// Sum of element i of slot (seq & 1) over the ranks, in rank order (identical on every rank).
+// Sum of element i of slot (seq & 1) over the ranks, in rank order (identical on every rank).  The loads of up to eight
+// ranks are ISSUED together and only then added: a loop of load-and-add serialises the NVLink round trips (~2 us each:
+// it was most of the 18 us a minibatch's exchange cost at 8 GPUs in round 1).
 __device__ __forceinline__ float peer_sum(char* const* peers, int world, size_t slot_b, uint32_t seq, int i) {
   const size_t off = HEADER + (size_t)(seq & 1u) * slot_b;
   float s = 0.f;
-  for (int r = 0; r < world; ++r) s += ld_volatile_f32(reinterpret_cast<const float*>(peers[r] + off) + i);
+  for (int r0 = 0; r0 < world; r0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      v[k] = (r0 + k < world) ? ld_volatile_f32(reinterpret_cast<const float*>(peers[r0 + k] + off) + i) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (r0 + k < world) s += v[k];
+  }
   return s;
 }
 

@@ -453,18 +453,20 @@ apply_kernel(float* __restrict__ params, float* __restrict__ m, float* __restric
   const float nbad = g[P + 6];
   const bool bad = nbad > 0.f || !isfinite(norm);
   cooperative_groups::this_grid().sync();
-  const int p = blockIdx.x * blockDim.x + tid;
-  if (!bad && p < P) {
+  // the grid is capped at what a cooperative launch can keep resident (launch_apply): walk the parameters with a stride
+  if (!bad) {
     const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
     const float bc2 = 1.0f - powf(h.adam_b2, (float)cnt);
-    float gp = g[p] + (p == log_std_off ? ls_extra : 0.f);
-    if (!(norm < h.max_grad_norm)) gp = (gp / norm) * h.max_grad_norm;
-    const float mn = h.adam_b1 * m[p] + (1.0f - h.adam_b1) * gp;
-    const float vn = h.adam_b2 * v[p] + (1.0f - h.adam_b2) * (gp * gp);
-    m[p] = mn;
-    v[p] = vn;
-    const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
-    params[p] = params[p] + (-h.learning_rate) * upd;
+    for (int p = blockIdx.x * blockDim.x + tid; p < P; p += gridDim.x * blockDim.x) {
+      float gp = g[p] + (p == log_std_off ? ls_extra : 0.f);
+      if (!(norm < h.max_grad_norm)) gp = (gp / norm) * h.max_grad_norm;
+      const float mn = h.adam_b1 * m[p] + (1.0f - h.adam_b1) * gp;
+      const float vn = h.adam_b2 * v[p] + (1.0f - h.adam_b2) * (gp * gp);
+      m[p] = mn;
+      v[p] = vn;
+      const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
+      params[p] = params[p] + (-h.learning_rate) * upd;
+    }
   }
   if (blockIdx.x == 0 && tid == 0) {
     if (!bad) *count = cnt;
@@ -499,17 +501,23 @@ apply_p2p_kernel(float* __restrict__ params, float* __restrict__ m, float* __res
   __shared__ double red[8];
   __shared__ float norm_s;
   const int tid = threadIdx.x;
-  p2p::publish_and_wait(peers, rank, world, seq, blockIdx.x == 0, error_flag);
+  const bool arrived = p2p::publish_and_wait(peers, rank, world, seq, blockIdx.x == 0, error_flag);
   const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
   const int cnt = *count + 1;
-  const int p = blockIdx.x * blockDim.x + tid;
-  float gp = 0.f;
-  if (p < P + LRX_PPO_NSTATS) {
-    const float s = p2p::peer_sum(peers, world, slot_b, seq, p);
-    gsum[p] = s;
-    if (p < P) gp = s + (p == log_std_off ? ls_extra : 0.f);
+  // pass 1 (grid stride; the grid is capped at what a cooperative launch keeps resident): rank-ordered sum of every
+  // element over the peers' slots -> gsum, this block's share of the sum of squares
+  double ss = 0;
+  if (arrived) {  // a lost peer's slot may be stale or half written: never summed
+    for (int p = blockIdx.x * blockDim.x + tid; p < P + LRX_PPO_NSTATS; p += gridDim.x * blockDim.x) {
+      const float sum = p2p::peer_sum(peers, world, slot_b, seq, p);
+      gsum[p] = sum;
+      if (p < P) {
+        const float gp = sum + (p == log_std_off ? ls_extra : 0.f);
+        ss += (double)gp * gp;
+      }
+    }
   }
-  double ss = warp_sum((double)gp * gp);
+  ss = warp_sum(ss);
   if ((tid & 31) == 0) red[tid >> 5] = ss;
   __syncthreads();
   if (tid == 0) {
@@ -521,28 +529,34 @@ apply_p2p_kernel(float* __restrict__ params, float* __restrict__ m, float* __res
   cooperative_groups::this_grid().sync();
   if (tid == 0) {
     double t = 0;
-    for (unsigned b = 0; b < gridDim.x; ++b) t += blk_ss[b];  // block order: deterministic
+    for (unsigned b = 0; b < gridDim.x; ++b) t += blk_ss[b];  // block order: deterministic (same grid on every rank)
     norm_s = (float)sqrt(t);
   }
   __syncthreads();
   const float norm = norm_s;
-  const float nbad = gsum[P + 6];
-  const bool bad = nbad > 0.f || !isfinite(norm);
-  if (!bad && p < P) {
+  // a peer that timed out in ANY block (the flag is sticky) voids the exchange for every block alike: no parameter, moment
+  // or count update and no statistics; the host raises when it reads the flag (GradientExchange.check)
+  const bool peer_lost = *reinterpret_cast<volatile int*>(error_flag) != 0;
+  const float nbad = peer_lost ? 0.f : gsum[P + 6];
+  const bool bad = peer_lost || nbad > 0.f || !isfinite(norm);
+  if (!bad) {  // pass 2: clip + Adam on the block's own elements (written by this very thread in pass 1)
     const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
     const float bc2 = 1.0f - powf(h.adam_b2, (float)cnt);
-    if (!(norm < h.max_grad_norm)) gp = (gp / norm) * h.max_grad_norm;
-    const float mn = h.adam_b1 * m[p] + (1.0f - h.adam_b1) * gp;
-    const float vn = h.adam_b2 * v[p] + (1.0f - h.adam_b2) * (gp * gp);
-    m[p] = mn;
-    v[p] = vn;
-    const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
-    params[p] = params[p] + (-h.learning_rate) * upd;
+    for (int p = blockIdx.x * blockDim.x + tid; p < P; p += gridDim.x * blockDim.x) {
+      float gp = gsum[p] + (p == log_std_off ? ls_extra : 0.f);
+      if (!(norm < h.max_grad_norm)) gp = (gp / norm) * h.max_grad_norm;
+      const float mn = h.adam_b1 * m[p] + (1.0f - h.adam_b1) * gp;
+      const float vn = h.adam_b2 * v[p] + (1.0f - h.adam_b2) * (gp * gp);
+      m[p] = mn;
+      v[p] = vn;
+      const float upd = (mn / bc1) / (sqrtf(vn / bc2) + h.adam_eps);
+      params[p] = params[p] + (-h.learning_rate) * upd;
+    }
   }
   if (blockIdx.x == 0 && tid == 0) {
     if (!bad) *count = cnt;
-    else if (nonfinite_flag) atomicOr(nonfinite_flag, 1);
-    if (stats_out) {
+    else if (nonfinite_flag && !peer_lost) atomicOr(nonfinite_flag, 1);
+    if (stats_out && !peer_lost) {
       const float kl = gsum[P + 0] - 1.0f;
       const float pl = -gsum[P + 1];
       const float vl = gsum[P + 2] / 2.0f;
@@ -564,7 +578,10 @@ static int launch_apply(float* params, float* m, float* v, int32_t* count, const
   LrxPpoHyper hh = h;
   void* args[] = {(void*)&params, (void*)&m, (void*)&v, (void*)&count, (void*)&g, (void*)&P, (void*)&log_std_off,
                   (void*)&hh, (void*)&stats_out, (void*)&nonfinite_flag};
-  LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)apply_kernel, dim3((P + 255) / 256), dim3(256), args, 0, s));
+  // every block must be resident at once (grid barrier): at most 4 blocks of 256 threads per SM, parameters walked with a
+  // grid stride (a 512-wide policy has > 300 k parameters, more blocks than a cooperative launch accepts)
+  const int cap = 4 * lrx_sm_count(), want = (P + 255) / 256;
+  LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)apply_kernel, dim3(want < cap ? want : cap), dim3(256), args, 0, s));
   return LRX_OK;
 }
 
@@ -648,25 +665,27 @@ extern "C" size_t lrx_ppo_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) {
   return workspace_tail(pol, B).total;
 }
 
-void lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
-                                int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
-                                const LrxApplyArgs* apply, cudaStream_t s) {
+int lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
+                               int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
+                               const LrxApplyArgs* apply, cudaStream_t s) {
   LrxApplyArgs ap{};
   const int grid = (P + 31) / 32;
-  if (apply && grid <= 900) {
+  if (apply && grid <= 4 * lrx_sm_count()) {
     // fused reduce + clip + Adam: needs every block resident at once (grid barrier) -> cooperative launch
     ap = *apply;
     void* args[] = {(void*)&partial, (void*)&splits, (void*)&stride, (void*)&P, (void*)&loss_partial,
                     (void*)&loss_blocks, (void*)&log_std_off, (void*)&ent_coef, (void*)&B_global, (void*)&gradbuf,
                     (void*)&ap};
-    cudaLaunchCooperativeKernel((const void*)reduce_partials_kernel, dim3(grid), dim3(256), args, 0, s);
-    return;
+    LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)reduce_partials_kernel, dim3(grid), dim3(256), args, 0, s));
+    return LRX_OK;
   }
   reduce_partials_kernel<<<grid, 256, 0, s>>>(partial, splits, stride, P, loss_partial, loss_blocks, log_std_off,
                                               ent_coef, B_global, gradbuf, ap);
+  LRX_CUDA_CHECK(cudaGetLastError());
   if (apply)  // too many blocks for one resident wave of the fused kernel: separate apply launch
-    launch_apply(apply->params, apply->m, apply->v, apply->count, gradbuf, P, log_std_off, apply->h, apply->stats_out,
-                 apply->nonfinite_flag, s);
+    return launch_apply(apply->params, apply->m, apply->v, apply->count, gradbuf, P, log_std_off, apply->h, apply->stats_out,
+                        apply->nonfinite_flag, s);
+  return LRX_OK;
 }
 
 // ======================================================================== host driver
@@ -882,7 +901,8 @@ extern "C" int lrx_ppo_apply_p2p(const LrxPolicyDesc* pol, float* params, float*
   void* args[] = {(void*)&params, (void*)&adam_m, (void*)&adam_v, (void*)&adam_count, (void*)&peers, (void*)&rk,
                   (void*)&wd, (void*)&slot_b, (void*)&sq, (void*)&error_flag, (void*)&gsum, (void*)&blk_ss, (void*)&P,
                   (void*)&log_std_off, (void*)&hh, (void*)&stats_out, (void*)&nonfinite_flag};
-  LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)apply_p2p_kernel, dim3((n + 255) / 256), dim3(256), args, 0,
+  const int cap = 4 * lrx_sm_count(), want = (n + 255) / 256;
+  LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)apply_p2p_kernel, dim3(want < cap ? want : cap), dim3(256), args, 0,
                                              (cudaStream_t)stream));
   LRX_LAUNCH_CHECK();
   return LRX_OK;

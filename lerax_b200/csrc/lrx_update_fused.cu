@@ -907,9 +907,9 @@ FusedWorkspace carve_fused(const LrxPolicyDesc& pol, void* base) {
 
 // defined in lrx_update.cu
 struct LrxApplyArgs;
-void lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
-                                int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
-                                const LrxApplyArgs* apply, cudaStream_t s);
+int lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
+                               int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
+                               const LrxApplyArgs* apply, cudaStream_t s);
 
 size_t lrx_fused_workspace_bytes(const LrxPolicyDesc* pol, int64_t B) {
   if (!tc::is_default_policy(*pol)) return 0;
@@ -955,8 +955,9 @@ int lrx_ppo_grad_fused(const LrxPolicyDesc* pol, const float* params, const LrxB
     default: ppo_grad_fused_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
   }
   LRX_LAUNCH_CHECK();
-  lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid, a.lo.log_std,
-                             h->entropy_loss_coefficient, (double)B_global, gradbuf, apply, stream);
+  const int rc = lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid,
+                                            a.lo.log_std, h->entropy_loss_coefficient, (double)B_global, gradbuf, apply, stream);
+  if (rc) return rc;
   LRX_LAUNCH_CHECK();
   *handled = true;
   return LRX_OK;

@@ -880,9 +880,9 @@ FusedWorkspace carve_fused(const LrxPolicyDesc& pol, void* base) {
 
 // defined in lrx_update.cu
 struct LrxApplyArgs;
-void lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
-                                int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
-                                const LrxApplyArgs* apply, cudaStream_t s);
+int lrx_launch_reduce_partials(const float* partial, int splits, long long stride, int P, const double* loss_partial,
+                               int loss_blocks, int log_std_off, float ent_coef, double B_global, float* gradbuf,
+                               const LrxApplyArgs* apply, cudaStream_t s);
 
 static long long* g_tc128_prof = nullptr;  // test hook, include/lerax_b200_debug.h
 extern "C" void lrx_debug_set_tc128_prof(long long* device_buffer_64) { g_tc128_prof = device_buffer_64; }
@@ -927,8 +927,9 @@ int lrx_ppo_grad_tc128(const LrxPolicyDesc* pol, const float* params, const LrxB
     default: ppo_grad_tc128_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
   }
   LRX_LAUNCH_CHECK();
-  lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid, a.lo.log_std,
-                             h->entropy_loss_coefficient, (double)B_global, gradbuf, apply, stream);
+  const int rc = lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid,
+                                            a.lo.log_std, h->entropy_loss_coefficient, (double)B_global, gradbuf, apply, stream);
+  if (rc) return rc;
   LRX_LAUNCH_CHECK();
   *handled = true;
   return LRX_OK;

@@ -362,3 +362,20 @@ def test_invalid_arguments_are_reported():
     d.n_params = 7
     assert L.lib.lrx_policy_forward(d, None, None, None, None, 1, None) == -1
     assert b"n_params" in L.lib.lrx_last_error()
+
+
+def test_update_512_wide_policy_apply_walks_parameters_with_a_stride():
+    """> 303 k parameters: more 256-parameter blocks than a cooperative launch keeps resident.  clip + Adam must walk
+    the parameters with a grid stride (round 1's one-block-per-256-parameters launch failed here)."""
+    pkw = dict(feature_width=512, value_width=512, action_width=512)
+    T, N, nb = 8, 16, 2
+    spec, params, pol, rng, flat, buf = synthetic_buffer("cartpole", T, N, seed=23, **pkw)
+    assert spec.n_params > 303_000
+    hp = OU.Hyper(entropy_loss_coefficient=0.01)
+    idx = OU.batch_indices(T * N, T * N // nb, rng)[None]
+    p1, st, log = OU.train(spec, params.copy(), OU.AdamState.init(params), flat, idx, hp)
+    gp, gm, gv, cnt, stats, flag = H.run_update(pol, buf, idx, hp)
+    assert cnt == nb and flag == 0
+    tol, tight = H.adam_conditioned_tolerance(spec, params, flat, idx, hp)
+    H.assert_params_close(gp, p1, tol, tight, "params (512-wide)", max_loose_frac=2e-2)
+    assert np.abs(gp - params).max() > 1e-5
