@@ -333,7 +333,8 @@ def run_ours(args):
         ev[i][0].record(stream)
         b = algo._buffers(env, state.policy, state.policy.params.device)
         out = L.LrxRolloutOut(L.ptr(b["obs"]), L.ptr(b["act"]), L.ptr(b["rew"]), L.ptr(b["done"]), L.ptr(b["logp"]),
-                              L.ptr(b["val"]), L.ptr(b["last_value"]), None, None, None)
+                              L.ptr(b["val"]), L.ptr(b["last_value"]), None, None, None, L.ptr(b["rollout_ws"]),
+                              0 if b["rollout_ws"] is None else b["rollout_ws"].numel())
         rng = L.LrxRng(state.rollout_seed, rank * n_local, state.steps_done & 0xFFFFFFFF)
         L.check(L.lib.lrx_rollout(env.desc(), state.policy.desc(), L.ptr(state.policy.params),
                                   state.step_state.env_state.c_state(), rng, None, out, n_local, args.horizon,

@@ -143,7 +143,14 @@ typedef struct LrxRolloutOut {
   float* y_trace;
   float* t_trace;
   float* y_next_trace;
+  /* Optional scratch for policies with NON-default widths (lrx_rollout_workspace_bytes; NULL = none): with it a rollout
+   * of >= 512 envs runs step by step as batched GEMMs over the envs instead of one lane per env. */
+  void* workspace;
+  size_t workspace_bytes;
 } LrxRolloutOut;
+
+/* Bytes of LrxRolloutOut.workspace for N envs (0 on invalid arguments). */
+size_t lrx_rollout_workspace_bytes(const LrxPolicyDesc* pol, int32_t N);
 
 /* env.initial for N envs (PPOStepState.initial, algorithm/ppo.py:45-58,331-333).
  * uniform: optional injected draws [N][k] in [0,1); NULL -> Philox stream 1 at

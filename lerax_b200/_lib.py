@@ -53,7 +53,8 @@ class LrxReplay(C.Structure):
 class LrxRolloutOut(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("act", C.c_void_p), ("rew", C.c_void_p), ("done", C.c_void_p),
                 ("logp", C.c_void_p), ("val", C.c_void_p), ("last_value", C.c_void_p),
-                ("y_trace", C.c_void_p), ("t_trace", C.c_void_p), ("y_next_trace", C.c_void_p)]
+                ("y_trace", C.c_void_p), ("t_trace", C.c_void_p), ("y_next_trace", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class LrxPpoHyper(C.Structure):
@@ -86,6 +87,7 @@ PROTOTYPES = {
     "lrx_policy_forward": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, C.c_int32, _vp]),
     "lrx_rollout": (C.c_int, [_P(LrxEnvDesc), _P(LrxPolicyDesc), _vp, LrxEnvState, LrxRng, _P(LrxReplay),
                               LrxRolloutOut, C.c_int32, C.c_int32, C.c_float, _vp]),
+    "lrx_rollout_workspace_bytes": (C.c_size_t, [_P(LrxPolicyDesc), C.c_int32]),
     "lrx_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,
                           _vp, _vp]),
     "lrx_returns": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, _vp]),

@@ -187,6 +187,9 @@ class PPO(AbstractAlgorithm):
             adv_sums=torch.zeros((self.minibatches_per_epoch, 2), dtype=torch.float64, device=device),
             # row-major copy of the buffer for the minibatch gather of the tensor-core update kernel (default widths)
             packed=(torch.empty((T * N, L.LRX_PACKED_FLOATS), **f32) if (d <= 8 and policy.is_default_widths()) else None),
+            # activations of the step-by-step (GEMM-batched) rollout of non-default widths
+            rollout_ws=(None if policy.is_default_widths() else torch.empty(
+                (max(int(L.lib.lrx_rollout_workspace_bytes(policy.desc(), N)), 1),), dtype=torch.uint8, device=device)),
         )
         return self._bufs
 
@@ -223,7 +226,8 @@ class PPO(AbstractAlgorithm):
         N, T = self._local_envs(), self.num_steps
         b = self._buffers(env, policy, policy.params.device)
         out = L.LrxRolloutOut(L.ptr(b["obs"]), L.ptr(b["act"]), L.ptr(b["rew"]), L.ptr(b["done"]), L.ptr(b["logp"]),
-                              L.ptr(b["val"]), L.ptr(b["last_value"]), None, None, None)
+                              L.ptr(b["val"]), L.ptr(b["last_value"]), None, None, None, L.ptr(b["rollout_ws"]),
+                              0 if b["rollout_ws"] is None else b["rollout_ws"].numel())
         rng = L.LrxRng(seed & _MASK64, rank * N, step_offset & 0xFFFFFFFF)
         L.check(L.lib.lrx_rollout(env.desc(), policy.desc(), L.ptr(policy.params), step_state.env_state.c_state(),
                                   rng, replay, out, N, T, float(self.gamma), L.stream_ptr()), "lrx_rollout")

@@ -380,6 +380,10 @@ int lrx_rollout_fast(const LrxEnvDesc* env, const LrxPolicyDesc* pol, const floa
                      LrxEnvState state, LrxRng rng, const LrxReplay* replay, LrxRolloutOut out,
                      int32_t N, int32_t T, float gamma, cudaStream_t stream, bool* handled);
 
+int lrx_rollout_stepwise(const LrxEnvDesc* env, const LrxPolicyDesc* pol, const float* params, LrxEnvState state,
+                         LrxRng rng, const LrxReplay* replay, LrxRolloutOut out, int32_t N, int32_t T, float gamma,
+                         cudaStream_t s, bool* handled);
+
 extern "C" int lrx_rollout(const LrxEnvDesc* env, const LrxPolicyDesc* pol, const float* params,
                            LrxEnvState state, LrxRng rng, const LrxReplay* replay, LrxRolloutOut out,
                            int32_t N, int32_t T, float gamma, lrx_stream_t stream) {
@@ -405,6 +409,9 @@ extern "C" int lrx_rollout(const LrxEnvDesc* env, const LrxPolicyDesc* pol, cons
 
   bool handled = false;
   rc = lrx_rollout_fast(env, pol, params, state, rng, &rp, out, N, T, gamma, s, &handled);
+  if (rc) return rc;
+  if (handled) return LRX_OK;
+  rc = lrx_rollout_stepwise(env, pol, params, state, rng, &rp, out, N, T, gamma, s, &handled);  // wide policies, many envs
   if (rc) return rc;
   if (handled) return LRX_OK;
 

@@ -13,6 +13,7 @@
 #include <cooperative_groups.h>
 
 #include "lrx_common.cuh"
+#include "lrx_gemm.cuh"
 #include "lrx_p2p.cuh"
 #include "lrx_policy.cuh"
 
@@ -22,21 +23,6 @@ constexpr int LRX_MAX_SPLIT = 128;
 
 // ============================================================================== SGEMM
 // C[M x N] (+)= op(A)[M x K] * op(B)[K x N], fp32, 64x64x16 tiles, 4x4 micro-tiles.
-struct GemmArgs {
-  const float* A; int lda;
-  const float* B; int ldb;
-  float* C; int ldc;
-  int M, N, K;
-  const float* bias;   // + bias[i]
-  int relu;
-  const float* mask; int ldm;  // *= (mask[i][j] > 0)
-  int accumulate;      // C += result
-  int ones_row;        // additionally write C[M][j] = 1
-  int k_chunk;         // K range per blockIdx.z (split-K)
-  long long c_split_stride;  // C/C2 offset per blockIdx.z
-  float* C2; int n_main;     // column j == n_main is redirected to C2[i]
-};
-
 template <bool AT, bool BT>
 __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
   constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
@@ -121,6 +107,20 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
 }
 
 static int launch_gemm(const GemmArgs& g, bool at, bool bt, int splits, cudaStream_t s) {
+  bool handled = false;  // layer widths and contractions of at least 16: tensor cores (lrx_gemm_tc.cu)
+  const int rc = lrx_launch_gemm_tc(g, at, bt, splits, s, &handled);
+  if (rc || handled) return rc;
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, splits);
+  if (!at && !bt) sgemm_kernel<false, false><<<grid, 256, 0, s>>>(g);
+  else if (at && !bt) sgemm_kernel<true, false><<<grid, 256, 0, s>>>(g);
+  else if (!at && bt) sgemm_kernel<false, true><<<grid, 256, 0, s>>>(g);
+  else sgemm_kernel<true, true><<<grid, 256, 0, s>>>(g);
+  LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+// exact-fp32 GEMM for callers outside this file (the step-by-step rollout of wide policies, lrx_rollout_steps.cu)
+int lrx_launch_gemm_fma(const GemmArgs& g, bool at, bool bt, int splits, cudaStream_t s) {
   dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, splits);
   if (!at && !bt) sgemm_kernel<false, false><<<grid, 256, 0, s>>>(g);
   else if (at && !bt) sgemm_kernel<true, false><<<grid, 256, 0, s>>>(g);
@@ -431,28 +431,50 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
 __global__ void __launch_bounds__(256)
 apply_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, int32_t* count,
              const float* __restrict__ g, int P, int log_std_off, LrxPpoHyper h, float* stats_out,
-             int32_t* nonfinite_flag) {
+             int32_t* nonfinite_flag, double* blk_ss) {
   __shared__ double red[8];
   const int tid = threadIdx.x;
   // d entropy_loss / d log_std = -1 per row mean -> -c_H, contributed once (not per rank):
   // callers all-reduce gradbuf, so it is added here, after the reduction.
   const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
   const int cnt = *count + 1;
+  // global norm: with scratch (lrx_ppo_update) every block sums ITS parameters, the blocks' sums meet at the grid barrier
+  // and are added in block order; without (the public lrx_ppo_apply has no workspace) every block walks all of them.
+  // Fixed order either way -> deterministic.
   double ss = 0;
-  for (int p = tid; p < P; p += blockDim.x) {
+  const int first = blk_ss ? blockIdx.x * blockDim.x + tid : tid, stride = blk_ss ? gridDim.x * blockDim.x : blockDim.x;
+  for (int p = first; p < P; p += stride) {
     float gp = g[p] + (p == log_std_off ? ls_extra : 0.f);
     ss += (double)gp * gp;
   }
-  ss = warp_sum(ss);  // fixed order -> deterministic
+  ss = warp_sum(ss);
   if ((tid & 31) == 0) red[tid >> 5] = ss;
   __syncthreads();
   double t = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) t += red[i];
+  if (blk_ss && tid == 0) blk_ss[blockIdx.x] = t;
+  cooperative_groups::this_grid().sync();
+  if (blk_ss) {
+    __shared__ double tot_s;
+    double acc = 0;
+    for (int b = tid; b < (int)gridDim.x; b += blockDim.x) acc += __ldcg(blk_ss + b);
+    acc = warp_sum(acc);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double u = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u += red[i];
+      tot_s = u;
+    }
+    __syncthreads();
+    t = tot_s;
+  }
   const float norm = (float)sqrt(t);
   const float nbad = g[P + 6];
   const bool bad = nbad > 0.f || !isfinite(norm);
-  cooperative_groups::this_grid().sync();
   // the grid is capped at what a cooperative launch can keep resident (launch_apply): walk the parameters with a stride
   if (!bad) {
     const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
@@ -574,13 +596,15 @@ apply_p2p_kernel(float* __restrict__ params, float* __restrict__ m, float* __res
 }
 
 static int launch_apply(float* params, float* m, float* v, int32_t* count, const float* g, int P, int log_std_off,
-                        const LrxPpoHyper& h, float* stats_out, int32_t* nonfinite_flag, cudaStream_t s) {
+                        const LrxPpoHyper& h, float* stats_out, int32_t* nonfinite_flag, cudaStream_t s,
+                        double* blk_ss = nullptr) {
   LrxPpoHyper hh = h;
   void* args[] = {(void*)&params, (void*)&m, (void*)&v, (void*)&count, (void*)&g, (void*)&P, (void*)&log_std_off,
-                  (void*)&hh, (void*)&stats_out, (void*)&nonfinite_flag};
+                  (void*)&hh, (void*)&stats_out, (void*)&nonfinite_flag, (void*)&blk_ss};
   // every block must be resident at once (grid barrier): at most 4 blocks of 256 threads per SM, parameters walked with a
   // grid stride (a 512-wide policy has > 300 k parameters, more blocks than a cooperative launch accepts)
-  const int cap = 4 * lrx_sm_count(), want = (P + 255) / 256;
+  // without scratch every block reads the whole gradient for the norm: keep that to one block per SM
+  const int cap = (blk_ss ? 4 : 1) * lrx_sm_count(), want = (P + 255) / 256;
   LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)apply_kernel, dim3(want < cap ? want : cap), dim3(256), args, 0, s));
   return LRX_OK;
 }
@@ -684,7 +708,7 @@ int lrx_launch_reduce_partials(const float* partial, int splits, long long strid
   LRX_CUDA_CHECK(cudaGetLastError());
   if (apply)  // too many blocks for one resident wave of the fused kernel: separate apply launch
     return launch_apply(apply->params, apply->m, apply->v, apply->count, gradbuf, P, log_std_off, apply->h, apply->stats_out,
-                        apply->nonfinite_flag, s);
+                        apply->nonfinite_flag, s, apply->blk_ss);
   return LRX_OK;
 }
 
@@ -943,9 +967,13 @@ extern "C" int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* ad
     rc = lrx_ppo_grad(pol, params, buf, idx + (size_t)b * B, B, B, adv_sums + 2 * b, h, gradbuf, workspace,
                       tail.adv_sums_off, stream);
     if (rc) return rc;
-    rc = lrx_ppo_apply(pol, params, adam_m, adam_v, adam_count, gradbuf, h, stats_out + (size_t)b * LRX_PPO_NSTATS,
-                       nonfinite_flag, stream);
-    if (rc) return rc;
+    {
+      PolicyTable tab = lrx_make_table(*pol);
+      rc = launch_apply(params, adam_m, adam_v, adam_count, gradbuf, pol->n_params, tab.log_std_off, *h,
+                        stats_out + (size_t)b * LRX_PPO_NSTATS, nonfinite_flag, (cudaStream_t)stream, ap.blk_ss);
+      if (rc) return rc;
+      LRX_LAUNCH_CHECK();
+    }
   }
   return LRX_OK;
 }

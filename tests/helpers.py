@@ -42,7 +42,7 @@ def dev(x):
 
 
 def run_rollout(env, policy, y0, t0, sc0, T, gamma, noise_action=None, reset_uniform=None, seed=0,
-                env_offset=0, step_offset=0, trace=True):
+                env_offset=0, step_offset=0, trace=True, workspace=True):
     """Call lrx_rollout; returns a dict of NumPy arrays shaped like oracle.rollout's output."""
     import torch
 
@@ -60,8 +60,10 @@ def run_rollout(env, policy, y0, t0, sc0, T, gamma, noise_action=None, reset_uni
     ytr = torch.empty((T, k, N), **f32) if trace else None
     ttr = torch.empty((T, N), **f32) if trace else None
     yn = torch.empty((T, k, N), **f32) if trace else None
+    ws_bytes = int(L.lib.lrx_rollout_workspace_bytes(policy.desc(), N)) if workspace else 0
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda") if workspace else None
     out = L.LrxRolloutOut(L.ptr(obs), L.ptr(act), L.ptr(rew), L.ptr(done), L.ptr(logp), L.ptr(val), L.ptr(last),
-                          L.ptr(ytr), L.ptr(ttr), L.ptr(yn))
+                          L.ptr(ytr), L.ptr(ttr), L.ptr(yn), L.ptr(ws), ws_bytes)
     rp = None
     keep = []
     if noise_action is not None or reset_uniform is not None:

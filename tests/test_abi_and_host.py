@@ -59,7 +59,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(L.LrxEnvDesc) == 4 + 4 + 4 + 16 * 4
     assert ctypes.sizeof(L.LrxPolicyDesc) == 4 * 4 + 3 * 4 + 3 * 9 * 4 + 3 * 8 * 4
     assert ctypes.sizeof(L.LrxRng) == 16
-    assert ctypes.sizeof(L.LrxRolloutOut) == 10 * 8
+    assert ctypes.sizeof(L.LrxRolloutOut) == 12 * 8
     assert ctypes.sizeof(L.LrxPpoHyper) == 8 * 4 + 3 * 4
     assert ctypes.sizeof(L.LrxBatchView) == 6 * 8 + 8 + 8
 

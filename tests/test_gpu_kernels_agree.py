@@ -173,3 +173,64 @@ def test_packed_rows_gather_equals_plane_gather(kind):
     gb, _ = H.run_grad(pol, buf, idx, hp)
     np.testing.assert_array_equal(ga, gb)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("widths", [dict(feature_width=256, value_width=256, action_width=256),
+                                    dict(feature_width=96, value_width=40, action_width=72, feature_size=24, value_depth=3)])
+def test_wide_policy_gradient_tensor_core_gemm_vs_fma(widths, fused_toggle):
+    """Non-default widths (BASELINE configs[2]: 256-wide): the layer-by-layer update with the tcgen05 GEMM
+    (lrx_gemm_tc.cu: all four operand orientations, ragged tiles, split-K weight gradients) against the same path on the
+    FMA kernel, and both against the oracle."""
+    T, N, B = 40, 60, 2100  # 16 full 128-row tiles + a ragged one; split-K over 3 row chunks
+    spec, params, pol, rng, flat, buf = synthetic_buffer("pendulum", T, N, seed=29, **widths)
+    hp = OU.Hyper(clip_value_loss=True, entropy_loss_coefficient=0.01)
+    idx = rng.permutation(T * N)[:B].astype(np.int32)
+    fused_toggle(2)
+    ga, _ = H.run_grad(pol, buf, idx, hp)
+    ga2, _ = H.run_grad(pol, buf, idx, hp)
+    np.testing.assert_array_equal(ga, ga2)
+    fused_toggle(0)
+    gb, _ = H.run_grad(pol, buf, idx, hp)
+    P = spec.n_params
+    scale = np.abs(gb[:P]).max()
+    H.assert_close(ga[:P], gb[:P], 1e-4, 1e-5 * scale, "gradient (tensor-core GEMM vs FMA)")
+    H.assert_close(ga[P:P + 4], gb[P:P + 4], 1e-5, 1e-6, "stat sums")
+    _, stats, g = OU.ppo_loss_and_grad(spec, params, OU.gather(flat, idx), hp)
+    gg = ga[:P].copy()
+    gg[-1] -= hp.entropy_loss_coefficient
+    H.assert_close(gg, g, 1e-4, 1e-5 * np.abs(g).max(), "gradient vs oracle")
+
+
+@pytest.mark.parametrize("kind,mes", [("pendulum", 0), ("pendulum", 6), ("cartpole", 5), ("acrobot", 0)])
+def test_wide_policy_stepwise_rollout(kind, mes, fused_toggle):
+    """Non-default widths, >= 512 envs: the step-by-step GEMM-batched rollout (lrx_rollout_steps.cu) against the oracle
+    and against the one-lane-per-env kernel -- identical event order (PPO.step: sample, clip, transition, reward,
+    terminal / truncate, TimeLimit bootstrap from the PRE-reset state, reset), same injected noise."""
+    widths = dict(feature_width=96, value_width=80, action_width=72, feature_size=24)
+    N, T = 600, 20
+    oenv, spec, params, env, pol, rng, y0 = setup(kind, N=N, mes=mes, **widths)
+    na, ru = noise_for(spec, rng, T, N, oenv.state_dim)
+    t0, sc0 = np.zeros(N, np.float32), np.zeros(N, np.int32)
+    from oracle import rollout as OR
+
+    want = OR.rollout(oenv, spec, params, y0, t0, sc0, T, 0.99, na, ru)
+    fused_toggle(2)
+    a = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, na, ru)           # stepwise (workspace given, N >= 512)
+    b = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, na, ru, workspace=False)  # one lane per env
+    for got, name in ((a, "stepwise"), (b, "per-lane")):
+        assert (got["done"] != want["done"]).mean() == 0, name
+        if not spec.is_box:
+            assert (got["act"] != want["act"]).mean() == 0, name
+        for k in ("obs", "logp", "val", "rew"):
+            H.assert_close(got[k][0], want[k][0], 1e-5, 2e-6, f"{name} {k}[t=0]")
+        drift = 1e-5 if kind == "cartpole" else 3e-4
+        for k in ("obs", "logp", "val", "rew", "last_value", "y"):
+            H.assert_close(got[k], want[k], 1e-4, drift, f"{name} {k}")
+        np.testing.assert_array_equal(got["step_count"], want["step_count"])
+    if mes:
+        assert want["done"].any()
+    # Philox noise (no replay): both kernels draw the same streams
+    c = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, seed=5, trace=False)
+    d = H.run_rollout(env, pol, y0, t0, sc0, T, 0.99, seed=5, trace=False, workspace=False)
+    assert (c["done"] != d["done"]).mean() < 2e-3
+    H.assert_close(c["val"][0], d["val"][0], 1e-5, 2e-6, "Philox: value[t=0]")

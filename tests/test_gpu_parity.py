@@ -333,7 +333,8 @@ def test_update_wide_pendulum_config3():
     p1, st, log = OU.train(spec, params.copy(), OU.AdamState.init(params), flat, idx, hp)
     gp, gm, gv, cnt, stats, flag = H.run_update(pol, buf, idx, hp)
     assert cnt == nb and flag == 0
-    H.assert_close(gp, p1, 1e-4, 1e-6, "params (256-wide)")
+    tol, tight = H.adam_conditioned_tolerance(spec, params, flat, idx, hp)
+    H.assert_params_close(gp, p1, tol, tight, "params (256-wide)")
 
 
 def test_nonfinite_flag_and_skip():
