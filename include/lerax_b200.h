@@ -328,6 +328,15 @@ int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* adam_m, float
                    int32_t* nonfinite_flag, void* workspace, size_t workspace_bytes,
                    lrx_stream_t stream);
 
+/* The same with a learning-rate SCHEDULE (ppo.py:176,192-194: optax.inject_hyperparams evaluates a callable
+ * learning_rate at its own update count): learning_rates_host is a HOST array of num_batches rates, one per minibatch
+ * (NULL: h->learning_rate for all of them). */
+int lrx_ppo_update_schedule(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
+                            int32_t* adam_count, const LrxBatchView* buf, const int32_t* idx,
+                            int32_t num_batches, int64_t B, const LrxPpoHyper* h, const float* learning_rates_host,
+                            float* stats_out, int32_t* nonfinite_flag, void* workspace, size_t workspace_bytes,
+                            lrx_stream_t stream);
+
 /* ------------------------------------------------------------------------- misc */
 const char* lrx_last_error(void);
 int lrx_version(void);

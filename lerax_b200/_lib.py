@@ -111,6 +111,8 @@ PROTOTYPES = {
     "lrx_ppo_apply": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _vp, _P(LrxPpoHyper), _vp, _vp, _vp]),
     "lrx_ppo_update": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _P(LrxBatchView), _vp, C.c_int32,
                                  C.c_int64, _P(LrxPpoHyper), _vp, _vp, _vp, C.c_size_t, _vp]),
+    "lrx_ppo_update_schedule": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _P(LrxBatchView), _vp, C.c_int32,
+                                          C.c_int64, _P(LrxPpoHyper), _P(C.c_float), _vp, _vp, _vp, C.c_size_t, _vp]),
     "lrx_last_error": (C.c_char_p, []),
     "lrx_version": (C.c_int, []),
     "lrx_launch_count": (C.c_int64, [C.c_int]),

@@ -261,11 +261,18 @@ class PPO(AbstractAlgorithm):
             perm_key = Key((int(epoch_keys[e]) + rank) & _MASK64) if self._shuffle else None
             idx = buffer.batch_indices(B_local, key=perm_key)[: self.minibatches_per_epoch]
             nb = idx.shape[0]
-            if world == 1 and not callable(self.learning_rate):
+            if world == 1:
+                # one C call per epoch; a callable learning_rate (optax schedule of the update count, ppo.py:176,192-194)
+                # travels as one rate per minibatch
                 h = self._hyper(self._lr_at(count))
-                L.check(L.lib.lrx_ppo_update(pol_d, L.ptr(policy.params), L.ptr(opt_state.mu), L.ptr(opt_state.nu),
-                                             L.ptr(opt_state.count), view, L.ptr(idx), nb, B_local, h,
-                                             L.ptr(stats[e]), L.ptr(b["nonfinite"]), ws, ws_bytes, L.stream_ptr()),
+                lrs = None
+                if callable(self.learning_rate):
+                    import ctypes
+
+                    lrs = (ctypes.c_float * nb)(*[self._lr_at(count + i) for i in range(nb)])
+                L.check(L.lib.lrx_ppo_update_schedule(pol_d, L.ptr(policy.params), L.ptr(opt_state.mu), L.ptr(opt_state.nu),
+                                                      L.ptr(opt_state.count), view, L.ptr(idx), nb, B_local, h, lrs,
+                                                      L.ptr(stats[e]), L.ptr(b["nonfinite"]), ws, ws_bytes, L.stream_ptr()),
                         "lrx_ppo_update")
                 count += nb
                 continue

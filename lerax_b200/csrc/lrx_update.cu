@@ -152,30 +152,43 @@ __global__ void gather_kernel(LrxBatchView buf, const int32_t* __restrict__ idx,
 }
 
 // ========================================================================== adv sums
-__global__ void adv_sums_kernel(const float* __restrict__ adv, int N, int T,
-                                const int32_t* __restrict__ idx, long long B, double* sums) {
-  const int b = blockIdx.y;
+// One block per minibatch, every thread a fixed strided subset of its rows, fixed-order tree: the sums -- and with them
+// the normalised advantages and every gradient -- are bitwise reproducible (no atomics, no memset).
+__global__ void __launch_bounds__(1024)
+adv_sums_kernel(const float* __restrict__ adv, int N, int T, const int32_t* __restrict__ idx, long long B, double* sums) {
+  const int b = blockIdx.x;
   const int32_t* row = idx + (size_t)b * B;
   double s = 0, s2 = 0;
-  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < B;
-       m += (long long)gridDim.x * blockDim.x) {
-    const int i = row[m];
-    const int n = i / T, t = i - n * T;
-    const float a = adv[(size_t)t * N + n];
-    s += a;
-    s2 += (double)a * a;
+  constexpr int U = 8;  // gathered loads in flight per thread
+  for (long long m0 = threadIdx.x; m0 < B; m0 += (long long)U * blockDim.x) {
+    float a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long m = m0 + (long long)u * blockDim.x;
+      a[u] = 0.f;
+      if (m < B) {
+        const int i = __ldg(row + m);
+        const int n = i / T, t = i - n * T;
+        a[u] = __ldg(adv + (size_t)t * N + n);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      s += a[u];
+      s2 += (double)a[u] * a[u];
+    }
   }
   s = warp_sum(s);
   s2 = warp_sum(s2);
-  __shared__ double sh[2][8];
+  __shared__ double sh[2][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) { sh[0][w] = s; sh[1][w] = s2; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double a = 0, c = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh[0][i]; c += sh[1][i]; }
-    atomicAdd(sums + 2 * b, a);
-    atomicAdd(sums + 2 * b + 1, c);
+    double x = 0, c = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { x += sh[0][i]; c += sh[1][i]; }
+    sums[2 * b] = x;
+    sums[2 * b + 1] = c;
   }
 }
 
@@ -718,12 +731,8 @@ extern "C" int lrx_ppo_adv_sums(const float* adv, int32_t N, int32_t T, const in
   LRX_REQUIRE(adv && idx && sums && N > 0 && T > 0 && num_batches >= 0 && B > 0, LRX_ERR_INVALID_ARG,
               "lrx_ppo_adv_sums: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
-  LRX_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)num_batches * 2 * sizeof(double), s));
   if (num_batches == 0) return LRX_OK;
-  int bx = (int)((B + 256 * 8 - 1) / (256 * 8));
-  if (bx < 1) bx = 1;
-  if (bx > 64) bx = 64;
-  adv_sums_kernel<<<dim3(bx, num_batches), 256, 0, s>>>(adv, N, T, idx, B, sums);
+  adv_sums_kernel<<<num_batches, 1024, 0, s>>>(adv, N, T, idx, B, sums);
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }
@@ -937,6 +946,15 @@ extern "C" int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* ad
                               int32_t num_batches, int64_t B, const LrxPpoHyper* h, float* stats_out,
                               int32_t* nonfinite_flag, void* workspace, size_t workspace_bytes,
                               lrx_stream_t stream) {
+  return lrx_ppo_update_schedule(pol, params, adam_m, adam_v, adam_count, buf, idx, num_batches, B, h, nullptr, stats_out,
+                                 nonfinite_flag, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lrx_ppo_update_schedule(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
+                                       int32_t* adam_count, const LrxBatchView* buf, const int32_t* idx,
+                                       int32_t num_batches, int64_t B, const LrxPpoHyper* h,
+                                       const float* learning_rates_host, float* stats_out, int32_t* nonfinite_flag,
+                                       void* workspace, size_t workspace_bytes, lrx_stream_t stream) {
   int rc = validate_update_args(pol, buf, h);
   if (rc) return rc;
   LRX_REQUIRE(num_batches >= 0 && num_batches <= LRX_MAX_BATCHES, LRX_ERR_INVALID_ARG,
@@ -959,6 +977,7 @@ extern "C" int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* ad
     // default widths: one fused gradient launch + one reduce/clip/Adam launch per minibatch
     bool handled = false;
     ap.stats_out = stats_out + (size_t)b * LRX_PPO_NSTATS;
+    if (learning_rates_host) ap.h.learning_rate = learning_rates_host[b];  // optax inject_hyperparams: a schedule of the count
     LRX_REQUIRE(!h->normalize_advantages || adv_sums, LRX_ERR_INVALID_ARG, "adv_sums missing");
     rc = lrx_ppo_grad_tensor(pol, params, buf, idx + (size_t)b * B, B, B, adv_sums + 2 * b, h, gradbuf, workspace,
                              tail.adv_sums_off, (cudaStream_t)stream, &handled, &ap);
@@ -969,7 +988,7 @@ extern "C" int lrx_ppo_update(const LrxPolicyDesc* pol, float* params, float* ad
     if (rc) return rc;
     {
       PolicyTable tab = lrx_make_table(*pol);
-      rc = launch_apply(params, adam_m, adam_v, adam_count, gradbuf, pol->n_params, tab.log_std_off, *h,
+      rc = launch_apply(params, adam_m, adam_v, adam_count, gradbuf, pol->n_params, tab.log_std_off, ap.h,
                         stats_out + (size_t)b * LRX_PPO_NSTATS, nonfinite_flag, (cudaStream_t)stream, ap.blk_ss);
       if (rc) return rc;
       LRX_LAUNCH_CHECK();
