@@ -62,3 +62,12 @@ def iteration_scalars(state: dict) -> dict:
         "episode/length": float(state["average_length"].astype(np.float32).mean(dtype=np.float32)),
         "step": int(state["step"].sum()),
     }
+
+
+def adaptive_curriculum_step_state(metric0, step_values, dones):
+    """AbstractAdaptiveCurriculum.on_step scanned over T (curriculum/adaptive.py:64-70), per env:
+    episode_metric = where(done, 0, episode_metric + metric_fn(done, reward, locals)).  step_values, dones: [T, N]."""
+    m = np.asarray(metric0, np.float32).copy()
+    for t in range(step_values.shape[0]):
+        m = np.where(dones[t], np.float32(0.0), m + step_values[t].astype(np.float32)).astype(np.float32)
+    return m

@@ -86,3 +86,45 @@ def test_curriculum_changes_the_dynamics_the_rollout_sees():
         runs.append(tap.rewards)
     assert torch.equal(runs[0][0], runs[1][0])
     assert not torch.equal(runs[0][1], runs[1][1])
+
+
+def test_adaptive_curriculum_step_state_matches_reference_recurrence():
+    """AdaptiveCurriculumStepState (curriculum/adaptive.py:64-70) replayed from the rollout's (reward, done) buffers ==
+    the step-by-step accumulation (oracle/callback.py), bit for bit; metric_fn sees the whole [T][N] buffers."""
+    import torch
+
+    from lerax_b200.curriculum import AdaptiveCurriculumStepState, LevelCurriculum
+    from oracle import callback as OC
+
+    rng = np.random.default_rng(3)
+    T, N = 37, 21
+    rew = rng.standard_normal((T, N)).astype(np.float32)
+    done = rng.random((T, N)) < 0.15
+    m0 = rng.standard_normal(N).astype(np.float32)
+    cur = LevelCurriculum(where=lambda env: env.max_speed, levels=[4.0, 6.0, 8.0],
+                          metric_fn=lambda d, r, loc: r * 2.0 + d.to(r.dtype), threshold=1.0)
+    st = AdaptiveCurriculumStepState(torch.from_numpy(m0).cuda())
+    out = cur.advance_step_state(st, torch.from_numpy(rew).cuda(), torch.from_numpy(done.astype(np.uint8)).cuda(), N, T)
+    want = OC.adaptive_curriculum_step_state(m0, rew * np.float32(2.0) + done.astype(np.float32), done)
+    np.testing.assert_array_equal(out.episode_metric.cpu().numpy(), want)
+
+
+def test_level_curriculum_through_learn():
+    """LevelCurriculum (adaptive.py:121-173) in PPO.learn: the env field steps through the levels as the running metric
+    crosses the threshold, and the rewritten field reaches the kernels."""
+    from lerax_b200.algorithm import PPO
+    from lerax_b200.curriculum import LevelCurriculum
+
+    env, policy, learn_key = _setup(4)
+    # Pendulum rewards are <= 0: the metric -reward is >= 0 and accumulates to well above the threshold within an iteration
+    cur = LevelCurriculum(where=lambda env: env.max_speed, levels=[4.0, 6.0, 8.0], metric_fn=lambda d, r, loc: -r,
+                          threshold=5.0, smoothing=0.5)
+    algo = PPO(num_envs=2, num_steps=32, num_epochs=1, num_batches=2)
+    trained = algo.learn(env, policy, total_timesteps=2 * 32 * 1, key=learn_key, callback=cur)
+    assert trained is not None
+    st = algo.last_state  # one iteration: the running metric 0.5 * (sum of -reward) crossed 5 -> level 0 -> 1
+    assert st.callback_state.level == 1 and st.env.max_speed == pytest.approx(6.0) and env.max_speed == 8.0
+    assert st.env.desc().p[0] == np.float32(6.0)  # what the next rollout launch receives
+    assert float(st.step_state.callback_state.episode_metric.min()) >= 0.0
+    algo.learn(env, policy, total_timesteps=2 * 32 * 5, key=learn_key, callback=cur)
+    assert algo.last_state.callback_state.level == 2 and algo.last_state.env.max_speed == pytest.approx(8.0)  # capped at the last level
