@@ -504,7 +504,8 @@ def run_sweep(args):
             gae_ms = tot / 5
             # CPU oracle on a bounded strip of the same arrays
             nc = min(N, 4096)
-            rc, vc, dc, lc = (x[:, :nc].cpu().numpy() for x in (r, v, d)) + (lv[:nc].cpu().numpy(),)
+            rc, vc, dc = (x[:, :nc].cpu().numpy() for x in (r, v, d))
+            lc = lv[:nc].cpu().numpy()
             t0 = time.perf_counter(); OG.gae(rc, vc, dc.astype(bool), lc, 0.99, 0.95); cpu_s = time.perf_counter() - t0
             del r, v, d, adv, ret
             # one epoch of PPO updates (32 minibatches) on a rollout produced by the kernel itself

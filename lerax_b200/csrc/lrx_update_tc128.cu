@@ -159,13 +159,42 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
   const tc2::Mat DY64{smem + OFF_DY64, ROWS, 8 * CG}, DY16{smem + OFF_DY16, ROWS, 2 * CG};
 
   // ------------------------------------------------------------------ one-time staging
-  tc2::stage_weight(a.params + a.lo.w[tc::L_ENC1], 64, 64, 64, W1, tid, THREADS);
-  tc2::stage_weight(a.params + a.lo.w[tc::L_ENC2], 16, 64, 64, W2, tid, THREADS);
-  tc2::stage_weight(a.params + a.lo.w[tc::L_V0], 64, 16, 16, WV0, tid, THREADS);
-  tc2::stage_weight(a.params + a.lo.w[tc::L_V1], 64, 64, 64, WV1, tid, THREADS);
-  tc2::stage_weight(a.params + a.lo.w[tc::L_A0], 64, 16, 16, WA0, tid, THREADS);
-  tc2::stage_weight(a.params + a.lo.w[tc::L_A1], 16, 64, 64, WA1, tid, THREADS);
-  tc::stage_f32(a.params, a.lo, n_out, a.obs_dim, fp, tid, THREADS);
+  {
+    // The six tensor-core weight matrices are 1536 chunks of 8 consecutive inputs of one output unit.  Every thread issues
+    // the loads of ALL its chunks (<= 3) before converting any: one L2 round trip for the whole staging instead of one per
+    // matrix (six dependent round trips were 8 k cycles of every launch).
+    constexpr int NCH = 512 + 128 + 128 + 512 + 128 + 128, PER = (NCH + THREADS - 1) / THREADS;
+    const uint32_t base[6] = {OFF_W1, OFF_W2, OFF_WV0, OFF_WV1, OFF_WA0, OFF_WA1}, lo_off[6] = {8192, 2048, 2048, 8192, 2048, 2048};
+    const int lay[6] = {tc::L_ENC1, tc::L_ENC2, tc::L_V0, tc::L_V1, tc::L_A0, tc::L_A1};
+    const int outs[6] = {64, 16, 64, 64, 64, 16}, ins[6] = {64, 64, 16, 64, 16, 64};
+    const int first[7] = {0, 512, 640, 768, 1280, 1408, 1536};
+    float v[PER][8];
+    int mi[PER], oo[PER], cc[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int e = tid + k * THREADS;
+      mi[k] = -1;
+      if (e < NCH) {
+        int m6 = 0;
+#pragma unroll
+        for (int j = 1; j < 6; ++j) m6 += (e >= first[j]) ? 1 : 0;
+        const int el = e - first[m6];
+        mi[k] = m6; oo[k] = el % outs[m6]; cc[k] = el / outs[m6];
+        const float* src = a.params + a.lo.w[lay[m6]] + (size_t)oo[k] * ins[m6] + cc[k] * 8;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(src)), y = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          v[k][0] = x.x; v[k][1] = x.y; v[k][2] = x.z; v[k][3] = x.w; v[k][4] = y.x; v[k][5] = y.y; v[k][6] = y.z; v[k][7] = y.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[k][j] = __ldg(src + j);
+        }
+      }
+    }
+    tc::stage_f32(a.params, a.lo, n_out, a.obs_dim, fp, tid, THREADS);  // its loads join the ones in flight
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+      if (mi[k] >= 0) tc2::store8(tc2::Mat{smem + base[mi[k]], (uint32_t)outs[mi[k]], lo_off[mi[k]]}, cc[k], oo[k], v[k]);
+  }
   if (tid < ROWS) {  // the constant ones columns (bf16 1.0 = 0x3F80 in element 0 of the extra c-group)
     const uint4 one = make_uint4(0x00003F80u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(XOBS.ptr + 1 * CG + tid * 16) = one;
