@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 
 METRIC = "env-steps/sec (rollout+GAE+PPO update)"
 UNIT = "env-steps/s"
-UPDATE_KERNEL = "ppo_grad_fused_kernel"  # the tensor-core gradient kernel default-width policies run (profiles/kernels.json key)
+UPDATE_KERNEL = "ppo_grad_tc128_kernel"  # the tensor-core gradient kernel default-width policies run (profiles/kernels.json key)
 
 WIDE = dict(feature_width=256, value_width=256, action_width=256)
 # name -> env, envs (per GPU for weak scaling, TOTAL for strong), horizon, epochs, minibatches, policy kwargs, scaling
@@ -280,6 +280,43 @@ def parity_check(algo, state, buf, world, dist):
             "max_param_step": moved, "exchange": "nvlink-p2p" if getattr(algo, "_ex", None) is not None else "nccl"}
 
 
+def grad_launch_alone_us(algo, state, buf, world):
+    """The dominant kernel by itself: one epoch's minibatches through `lrx_ppo_grad` only (gradient kernel + partial
+    reduction into gradbuf; no exchange, no clip, no Adam -- the parameters do not move), CUDA events on the launching
+    stream.  Returns (us per launch pair, launches)."""
+    import torch
+
+    from lerax_b200 import _lib as L
+    from lerax_b200 import random as jr
+
+    b = algo._bufs
+    view = buf.view(packed=b.get("packed"))
+    B_global = algo.batch_size
+    B_local = B_global // world
+    idx = buf.batch_indices(B_local, key=jr.key(12345))[: algo.minibatches_per_epoch]
+    nb = idx.shape[0]
+    L.check(L.lib.lrx_ppo_adv_sums(view.adv, view.N, view.T, L.ptr(idx), nb, B_local, L.ptr(b["adv_sums"]), L.stream_ptr()),
+            "lrx_ppo_adv_sums")
+    pol_d, h = state.policy.desc(), algo._hyper(algo._lr_at(0))
+    ws, ws_bytes = L.ptr(b["workspace"]), b["workspace"].numel()
+
+    def epoch():
+        for i in range(nb):
+            L.check(L.lib.lrx_ppo_grad(pol_d, L.ptr(state.policy.params), view, L.ptr(idx[i]), B_local, B_global,
+                                       L.ptr(b["adv_sums"][i]), h, L.ptr(b["gradbuf"]), ws, ws_bytes, L.stream_ptr()),
+                    "lrx_ppo_grad")
+
+    epoch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    epoch()
+    epoch()
+    e1.record()
+    torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / (2 * nb), 2 * nb
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -365,6 +402,9 @@ def run_ours(args):
     value = steps_per_iter / (ms_per_step / 1e3)
 
     par = parity_check(algo, state, buf, world, dist) if world > 1 else None
+    grad_us = grad_launch_alone_us(algo, state, buf, world) if rank == 0 and algo.minibatches_per_epoch > 0 else None
+    if world > 1:
+        dist.barrier()
 
     # ---- end to end through the public API with HOST parameters: learn() for one iteration
     e2e = None
@@ -436,6 +476,13 @@ def run_ours(args):
                          "for the Tsit5 step) / CUDA-event time of the stage over the timed region; peak = sustained bf16 "
                          "tensor throughput. `traffic`, `executed_*` come from the committed ncu capture of this kernel and "
                          "shape (profiles/kernels.json) and are null when that shape was never captured"})
+    if dominant == "update" and grad_us is not None:
+        roof.update({"kernel_us_alone": grad_us[0], "kernel_launches_alone": grad_us[1],
+                     "achieved_kernel_alone": 2.0 * (fwd + dw + dx) * mb_rows / (grad_us[0] * 1e-6) / 1e12,
+                     "frac_kernel_alone": 2.0 * (fwd + dw + dx) * mb_rows / (grad_us[0] * 1e-6) / 1e12 / peaks["tflops"],
+                     "kernel_alone_note": "lrx_ppo_grad only (gradient kernel(s) + partial reduction), 2 epochs of minibatches "
+                                          "back to back after the timed region; `achieved` above divides by the whole update "
+                                          "stage (also advantage sums, permutation, clip + Adam)"})
     if prof and prof.get("executed_flop_per_row_epoch") and dominant == "update":
         executed = prof["executed_flop_per_row_epoch"] * mb_rows * n_mb / (upd_ms / 1e3) / 1e12
         roof.update({"executed_tflops": executed, "executed_frac": executed / peaks["tflops"], "profile": prof.get("source")})

@@ -4,164 +4,339 @@
 //
 //     C[M x N] (+)= op(A)[M x K] * op(B)[K x N]      fp32 in HBM, two-piece bf16 emulation on the tensor cores
 //
-// One CTA = one 128 x (<= 256) accumulator in TMEM.  The inputs are fp32 in global memory in either orientation; a K
-// chunk of 64 of both operands is read with 32-byte accesses along the contiguous axis, split into bf16 hi / lo
-// (lrx_tc2.cuh) and written into the canonical no-swizzle layout, which serves as a K-major operand when K is the
-// contiguous axis and as an MN-major operand when the M/N index is -- so all four orientations of sgemm_kernel<AT, BT>
-// feed tcgen05.mma without a transpose.  SWAP decides which index of C rides on the 128 TMEM lanes:
+// One CTA (512 threads, one per SM) = one 128 x (<= 288) accumulator in TMEM, walked over K in chunks of 32 through a
+// two-deep asynchronous pipeline.  These GEMMs are HBM / latency bound (a 65 536-row minibatch of 256-wide activations
+// is 67 MB per operand, nothing stays in L2), so the structure is built around keeping loads in flight:
+//   1. cp.async (LDGSTS, zero-filling the ragged edges) copies the raw fp32 chunk k+1 / k+2 of both operands from
+//      global memory straight into a shared-memory ring -- no registers, so 50 - 100 KB per SM are in flight while
+//   2. all 16 warps convert chunk k from the ring to bf16 hi / lo (lrx_tc2.cuh) in the canonical no-swizzle layout,
+//      which serves as a K-major operand when K is the contiguous axis of the source and as an MN-major operand when
+//      the M/N index is -- so all four orientations of sgemm_kernel<AT, BT> feed tcgen05.mma without a transpose --
+//   3. one elected thread issues the MMAs of chunk k (3 products hi*lo + lo*hi + hi*hi per 16-wide K step) and commits
+//      them to the mbarrier that frees chunk k's operand buffer two chunks later.
+// (The first version staged through registers, 4 x 32 bytes in flight per thread, and waited for every chunk's MMAs:
+// ncu showed 40 - 55 % of the stall samples on the first use of a loaded value, 0.66 TB/s, tensor pipe 0.5 - 2 %; its
+// dX epilogue read the ReLU mask one dependent load at a time.)
+// SWAP decides which index of C rides on the 128 TMEM lanes:
 //   SWAP = 1 (forward / dX: N = minibatch rows, M = layer width): lanes = j, columns = i -> C[i][j] is written with
 //            consecutive lanes on consecutive addresses (coalesced);
-//   SWAP = 0 (weight gradients: M = out, N = in + 1, K = rows, split-K): lanes = i, columns = j.
-// A CTA is not software pipelined: stage -> MMA -> commit -> next chunk; two CTAs share an SM (96 KB of shared memory,
-// 256 TMEM columns each) so that one's staging runs under the other's MMAs.
+//   SWAP = 0 (weight gradients: M = out, N = in + 1 <= 288 in ONE column tile, K = rows, split-K): lanes = i.
+// The raw ring keeps 16-byte chunk p of row r at position p ^ (r & 7): both the LDGSTS writes (lanes along a row) and the
+// converters' reads (a quarter-warp = 8 rows of one chunk column) are bank-conflict free.
 #include "lrx_common.cuh"
 #include "lrx_gemm.cuh"
 #include "lrx_tc2.cuh"
 
 namespace {
 
-constexpr int KC = 64;          // K chunk
+constexpr int KC = 32;          // K chunk
 constexpr int UM = 128;         // UMMA M (TMEM lanes)
-constexpr int UN_MAX = 256;     // UMMA N per accumulator
-constexpr int THREADS = 256;
-// shared memory: operand X (UMMA A, 128 mn) and operand Y (UMMA B, <= 256 mn), each hi | lo
-constexpr uint32_t X_PIECE = UM * KC * 2, Y_PIECE = UN_MAX * KC * 2;
-constexpr uint32_t OFF_X = 0, OFF_Y = OFF_X + 2 * X_PIECE, OFF_MISC = OFF_Y + 2 * Y_PIECE;
+constexpr int UN_MAX = 288;     // accumulator columns per CTA: one MMA of N <= 256 plus one of N <= 32
+constexpr int THREADS = 512;
+constexpr uint32_t RAW_X = UM * KC * 4, RAW_Y = UN_MAX * KC * 4;              // fp32 ring, per stage
+constexpr uint32_t CAN_X_PIECE = UM * KC * 2, CAN_Y_PIECE = UN_MAX * KC * 2;  // bf16 operand pieces, per stage
+constexpr uint32_t STAGE_RAW = RAW_X + RAW_Y, STAGE_CAN = 2 * CAN_X_PIECE + 2 * CAN_Y_PIECE;
+constexpr uint32_t OFF_RAW = 0, OFF_CAN = 2 * STAGE_RAW, OFF_MISC = OFF_CAN + 2 * STAGE_CAN;
 constexpr uint32_t SMEM_BYTES = OFF_MISC + 64;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 // Source of one UMMA operand: element (mn, k) of op(.) lives at base[mn * s_mn + k * s_k]; exactly one stride is 1.
 struct Src {
   const float* base;
   long long s_mn, s_k;
   int mn_total;
+  int al16;  // every 4-element group along the contiguous axis starts on a 16-byte boundary
 };
 
-// Stage rows [mn0, mn0 + mn_tile) x [k0, k0 + KC) (zero filled outside [0, mn_total) x [k0, kend)) into `dst`.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 4 consecutive elements (`valid` of them inside the matrix, the rest zero filled) -> one 16-byte ring chunk
+__device__ __forceinline__ void copy4(uint32_t dst, const float* src, int valid, int al16) {
+  if (al16) {
+    cp_async16(dst, src, valid * 4);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cp_async4(dst + 4 * e, e < valid ? src + e : src, e < valid ? 4 : 0);
+  }
+}
+
+__device__ __forceinline__ uint32_t ring_pitch(bool mn_contig, int mn_tile) {  // bytes per ring row, a multiple of 128
+  return mn_contig ? (uint32_t)((mn_tile * 4 + 127) & ~127) : (uint32_t)(KC * 4);
+}
+
+// Everything about one thread's copies and conversions that does not depend on the K chunk is worked out ONCE per CTA (the
+// chunk loop is instruction-issue bound: ~8 instructions per 16-byte copy and ~30 per converted unit is what is left).
+constexpr int NXC = UM * (KC / 4) / THREADS;                         // 16-byte copies per thread and chunk, X operand
+constexpr int NYC = (UN_MAX * (KC / 4) + THREADS - 1) / THREADS;     // ... Y operand (the last ones may be idle)
+constexpr int NXU = UM * (KC / 8) / THREADS;                         // converted units per thread and chunk, X operand
+constexpr int NYU = (UN_MAX * (KC / 8) + THREADS - 1) / THREADS;
+static_assert(NXC * THREADS == UM * (KC / 4) && NXU * THREADS == UM * (KC / 8), "X work divides evenly");
+
+struct CopyPlan {
+  const float* src;  // first element of the 4-element group in chunk 0; advanced by one chunk per issue
+  uint32_t dst;      // byte offset inside the operand's ring stage
+  int vmn;           // valid elements along mn: -1 = no copy at all, 0 = zero fill (row outside the matrix)
+  int kpos;          // k offset of the group inside a chunk (k contiguous: first of its 4 k; mn contiguous: its k row)
+};
+
+// 16-byte copy number `id` of rows [mn0, mn0 + mn_tile) x [kbeg + chunk * KC, ...) of one operand.
+//   k contiguous : ring row = mn, KC floats     mn contiguous: ring row = k, mn_tile floats (pitch rounded up to 128 B)
+template <bool MN_CONTIG>
+__device__ __forceinline__ CopyPlan plan_copy(const Src& s, int mn0, int mn_tile, int kbeg, int id) {
+  CopyPlan c;
+  if (!MN_CONTIG) {
+    const int r = id >> 3, p = id & 7, mn = mn0 + r;
+    c.vmn = id < mn_tile * (KC / 4) ? (mn < s.mn_total ? 4 : 0) : -1;
+    c.src = c.vmn > 0 ? s.base + (long long)mn * s.s_mn + kbeg + p * 4 : s.base;
+    c.dst = (uint32_t)r * (KC * 4) + (uint32_t)((p ^ (r & 7)) << 4);
+    c.kpos = p * 4;
+  } else {
+    const int cpr = mn_tile >> 2;  // 16-byte chunks per ring row
+    const int r = id / cpr, p = id - r * cpr, mn = mn0 + p * 4;
+    const int v = s.mn_total - mn;
+    c.vmn = id < KC * cpr ? (v < 0 ? 0 : (v > 4 ? 4 : v)) : -1;
+    c.src = c.vmn > 0 ? s.base + (long long)(kbeg + r) * s.s_k + mn : s.base;
+    c.dst = (uint32_t)r * ring_pitch(true, mn_tile) + (uint32_t)((p ^ (r & 7)) << 4);
+    c.kpos = r;
+  }
+  return c;
+}
+
+// Start copy `c` for the chunk whose first k is `krem` short of kend; `raw` = shared address of the operand's ring stage.
+template <bool MN_CONTIG>
+__device__ __forceinline__ void issue_copy(CopyPlan& c, const Src& s, uint32_t raw, int krem, long long kadv) {
+  if (c.vmn < 0) return;
+  int valid;
+  if (!MN_CONTIG) {
+    valid = krem - c.kpos;
+    valid = c.vmn == 0 || valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+  } else {
+    valid = c.kpos < krem ? c.vmn : 0;
+  }
+  const float* src = valid ? c.src : s.base;
+  if (s.al16) {
+    cp_async16(raw + c.dst, src, valid * 4);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cp_async4(raw + c.dst + 4 * e, e < valid ? src + e : s.base, e < valid ? 4 : 0);
+  }
+  c.src += kadv;
+}
+
+struct UnitPlan {
+  uint32_t src;  // ring offset of the first of the two 16-byte chunks (its partner is at src ^ 16)
+  uint32_t dst;  // canonical offset of the unit in the hi piece; 0xFFFFFFFF = idle
+};
+
+// Unit = 8 elements along the contiguous axis.  A quarter-warp takes 8 ring rows of one unit column: conflict-free 16-byte
+// reads through the XOR placement, and 8 consecutive 16-byte rows of one canonical chunk column on the way out.
 //   k contiguous : matrix r = mn, c = k   (R = mn_tile rows)  -> K-major operand
 //   mn contiguous: matrix r = k,  c = mn  (R = KC rows)       -> MN-major operand
 template <bool MN_CONTIG>
-__device__ __forceinline__ void stage(const Src& s, int mn0, int mn_tile, int k0, int kend, const tc2::Mat& dst, int tid) {
-  const int R = MN_CONTIG ? KC : mn_tile;
-  const int chunks = (MN_CONTIG ? mn_tile : KC) >> 3;
-  const int total = R * chunks;
-  constexpr int U = 4;  // 16-byte-chunk pairs in flight per thread: the loads of U chunks are issued before any is converted
-  for (int e0 = tid; e0 < total; e0 += U * THREADS) {
-    float v[U][8];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int e = e0 + u * THREADS;
-      const int r = e % R, ch = e / R;
-      // (mn, k) of the first of the 8 contiguous elements; `lim` = valid elements along the contiguous axis
-      const int mn = MN_CONTIG ? mn0 + ch * 8 : mn0 + r, k = MN_CONTIG ? k0 + r : k0 + ch * 8;
-      const bool row_ok = e < total && (MN_CONTIG ? k < kend : mn < s.mn_total);
-      const int lim = row_ok ? (MN_CONTIG ? s.mn_total - mn : kend - k) : 0;
-      const float* src = s.base + (MN_CONTIG ? (long long)k * s.s_k + mn : (long long)mn * s.s_mn + k);
-      if (lim >= 8 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[u][j] = j < lim ? __ldg(src + j) : 0.f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int e = e0 + u * THREADS;
-      if (e < total) tc2::store8(dst, e / R, e % R, v[u]);
-    }
+__device__ __forceinline__ UnitPlan plan_unit(int mn_tile, int u) {
+  UnitPlan p;
+  const int chunks = MN_CONTIG ? mn_tile >> 3 : KC / 8;
+  const int cb_shift = (chunks & 3) ? 1 : 2;
+  const int r8 = u & 7, cl = (u >> 3) & ((1 << cb_shift) - 1), blk = u >> (3 + cb_shift);
+  int r, ch;
+  if (MN_CONTIG) {  // KC / 8 = 4 row blocks
+    r = ((blk & 3) << 3) | r8;
+    ch = ((blk >> 2) << cb_shift) | cl;
+  } else {          // 4 unit columns per row: blk = row block
+    r = (blk << 3) | r8;
+    ch = cl;
   }
+  const uint32_t R = MN_CONTIG ? KC : mn_tile;
+  p.src = (uint32_t)r * ring_pitch(MN_CONTIG, mn_tile) + (uint32_t)(((2 * ch) ^ r8) << 4);
+  p.dst = u < mn_tile * (KC / 8) ? (uint32_t)ch * (R * 16u) + (uint32_t)r * 16u : 0xFFFFFFFFu;
+  return p;
+}
+
+__device__ __forceinline__ void convert_unit(const UnitPlan& p, const uint8_t* raw, uint8_t* can, uint32_t lo_off) {
+  if (p.dst == 0xFFFFFFFFu) return;
+  const float4 a = *reinterpret_cast<const float4*>(raw + p.src);
+  const float4 b = *reinterpret_cast<const float4*>(raw + (p.src ^ 16u));
+  uint32_t h[4], l[4];
+  tc2::split2(a.x, a.y, h[0], l[0]);
+  tc2::split2(a.z, a.w, h[1], l[1]);
+  tc2::split2(b.x, b.y, h[2], l[2]);
+  tc2::split2(b.z, b.w, h[3], l[3]);
+  *reinterpret_cast<uint4*>(can + p.dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(can + p.dst + lo_off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // X_MN / Y_MN: the UMMA A / B operand's source has the MN index contiguous (-> MN-major descriptor).
 template <bool SWAP, bool X_MN, bool Y_MN>
-__global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, const int x_al16, const int y_al16) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_MISC);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_MISC);  // [2]: the MMAs that read operand stage s are done
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 16);
 
-  // tile of C: x -> the index on the TMEM lanes (128 per CTA), y -> the index on the TMEM columns (<= 256 per CTA)
+  // tile of C: x -> the index on the TMEM lanes (128 per CTA), y -> the index on the TMEM columns (<= 288 per CTA)
   const int x_total = SWAP ? g.N : g.M, y_total = SWAP ? g.M : g.N;
   const int x0 = blockIdx.x * UM;
   const int y0 = blockIdx.y * UN_MAX;
   const int y_cnt = min(UN_MAX, y_total - y0);
   const int un = (y_cnt + 15) & ~15;  // UMMA N: multiple of 16 for M = 128
+  const int n1 = min(un, 256), n2 = un - n1;
   const int kbeg = blockIdx.z * g.k_chunk;
   const int kend = min(g.K, kbeg + g.k_chunk);
+  const int nk = kend > kbeg ? (kend - kbeg + KC - 1) / KC : 0;
 
   // op(A)[i][k]: AT ? A[k * lda + i] : A[i * lda + k];   op(B)[k][j]: BT ? B[j * ldb + k] : B[k * ldb + j]
   // X carries the lane index (SWAP: j from B, else i from A), Y the column index.
   Src sx, sy;
   if (SWAP) {
-    sx = Src{g.B, X_MN ? 1 : g.ldb, X_MN ? g.ldb : 1, g.N};  // mn = j
-    sy = Src{g.A, Y_MN ? 1 : g.lda, Y_MN ? g.lda : 1, g.M};  // mn = i
+    sx = Src{g.B, X_MN ? 1 : g.ldb, X_MN ? g.ldb : 1, g.N, x_al16};  // mn = j
+    sy = Src{g.A, Y_MN ? 1 : g.lda, Y_MN ? g.lda : 1, g.M, y_al16};  // mn = i
   } else {
-    sx = Src{g.A, X_MN ? 1 : g.lda, X_MN ? g.lda : 1, g.M};
-    sy = Src{g.B, Y_MN ? 1 : g.ldb, Y_MN ? g.ldb : 1, g.N};
+    sx = Src{g.A, X_MN ? 1 : g.lda, X_MN ? g.lda : 1, g.M, x_al16};
+    sy = Src{g.B, Y_MN ? 1 : g.ldb, Y_MN ? g.ldb : 1, g.N, y_al16};
   }
-  const tc2::Mat X{smem + OFF_X, (uint32_t)(X_MN ? KC : UM), X_PIECE};
-  const tc2::Mat Y{smem + OFF_Y, (uint32_t)(Y_MN ? KC : un), Y_PIECE};
+  CopyPlan cx[NXC], cy[NYC];
+  UnitPlan ux[NXU], uy[NYU];
+#pragma unroll
+  for (int n = 0; n < NXC; ++n) cx[n] = plan_copy<X_MN>(sx, x0, UM, kbeg, tid + n * THREADS);
+#pragma unroll
+  for (int n = 0; n < NYC; ++n) cy[n] = plan_copy<Y_MN>(sy, y0, un, kbeg, tid + n * THREADS);
+#pragma unroll
+  for (int n = 0; n < NXU; ++n) ux[n] = plan_unit<X_MN>(UM, tid + n * THREADS);
+#pragma unroll
+  for (int n = 0; n < NYU; ++n) uy[n] = plan_unit<Y_MN>(un, tid + n * THREADS);
+  const long long kadv_x = X_MN ? (long long)KC * sx.s_k : KC, kadv_y = Y_MN ? (long long)KC * sy.s_k : KC;
+  const uint32_t smem_base = umma::smem_u32(smem);
+  auto issue = [&](int kc) {  // chunk kc -> ring stage kc & 1; called for kc = 0, 1, 2, ... in order
+    const uint32_t raw = smem_base + OFF_RAW + (uint32_t)(kc & 1) * STAGE_RAW;
+    const int krem = kend - (kbeg + kc * KC);
+#pragma unroll
+    for (int n = 0; n < NXC; ++n) issue_copy<X_MN>(cx[n], sx, raw, krem, kadv_x);
+#pragma unroll
+    for (int n = 0; n < NYC; ++n) issue_copy<Y_MN>(cy[n], sy, raw + RAW_X, krem, kadv_y);
+  };
 
   if (tid == 0) {
     umma::mbar_init(bar, 1);
+    umma::mbar_init(bar + 1, 1);
     umma::fence_mbar_init();
   }
-  if (warp == 0) umma::tmem_alloc(tslot, UN_MAX);
+  if (warp == 0) umma::tmem_alloc(tslot, 512);
+  if (nk > 0) issue(0);
+  cp_async_commit();
+  if (nk > 1) issue(1);
+  cp_async_commit();
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tb = *tslot;
 
-  uint32_t phase = 0, acc = 0;
-  for (int k0 = kbeg; k0 < kend; k0 += KC) {
-    stage<X_MN>(sx, x0, UM, k0, kend, X, tid);
-    stage<Y_MN>(sy, y0, un, k0, kend, Y, tid);
+  uint32_t phase[2] = {0u, 0u};
+  for (int kc = 0; kc < nk; ++kc) {
+    const int st = kc & 1;
+    uint8_t* can = smem + OFF_CAN + (uint32_t)st * STAGE_CAN;
+    const tc2::Mat X{can, (uint32_t)(X_MN ? KC : UM), CAN_X_PIECE};
+    const tc2::Mat Y{can + 2 * CAN_X_PIECE, (uint32_t)(Y_MN ? KC : un), CAN_Y_PIECE};
+    cp_async_wait<1>();  // this thread's copies of chunk kc have landed (chunk kc + 1 may still be in flight)
+    if (kc >= 2) {       // the MMAs of chunk kc - 2 have read operand stage st
+      umma::mbar_wait(bar + st, phase[st]);
+      phase[st] ^= 1u;
+      umma::tc_fence_after();
+    }
+    __syncthreads();     // every thread's copies of chunk kc are visible
+    const uint8_t* raw = smem + OFF_RAW + (uint32_t)st * STAGE_RAW;
+#pragma unroll
+    for (int n = 0; n < NXU; ++n) convert_unit(ux[n], raw, X.ptr, CAN_X_PIECE);
+#pragma unroll
+    for (int n = 0; n < NYU; ++n) convert_unit(uy[n], raw + RAW_X, Y.ptr, CAN_Y_PIECE);
     umma::fence_async_smem();
     umma::tc_fence_before();
-    __syncthreads();
+    __syncthreads();     // operand stage complete, ring stage st free
+    if (kc + 2 < nk) issue(kc + 2);
+    cp_async_commit();
     if (warp == 0) {
       umma::tc_fence_after();
       const bool leader = umma::elect_one();
-      const int ksteps = (min(KC, kend - k0) + 15) >> 4;  // zero-filled beyond kend
-      tc2::gemm<X_MN, Y_MN>(leader, tb, X, Y, UM, un, un, ksteps, acc);
-      if (leader) umma::mma_commit(bar);
+      const int ksteps = (min(KC, kend - (kbeg + kc * KC)) + 15) >> 4;  // zero-filled beyond kend
+      tc2::gemm<X_MN, Y_MN>(leader, tb, X, Y, UM, n1, n1, ksteps, kc > 0 ? 1u : 0u);
+      if (n2) {
+        const tc2::Mat Y2{Y.ptr + (Y_MN ? 32u * (KC * 16u) : 256u * 16u), Y.R, CAN_Y_PIECE};  // columns 256 ..
+        tc2::gemm<X_MN, Y_MN>(leader, tb + 256, X, Y2, UM, n2, n2, ksteps, kc > 0 ? 1u : 0u);
+      }
+      if (leader) umma::mma_commit(bar + st);
       __syncwarp();
     }
-    acc = 1u;
-    umma::mbar_wait(bar, phase);  // the MMAs have read the staging buffers: free for the next chunk
-    phase ^= 1u;
+  }
+  cp_async_wait<0>();
+  if (nk > 0) {  // the last commit covers every earlier MMA
+    umma::mbar_wait(bar + ((nk - 1) & 1), phase[(nk - 1) & 1]);
     umma::tc_fence_after();
   }
 
-  // ---- epilogue: warp w reads TMEM quadrant w & 3 (lanes = x), column half w >> 2
-  const int q = warp & 3, half = warp >> 2;
+  // ---- epilogue: warp w reads TMEM quadrant w & 3 (lanes = x), 16 of every 64 columns.  Element t of a group is
+  // C[i][j] with (i, j) = SWAP ? (yb + t, x) : (x, yb + t): base pointer + t * stride.
+  const int q = warp & 3, cgp = warp >> 2;
   const int x = x0 + q * 32 + lane;
+  const bool x_ok = x < x_total;
   const uint32_t tw = umma::tmem_addr(tb, q * 32, 0);
-  const int i_of = SWAP ? 0 : x, j_of = SWAP ? x : 0;  // the fixed index of this thread
   float* C = g.C + (size_t)blockIdx.z * g.c_split_stride;
   float* C2 = g.C2 ? g.C2 + (size_t)blockIdx.z * g.c_split_stride : nullptr;
-  const bool any_k = kend > kbeg;
-  for (int c0 = half * 16; c0 < un; c0 += 32) {
-    float v[16];
-    if (any_k) {
-      umma::tmem_ld16(tw + c0, v);
-      umma::tmem_ld_wait();
-    } else {
+  const size_t cstride = SWAP ? (size_t)g.ldc : 1, mstride = SWAP ? (size_t)g.ldm : 1;
+  const float bias_x = (!SWAP && g.bias && x_ok) ? __ldg(g.bias + x) : 0.f;
+  for (int c0 = cgp * 16; c0 < un; c0 += 64) {
+    float v[16], mk[16], old[16];
+    if (nk > 0) umma::tmem_ld16(tw + c0, v);
+    const int yb = y0 + c0;
+    const int ny = min(16, y_total - yb);  // valid elements of the group (<= 0: padding columns only)
+    const size_t off = SWAP ? (size_t)yb * g.ldc + x : (size_t)x * g.ldc + yb;
+    float* cp = C + off;
+    const float* mp = g.mask ? g.mask + (SWAP ? (size_t)yb * g.ldm + x : (size_t)x * g.ldm + yb) : nullptr;
+    // every global read of the group is issued before the first use (the mask and the accumulate target may alias C for
+    // all the compiler knows: interleaved with the stores they would be 16 dependent round trips to HBM)
+    if (x_ok && ny == 16 && !C2) {  // interior group, no redirected column: straight-line
 #pragma unroll
-      for (int t = 0; t < 16; ++t) v[t] = 0.f;
-    }
-    if (x < x_total) {
+      for (int t = 0; t < 16; ++t) mk[t] = mp ? __ldg(mp + t * mstride) : 1.f;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) old[t] = g.accumulate ? cp[t * cstride] : 0.f;
+      if (nk > 0) {
+        umma::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = 0.f;
+      }
 #pragma unroll
       for (int t = 0; t < 16; ++t) {
-        const int y = y0 + c0 + t;
-        if (y < y_total) {
-          const int i = SWAP ? y : i_of, j = SWAP ? j_of : y;
-          float r = v[t] + (g.bias ? __ldg(g.bias + i) : 0.f);
+        float r = v[t] + (SWAP ? (g.bias ? __ldg(g.bias + yb + t) : 0.f) : bias_x);
+        if (g.relu) r = fmaxf(r, 0.f);
+        r = mk[t] > 0.f ? r : 0.f;
+        cp[t * cstride] = r + old[t];
+      }
+    } else {
+      if (nk > 0) {
+        umma::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = 0.f;
+      }
+      if (x_ok) {
+#pragma unroll 1
+        for (int t = 0; t < ny; ++t) {
+          const int i = SWAP ? yb + t : x, j = SWAP ? x : yb + t;
+          float* dst = (C2 && j == g.n_main) ? (C2 + i) : (cp + t * cstride);
+          float r = v[0] + (g.bias ? __ldg(g.bias + i) : 0.f);
           if (g.relu) r = fmaxf(r, 0.f);
-          if (g.mask) r = (g.mask[(size_t)i * g.ldm + j] > 0.f) ? r : 0.f;
-          float* dst = (C2 && j == g.n_main) ? (C2 + i) : (C + (size_t)i * g.ldc + j);
+          if (mp) r = __ldg(mp + t * mstride) > 0.f ? r : 0.f;
           if (g.accumulate) r += *dst;
           *dst = r;
+#pragma unroll
+          for (int e = 0; e < 15; ++e) v[e] = v[e + 1];  // rotate: keeps v[] in registers under the rolled loop
         }
       }
     }
@@ -174,7 +349,11 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(const GemmArgs g) {
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tb, UN_MAX);
+  if (warp == 0) umma::tmem_dealloc(tb, 512);
+}
+
+static int aligned16(const float* base, long long stride_of_rows) {
+  return ((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride_of_rows & 3) == 0) ? 1 : 0;
 }
 
 template <bool SWAP, bool X_MN, bool Y_MN>
@@ -182,8 +361,12 @@ int launch(const GemmArgs& g, int splits, cudaStream_t s) {
   static bool attr_set[64];
   LRX_CUDA_CHECK(lrx_set_max_smem(tc_gemm_kernel<SWAP, X_MN, Y_MN>, (int)SMEM_BYTES, attr_set));
   const int x_total = SWAP ? g.N : g.M, y_total = SWAP ? g.M : g.N;
+  // the non-unit stride of each operand's source (rows of the ring are that far apart in global memory)
+  const float* xb = SWAP ? g.B : g.A;
+  const float* yb = SWAP ? g.A : g.B;
+  const int xl = SWAP ? g.ldb : g.lda, yl = SWAP ? g.lda : g.ldb;
   dim3 grid((x_total + UM - 1) / UM, (y_total + UN_MAX - 1) / UN_MAX, splits);
-  tc_gemm_kernel<SWAP, X_MN, Y_MN><<<grid, THREADS, SMEM_BYTES, s>>>(g);
+  tc_gemm_kernel<SWAP, X_MN, Y_MN><<<grid, THREADS, SMEM_BYTES, s>>>(g, aligned16(xb, xl), aligned16(yb, yl));
   return LRX_OK;
 }
 
@@ -194,11 +377,21 @@ int launch(const GemmArgs& g, int splits, cudaStream_t s) {
 int lrx_launch_gemm_tc(const GemmArgs& g, bool at, bool bt, int splits, cudaStream_t s, bool* handled) {
   *handled = false;
   if (lrx_fused_enabled() < 1) return LRX_OK;
-  const bool rows_on_n = g.N >= g.M;  // forward / dX: the minibatch rows are N; weight gradients: the rows are K
   // narrow layers (the d <= 8 first layer, scalar heads) ride along zero padded to the 16-wide MMA minimum: their cost is
   // the HBM pass over the wide operand, which the FMA kernel made at a sixth of the bandwidth.  Tiny problems stay on it.
   const long long big = (long long)(g.M > g.N ? g.M : g.N) * (g.K > 16 ? g.K : 16);
   if (g.M < 1 || g.N < 1 || g.K < 1 || big < 128 * 64) return LRX_OK;
+  // forward / dX: the minibatch rows are N and C's contiguous axis, so they ride on the lanes (coalesced stores).  Weight
+  // gradients (the rows are K, C is small): whichever orientation stages fewer operand rows -- out x (in + 1) with
+  // in + 1 <= 288 is one column tile per 128 outputs, not a third lane tile for the single bias column.
+  bool rows_on_n = g.N >= g.M;
+  if (g.K > g.M && g.K > g.N) {
+    auto cost = [](int x, int y) {
+      const long long xt = (x + UM - 1) / UM, yt = (y + UN_MAX - 1) / UN_MAX;
+      return xt * yt * (UM + (y < UN_MAX ? y : UN_MAX));
+    };
+    rows_on_n = cost(g.N, g.M) < cost(g.M, g.N) || (cost(g.N, g.M) == cost(g.M, g.N) && g.N >= g.M);
+  }
   int rc;
   if (rows_on_n) {
     // SWAP: X = op(B) (mn = j): contiguous in j unless BT;  Y = op(A) (mn = i): contiguous in i iff AT

@@ -1,7 +1,9 @@
 // Random permutation of [0, n) for the minibatch shuffle of buffer/base_buffer.py:85-88
 // (jr.permutation(key, N*T) in the reference; the RNG stream itself is not part of the parity
-// contract).  A keyed bijection instead of a sort: an 8-round balanced Feistel network on the
-// smallest even-bit domain >= n with cycle walking, so out[i] is computed independently per
+// contract).  A keyed bijection instead of a sort: 8 half-rounds of a (possibly unbalanced) Feistel
+// network on the smallest power-of-two domain >= n with cycle walking (fewer than two walks per
+// element on average, none when n is a power of two -- a balanced network on an even number of
+// bits made whole warps wait for their slowest lane), so out[i] is computed independently per
 // element in ONE pass over 4n bytes (torch.randperm's radix sort costs ~0.7 ms per epoch at
 // 8.4 M elements, this ~10 us).
 #include "lrx_common.cuh"
@@ -15,23 +17,21 @@ __device__ __forceinline__ uint32_t perm_mix(uint32_t x, uint32_t k) {
   return x;
 }
 
-__global__ void permutation_kernel(int32_t* __restrict__ out, long long n, uint32_t half_bits, uint32_t k0,
-                                   uint32_t k1) {
+__global__ void __launch_bounds__(256)
+permutation_kernel(int32_t* __restrict__ out, long long n, uint32_t lbits, uint32_t rbits, uint32_t k0, uint32_t k1) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t mask = (1u << half_bits) - 1u;
-  uint64_t x = (uint64_t)i;
-  do {  // cycle walking: the Feistel network permutes [0, 2^(2*half_bits)); re-apply until inside [0, n)
-    uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+  const uint32_t lmask = (1u << lbits) - 1u, rmask = (1u << rbits) - 1u;
+  uint32_t x = (uint32_t)i;
+  do {  // cycle walking: the network permutes [0, 2^(lbits+rbits)) with 2^(lbits+rbits) < 2n; re-apply until inside [0, n)
+    uint32_t l = x >> rbits, r = x & rmask;
 #pragma unroll
-    for (uint32_t round = 0; round < 8; ++round) {
-      const uint32_t f = perm_mix(r, (round & 1 ? k1 : k0) + round * 0x9E3779B9u) & mask;
-      const uint32_t nl = r;
-      r = l ^ f;
-      l = nl;
+    for (uint32_t round = 0; round < 4; ++round) {  // 8 half-rounds, alternating which side is rewritten
+      l ^= perm_mix(r, k0 + (2 * round) * 0x9E3779B9u) & lmask;
+      r ^= perm_mix(l, k1 + (2 * round + 1) * 0x9E3779B9u) & rmask;
     }
-    x = ((uint64_t)l << half_bits) | r;
-  } while (x >= (uint64_t)n);
+    x = (l << rbits) | r;
+  } while ((long long)x >= n);
   out[i] = (int32_t)x;
 }
 
@@ -40,9 +40,9 @@ extern "C" int lrx_permutation(int32_t* out, int64_t n, uint64_t seed, lrx_strea
   if (n == 0) return LRX_OK;
   LRX_REQUIRE(out, LRX_ERR_INVALID_ARG, "lrx_permutation: NULL pointer");
   uint32_t bits = 2;
-  while (((int64_t)1 << bits) < n) bits += 2;  // even number of bits: balanced halves
+  while (((int64_t)1 << bits) < n) ++bits;  // smallest domain >= n: no walk at all when n is a power of two
   const uint32_t k0 = (uint32_t)seed ^ 0xA511E9B3u, k1 = (uint32_t)(seed >> 32) ^ 0x63D83595u;
-  permutation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, bits / 2, k0, k1);
+  permutation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, bits - bits / 2, bits / 2, k0, k1);
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }

@@ -11,6 +11,7 @@
 // ones column).  The fused per-warp path for the default widths lives in
 // lrx_update_fused.cu and is tried first.
 #include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 #include "lrx_common.cuh"
 #include "lrx_gemm.cuh"
@@ -152,15 +153,19 @@ __global__ void gather_kernel(LrxBatchView buf, const int32_t* __restrict__ idx,
 }
 
 // ========================================================================== adv sums
-// One block per minibatch, every thread a fixed strided subset of its rows, fixed-order tree: the sums -- and with them
-// the normalised advantages and every gradient -- are bitwise reproducible (no atomics, no memset).
+// One thread-block CLUSTER per minibatch (up to 8 CTAs, so 32 minibatches fill the GPU instead of 32 SMs): every thread a
+// fixed strided subset of the rows, fixed-order tree inside the CTA, then CTA 0 of the cluster adds the CTA totals in rank
+// order through distributed shared memory.  The sums -- and with them the normalised advantages and every gradient -- are
+// bitwise reproducible (no atomics, no memset, no scratch).
 __global__ void __launch_bounds__(1024)
 adv_sums_kernel(const float* __restrict__ adv, int N, int T, const int32_t* __restrict__ idx, long long B, double* sums) {
-  const int b = blockIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned S = cluster.num_blocks(), rank = cluster.block_rank();
+  const int b = blockIdx.x / S;
   const int32_t* row = idx + (size_t)b * B;
   double s = 0, s2 = 0;
   constexpr int U = 8;  // gathered loads in flight per thread
-  for (long long m0 = threadIdx.x; m0 < B; m0 += (long long)U * blockDim.x) {
+  for (long long m0 = (long long)rank * U * blockDim.x + threadIdx.x; m0 < B; m0 += (long long)U * blockDim.x * S) {
     float a[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -181,15 +186,28 @@ adv_sums_kernel(const float* __restrict__ adv, int N, int T, const int32_t* __re
   s = warp_sum(s);
   s2 = warp_sum(s2);
   __shared__ double sh[2][32];
+  __shared__ double tot[2];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) { sh[0][w] = s; sh[1][w] = s2; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double x = 0, c = 0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { x += sh[0][i]; c += sh[1][i]; }
+    tot[0] = x;
+    tot[1] = c;
+  }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    double x = 0, c = 0;
+    for (unsigned k = 0; k < S; ++k) {
+      const double* peer = cluster.map_shared_rank(tot, k);
+      x += peer[0];
+      c += peer[1];
+    }
     sums[2 * b] = x;
     sums[2 * b + 1] = c;
   }
+  cluster.sync();  // the peers' shared memory must outlive CTA 0's reads
 }
 
 // =============================================================================== loss
@@ -732,8 +750,20 @@ extern "C" int lrx_ppo_adv_sums(const float* adv, int32_t N, int32_t T, const in
               "lrx_ppo_adv_sums: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   if (num_batches == 0) return LRX_OK;
-  adv_sums_kernel<<<num_batches, 1024, 0, s>>>(adv, N, T, idx, B, sums);
-  LRX_LAUNCH_CHECK();
+  unsigned S = 8;  // CTAs per minibatch: enough to fill the SMs, never more than the rows can feed
+  while (S > 1 && ((long long)num_batches * S > 2LL * lrx_sm_count() || B < (long long)S * 8 * 1024)) S >>= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)num_batches * S);
+  cfg.blockDim = dim3(1024);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LRX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, adv_sums_kernel, adv, (int)N, (int)T, idx, (long long)B, sums));
   return LRX_OK;
 }
 

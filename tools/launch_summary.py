@@ -9,10 +9,10 @@ from collections import OrderedDict
 def short(name: str) -> str:
     name = re.sub(r"<unnamed>::", "", name)
     name = re.sub(r"^void ", "", name)
+    if name.startswith("at::"):
+        return "torch elementwise / reduce kernels (host-side logging and the bench's own bookkeeping)"
     m = re.match(r"([A-Za-z0-9_:]+(<[^()]*>)?)\(", name)
     name = m.group(1) if m else name
-    if name.startswith("at::native::"):
-        return "torch elementwise / reduce kernels (host-side logging and the bench's own bookkeeping)"
     return "`" + name + "`"
 
 
