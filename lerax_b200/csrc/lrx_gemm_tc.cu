@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, c
     const float* mp = g.mask ? g.mask + (SWAP ? (size_t)yb * g.ldm + x : (size_t)x * g.ldm + yb) : nullptr;
     // every global read of the group is issued before the first use (the mask and the accumulate target may alias C for
     // all the compiler knows: interleaved with the stores they would be 16 dependent round trips to HBM)
-    if (x_ok && ny == 16 && !C2) {  // interior group, no redirected column: straight-line
+    // warp-uniform choice: tcgen05.wait::ld below is .sync.aligned, the whole warp must reach the same one
+    if (__all_sync(0xffffffffu, x_ok) && ny == 16 && !C2) {  // interior group, no redirected column: straight-line
 #pragma unroll
       for (int t = 0; t < 16; ++t) mk[t] = mp ? __ldg(mp + t * mstride) : 1.f;
 #pragma unroll
