@@ -49,7 +49,7 @@ struct Src {
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
@@ -214,9 +214,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, c
   for (int n = 0; n < NYU; ++n) uy[n] = plan_unit<Y_MN>(un, tid + n * THREADS);
   const long long kadv_x = X_MN ? (long long)KC * sx.s_k : KC, kadv_y = Y_MN ? (long long)KC * sy.s_k : KC;
   const uint32_t smem_base = umma::smem_u32(smem);
+  // bytes of a full, aligned copy (0 = zero fill) and its source: what issue() needs when the chunk lies wholly inside K
+  const bool al_both = sx.al16 && sy.al16;
   auto issue = [&](int kc) {  // chunk kc -> ring stage kc & 1; called for kc = 0, 1, 2, ... in order
     const uint32_t raw = smem_base + OFF_RAW + (uint32_t)(kc & 1) * STAGE_RAW;
     const int krem = kend - (kbeg + kc * KC);
+    if (al_both && krem >= KC) {  // the common case: one LDGSTS.128 and a pointer bump per copy
+#pragma unroll
+      for (int n = 0; n < NXC; ++n) {
+        if (cx[n].vmn >= 0) cp_async16(raw + cx[n].dst, cx[n].vmn ? cx[n].src : sx.base, cx[n].vmn * 4);
+        cx[n].src += kadv_x;
+      }
+#pragma unroll
+      for (int n = 0; n < NYC; ++n) {
+        if (cy[n].vmn >= 0) cp_async16(raw + RAW_X + cy[n].dst, cy[n].vmn ? cy[n].src : sy.base, cy[n].vmn * 4);
+        cy[n].src += kadv_y;
+      }
+      return;
+    }
 #pragma unroll
     for (int n = 0; n < NXC; ++n) issue_copy<X_MN>(cx[n], sx, raw, krem, kadv_x);
 #pragma unroll
@@ -288,24 +303,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, c
   const uint32_t tw = umma::tmem_addr(tb, q * 32, 0);
   float* C = g.C + (size_t)blockIdx.z * g.c_split_stride;
   float* C2 = g.C2 ? g.C2 + (size_t)blockIdx.z * g.c_split_stride : nullptr;
-  const size_t cstride = SWAP ? (size_t)g.ldc : 1, mstride = SWAP ? (size_t)g.ldm : 1;
+  const int cstride = SWAP ? g.ldc : 1, mstride = SWAP ? g.ldm : 1;
   const float bias_x = (!SWAP && g.bias && x_ok) ? __ldg(g.bias + x) : 0.f;
+  const bool relu = g.relu != 0;
   for (int c0 = cgp * 16; c0 < un; c0 += 64) {
-    float v[16], mk[16], old[16];
+    float v[16];
     if (nk > 0) umma::tmem_ld16(tw + c0, v);
     const int yb = y0 + c0;
     const int ny = min(16, y_total - yb);  // valid elements of the group (<= 0: padding columns only)
-    const size_t off = SWAP ? (size_t)yb * g.ldc + x : (size_t)x * g.ldc + yb;
-    float* cp = C + off;
+    float* cp = C + (SWAP ? (size_t)yb * g.ldc + x : (size_t)x * g.ldc + yb);
     const float* mp = g.mask ? g.mask + (SWAP ? (size_t)yb * g.ldm + x : (size_t)x * g.ldm + yb) : nullptr;
-    // every global read of the group is issued before the first use (the mask and the accumulate target may alias C for
-    // all the compiler knows: interleaved with the stores they would be 16 dependent round trips to HBM)
     // warp-uniform choice: tcgen05.wait::ld below is .sync.aligned, the whole warp must reach the same one
     if (__all_sync(0xffffffffu, x_ok) && ny == 16 && !C2) {  // interior group, no redirected column: straight-line
+      // every global read of the group is issued before the first use and before the TMEM wait (the mask and the
+      // accumulate target may alias C for all the compiler knows: interleaved with the stores they would be 16
+      // dependent round trips to HBM)
+      float bv[16], mk[16], old[16];
+      const float* bp = (SWAP && g.bias) ? g.bias + yb : nullptr;
 #pragma unroll
-      for (int t = 0; t < 16; ++t) mk[t] = mp ? __ldg(mp + t * mstride) : 1.f;
+      for (int t = 0; t < 16; ++t) bv[t] = bp ? __ldg(bp + t) : bias_x;
+      if (mp) {
 #pragma unroll
-      for (int t = 0; t < 16; ++t) old[t] = g.accumulate ? cp[t * cstride] : 0.f;
+        for (int t = 0; t < 16; ++t) mk[t] = __ldg(mp + t * mstride);
+      }
+      if (g.accumulate) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) old[t] = cp[t * cstride];
+      }
       if (nk > 0) {
         umma::tmem_ld_wait();
       } else {
@@ -314,11 +338,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, c
       }
 #pragma unroll
       for (int t = 0; t < 16; ++t) {
-        float r = v[t] + (SWAP ? (g.bias ? __ldg(g.bias + yb + t) : 0.f) : bias_x);
-        if (g.relu) r = fmaxf(r, 0.f);
-        r = mk[t] > 0.f ? r : 0.f;
-        cp[t * cstride] = r + old[t];
+        const float r = v[t] + bv[t];
+        v[t] = relu ? fmaxf(r, 0.f) : r;
       }
+      if (mp) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = mk[t] > 0.f ? v[t] : 0.f;
+      }
+      if (g.accumulate) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] += old[t];
+      }
+#pragma unroll
+      for (int t = 0; t < 16; ++t) cp[t * cstride] = v[t];
     } else {
       if (nk > 0) {
         umma::tmem_ld_wait();
@@ -330,10 +362,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, c
 #pragma unroll 1
         for (int t = 0; t < ny; ++t) {
           const int i = SWAP ? yb + t : x, j = SWAP ? x : yb + t;
-          float* dst = (C2 && j == g.n_main) ? (C2 + i) : (cp + t * cstride);
+          float* dst = (C2 && j == g.n_main) ? (C2 + i) : (cp + (size_t)t * cstride);
           float r = v[0] + (g.bias ? __ldg(g.bias + i) : 0.f);
-          if (g.relu) r = fmaxf(r, 0.f);
-          if (mp) r = __ldg(mp + t * mstride) > 0.f ? r : 0.f;
+          if (relu) r = fmaxf(r, 0.f);
+          if (mp) r = __ldg(mp + (size_t)t * mstride) > 0.f ? r : 0.f;
           if (g.accumulate) r += *dst;
           *dst = r;
 #pragma unroll
