@@ -28,6 +28,12 @@ void lrx_debug_set_gae_chunk(int knob);
  * consecutive step marks of row-owner thread 0 (slots 1..16) and of the issuer warp (slots 33..48); NULL switches it off. */
 void lrx_debug_set_tc128_prof(long long* device_buffer_64);
 /* device-to-device copy of n floats to a raw device address (an exchange slot of lrx_p2p_*). */
+/* The generic-width update's GEMM by itself: C[M x N] (+)= op(A)[M x K] op(B)[K x N] (+ bias[i], ReLU, ReLU mask,
+ * split-K over gridDim.z into C + z * c_split_stride); use_tc = 0 forces the fp32 FMA kernel. */
+int lrx_debug_gemm(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, int32_t M, int32_t N,
+                   int32_t K, int32_t at, int32_t bt, const float* bias, int32_t relu, const float* mask, int32_t ldm,
+                   int32_t accumulate, int32_t splits, int32_t k_chunk, int64_t c_split_stride, int32_t use_tc,
+                   lrx_stream_t stream);
 int lrx_debug_copy_f32(float* dst, const float* src, int32_t n, lrx_stream_t stream);
 
 /* ----------------------------------------------------------------- (2) liblerax_b200_test.so */

@@ -123,6 +123,9 @@ PROTOTYPES = {
 DEBUG_HOOKS = {
     "lrx_debug_set_fused": (None, [C.c_int]),
     "lrx_debug_copy_f32": (C.c_int, [_vp, _vp, C.c_int32, _vp]),
+    "lrx_debug_gemm": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                 C.c_int32, _vp]),
     "lrx_debug_set_gae_chunk": (None, [C.c_int]),
     "lrx_debug_set_tc128_prof": (None, [_vp]),
 }

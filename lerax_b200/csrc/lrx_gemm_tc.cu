@@ -174,16 +174,24 @@ __device__ __forceinline__ void convert_unit(const UnitPlan& p, const uint8_t* r
 }
 
 // X_MN / Y_MN: the UMMA A / B operand's source has the MN index contiguous (-> MN-major descriptor).
+// persistent != 0 (one column tile, <= 256 columns): gridDim.x CTAs walk the lane tiles blockIdx.x, + gridDim.x, ... as
+// ONE continuous stream of K chunks -- the copies of the next tile's first chunks are in flight and its first MMAs
+// issued (into the other half of TMEM) before the previous tile's epilogue runs, so neither the DRAM latency at a
+// tile's start nor the commit latency at its end is exposed.  Otherwise one tile per CTA (grid = tiles).
 template <bool SWAP, bool X_MN, bool Y_MN>
-__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, const int x_al16, const int y_al16) {
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const GemmArgs g, const int x_al16, const int y_al16, const int persistent) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_MISC);  // [2]: the MMAs that read operand stage s are done
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 16);
 
-  // tile of C: x -> the index on the TMEM lanes (128 per CTA), y -> the index on the TMEM columns (<= 288 per CTA)
+  // tile of C: x -> the index on the TMEM lanes (128 per tile), y -> the index on the TMEM columns (<= 288 per tile)
   const int x_total = SWAP ? g.N : g.M, y_total = SWAP ? g.M : g.N;
-  const int x0 = blockIdx.x * UM;
+  const int x_tiles = (x_total + UM - 1) / UM;
+  const int G = persistent ? (int)gridDim.x : x_tiles;
+  const int my_tiles = persistent ? (x_tiles - (int)blockIdx.x + G - 1) / G : 1;
+  auto tile_x0 = [&](int t) { return ((int)blockIdx.x + t * G) * UM; };
   const int y0 = blockIdx.y * UN_MAX;
   const int y_cnt = min(UN_MAX, y_total - y0);
   const int un = (y_cnt + 15) & ~15;  // UMMA N: multiple of 16 for M = 128
@@ -191,6 +199,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, c
   const int kbeg = blockIdx.z * g.k_chunk;
   const int kend = min(g.K, kbeg + g.k_chunk);
   const int nk = kend > kbeg ? (kend - kbeg + KC - 1) / KC : 0;
+  const int total = my_tiles * nk;  // chunks this CTA streams
 
   // op(A)[i][k]: AT ? A[k * lda + i] : A[i * lda + k];   op(B)[k][j]: BT ? B[j * ldb + k] : B[k * ldb + j]
   // X carries the lane index (SWAP: j from B, else i from A), Y the column index.
@@ -205,20 +214,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, c
   CopyPlan cx[NXC], cy[NYC];
   UnitPlan ux[NXU], uy[NYU];
 #pragma unroll
-  for (int n = 0; n < NXC; ++n) cx[n] = plan_copy<X_MN>(sx, x0, UM, kbeg, tid + n * THREADS);
-#pragma unroll
-  for (int n = 0; n < NYC; ++n) cy[n] = plan_copy<Y_MN>(sy, y0, un, kbeg, tid + n * THREADS);
-#pragma unroll
   for (int n = 0; n < NXU; ++n) ux[n] = plan_unit<X_MN>(UM, tid + n * THREADS);
 #pragma unroll
   for (int n = 0; n < NYU; ++n) uy[n] = plan_unit<Y_MN>(un, tid + n * THREADS);
   const long long kadv_x = X_MN ? (long long)KC * sx.s_k : KC, kadv_y = Y_MN ? (long long)KC * sy.s_k : KC;
   const uint32_t smem_base = umma::smem_u32(smem);
-  // bytes of a full, aligned copy (0 = zero fill) and its source: what issue() needs when the chunk lies wholly inside K
   const bool al_both = sx.al16 && sy.al16;
-  auto issue = [&](int kc) {  // chunk kc -> ring stage kc & 1; called for kc = 0, 1, 2, ... in order
-    const uint32_t raw = smem_base + OFF_RAW + (uint32_t)(kc & 1) * STAGE_RAW;
-    const int krem = kend - (kbeg + kc * KC);
+  int i_tile = 0, i_kc = 0, i_gc = 0;  // the next chunk to issue: tile, chunk inside the tile, position in the stream
+  auto issue_next = [&]() {            // -> ring stage i_gc & 1
+    if (i_kc == 0) {                   // a new tile: its copies start over at kbeg
+#pragma unroll
+      for (int n = 0; n < NXC; ++n) cx[n] = plan_copy<X_MN>(sx, tile_x0(i_tile), UM, kbeg, tid + n * THREADS);
+#pragma unroll
+      for (int n = 0; n < NYC; ++n) cy[n] = plan_copy<Y_MN>(sy, y0, un, kbeg, tid + n * THREADS);
+    }
+    const uint32_t raw = smem_base + OFF_RAW + (uint32_t)(i_gc & 1) * STAGE_RAW;
+    const int krem = kend - (kbeg + i_kc * KC);
     if (al_both && krem >= KC) {  // the common case: one LDGSTS.128 and a pointer bump per copy
 #pragma unroll
       for (int n = 0; n < NXC; ++n) {
@@ -230,12 +241,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, c
         if (cy[n].vmn >= 0) cp_async16(raw + RAW_X + cy[n].dst, cy[n].vmn ? cy[n].src : sy.base, cy[n].vmn * 4);
         cy[n].src += kadv_y;
       }
-      return;
+    } else {
+#pragma unroll
+      for (int n = 0; n < NXC; ++n) issue_copy<X_MN>(cx[n], sx, raw, krem, kadv_x);
+#pragma unroll
+      for (int n = 0; n < NYC; ++n) issue_copy<Y_MN>(cy[n], sy, raw + RAW_X, krem, kadv_y);
     }
-#pragma unroll
-    for (int n = 0; n < NXC; ++n) issue_copy<X_MN>(cx[n], sx, raw, krem, kadv_x);
-#pragma unroll
-    for (int n = 0; n < NYC; ++n) issue_copy<Y_MN>(cy[n], sy, raw + RAW_X, krem, kadv_y);
+    ++i_gc;
+    if (++i_kc == nk) {
+      i_kc = 0;
+      ++i_tile;
+    }
   };
 
   if (tid == 0) {
@@ -244,28 +260,124 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, c
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc(tslot, 512);
-  if (nk > 0) issue(0);
+  if (total > 0) issue_next();
   cp_async_commit();
-  if (nk > 1) issue(1);
+  if (total > 1) issue_next();
   cp_async_commit();
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tb = *tslot;
 
+  // ---- epilogue of tile e: warp w reads TMEM quadrant w & 3 (lanes = x), 16 of every 64 columns.  Element t of a group
+  // is C[i][j] with (i, j) = SWAP ? (yb + t, x) : (x, yb + t): base pointer + t * stride.  Warp-level only (no CTA barrier).
+  const int q = warp & 3, cgp = warp >> 2;
+  float* C = g.C + (size_t)blockIdx.z * g.c_split_stride;
+  float* C2 = g.C2 ? g.C2 + (size_t)blockIdx.z * g.c_split_stride : nullptr;
+  const int cstride = SWAP ? g.ldc : 1, mstride = SWAP ? g.ldm : 1;
+  const bool relu = g.relu != 0;
+  auto epilogue = [&](int e) {
+    const int x0 = tile_x0(e);
+    const int x = x0 + q * 32 + lane;
+    const bool x_ok = x < x_total;
+    const uint32_t tw = umma::tmem_addr(tb, q * 32, persistent ? (uint32_t)(e & 1) * 256u : 0u);
+    const float bias_x = (!SWAP && g.bias && x_ok) ? __ldg(g.bias + x) : 0.f;
+    for (int c0 = cgp * 16; c0 < un; c0 += 64) {
+      float v[16];
+      if (nk > 0) umma::tmem_ld16(tw + c0, v);
+      const int yb = y0 + c0;
+      const int ny = min(16, y_total - yb);  // valid elements of the group (<= 0: padding columns only)
+      float* cp = C + (SWAP ? (size_t)yb * g.ldc + x : (size_t)x * g.ldc + yb);
+      const float* mp = g.mask ? g.mask + (SWAP ? (size_t)yb * g.ldm + x : (size_t)x * g.ldm + yb) : nullptr;
+      // warp-uniform choice: tcgen05.wait::ld below is .sync.aligned, the whole warp must reach the same one
+      if (__all_sync(0xffffffffu, x_ok) && ny == 16 && !C2) {  // interior group, no redirected column: straight-line
+        // every global read of the group is issued before the first use and before the TMEM wait (the mask and the
+        // accumulate target may alias C for all the compiler knows: interleaved with the stores they would be 16
+        // dependent round trips to HBM)
+        float bv[16], mk[16], old[16];
+        const float* bp = (SWAP && g.bias) ? g.bias + yb : nullptr;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) bv[t] = bp ? __ldg(bp + t) : bias_x;
+        if (mp) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) mk[t] = __ldg(mp + t * mstride);
+        }
+        if (g.accumulate) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) old[t] = cp[t * cstride];
+        }
+        if (nk > 0) {
+          umma::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) v[t] = 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float r = v[t] + bv[t];
+          v[t] = relu ? fmaxf(r, 0.f) : r;
+        }
+        if (mp) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) v[t] = mk[t] > 0.f ? v[t] : 0.f;
+        }
+        if (g.accumulate) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) v[t] += old[t];
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) cp[t * cstride] = v[t];
+      } else {
+        if (nk > 0) {
+          umma::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) v[t] = 0.f;
+        }
+        if (x_ok) {
+#pragma unroll 1
+          for (int t = 0; t < ny; ++t) {
+            const int i = SWAP ? yb + t : x, j = SWAP ? x : yb + t;
+            float* dst = (C2 && j == g.n_main) ? (C2 + i) : (cp + (size_t)t * cstride);
+            float r = v[0] + (g.bias ? __ldg(g.bias + i) : 0.f);
+            if (relu) r = fmaxf(r, 0.f);
+            if (mp) r = __ldg(mp + (size_t)t * mstride) > 0.f ? r : 0.f;
+            if (g.accumulate) r += *dst;
+            *dst = r;
+#pragma unroll
+            for (int e2 = 0; e2 < 15; ++e2) v[e2] = v[e2 + 1];  // rotate: keeps v[] in registers under the rolled loop
+          }
+        }
+      }
+    }
+    if (g.ones_row && blockIdx.z == 0 && (SWAP ? blockIdx.y == 0 : x0 == 0)) {
+      // C[M][j] = 1 for the j of this tile
+      const int jn = SWAP ? UM : y_cnt, jb = SWAP ? x0 : y0;
+      for (int t = tid; t < jn; t += THREADS)
+        if (jb + t < g.N) g.C[(size_t)g.M * g.ldc + jb + t] = 1.0f;
+    }
+  };
+
   uint32_t phase[2] = {0u, 0u};
-  for (int kc = 0; kc < nk; ++kc) {
-    const int st = kc & 1;
+  int t_cur = 0, kc = 0, epi = 0;  // tile / chunk of stream position gc; the next tile whose epilogue is due
+  for (int gc = 0; gc < total; ++gc) {
+    const int st = gc & 1;
     uint8_t* can = smem + OFF_CAN + (uint32_t)st * STAGE_CAN;
     const tc2::Mat X{can, (uint32_t)(X_MN ? KC : UM), CAN_X_PIECE};
     const tc2::Mat Y{can + 2 * CAN_X_PIECE, (uint32_t)(Y_MN ? KC : un), CAN_Y_PIECE};
-    cp_async_wait<1>();  // this thread's copies of chunk kc have landed (chunk kc + 1 may still be in flight)
-    if (kc >= 2) {       // the MMAs of chunk kc - 2 have read operand stage st
+    cp_async_wait<1>();  // this thread's copies of chunk gc have landed (chunk gc + 1 may still be in flight)
+    if (gc >= 2) {       // the MMAs of chunk gc - 2 have read operand stage st
       umma::mbar_wait(bar + st, phase[st]);
       phase[st] ^= 1u;
       umma::tc_fence_after();
     }
-    __syncthreads();     // every thread's copies of chunk kc are visible
+    __syncthreads();     // every thread's copies of chunk gc are visible
+    // tile `epi` finished with chunk (epi + 1) * nk - 1, which the wait above has covered two chunks later: its epilogue
+    // runs here, under the copies of chunks gc, gc + 1 and with the next tile's first MMAs already queued or done
+    if (epi < t_cur && gc >= (epi + 1) * nk + 1) {
+      epilogue(epi);
+      ++epi;
+    }
     const uint8_t* raw = smem + OFF_RAW + (uint32_t)st * STAGE_RAW;
 #pragma unroll
     for (int n = 0; n < NXU; ++n) convert_unit(ux[n], raw, X.ptr, CAN_X_PIECE);
@@ -273,113 +385,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const GemmArgs g, c
     for (int n = 0; n < NYU; ++n) convert_unit(uy[n], raw + RAW_X, Y.ptr, CAN_Y_PIECE);
     umma::fence_async_smem();
     umma::tc_fence_before();
-    __syncthreads();     // operand stage complete, ring stage st free
-    if (kc + 2 < nk) issue(kc + 2);
+    __syncthreads();     // operand stage complete, ring stage st free, this iteration's epilogue reads of TMEM done
+    if (gc + 2 < total) issue_next();
     cp_async_commit();
     if (warp == 0) {
       umma::tc_fence_after();
       const bool leader = umma::elect_one();
       const int ksteps = (min(KC, kend - (kbeg + kc * KC)) + 15) >> 4;  // zero-filled beyond kend
-      tc2::gemm<X_MN, Y_MN>(leader, tb, X, Y, UM, n1, n1, ksteps, kc > 0 ? 1u : 0u);
+      const uint32_t d = tb + (persistent ? (uint32_t)(t_cur & 1) * 256u : 0u);
+      tc2::gemm<X_MN, Y_MN>(leader, d, X, Y, UM, n1, n1, ksteps, kc > 0 ? 1u : 0u);
       if (n2) {
         const tc2::Mat Y2{Y.ptr + (Y_MN ? 32u * (KC * 16u) : 256u * 16u), Y.R, CAN_Y_PIECE};  // columns 256 ..
-        tc2::gemm<X_MN, Y_MN>(leader, tb + 256, X, Y2, UM, n2, n2, ksteps, kc > 0 ? 1u : 0u);
+        tc2::gemm<X_MN, Y_MN>(leader, d + 256, X, Y2, UM, n2, n2, ksteps, kc > 0 ? 1u : 0u);
       }
       if (leader) umma::mma_commit(bar + st);
       __syncwarp();
     }
-  }
-  cp_async_wait<0>();
-  if (nk > 0) {  // the last commit covers every earlier MMA
-    umma::mbar_wait(bar + ((nk - 1) & 1), phase[(nk - 1) & 1]);
-    umma::tc_fence_after();
-  }
-
-  // ---- epilogue: warp w reads TMEM quadrant w & 3 (lanes = x), 16 of every 64 columns.  Element t of a group is
-  // C[i][j] with (i, j) = SWAP ? (yb + t, x) : (x, yb + t): base pointer + t * stride.
-  const int q = warp & 3, cgp = warp >> 2;
-  const int x = x0 + q * 32 + lane;
-  const bool x_ok = x < x_total;
-  const uint32_t tw = umma::tmem_addr(tb, q * 32, 0);
-  float* C = g.C + (size_t)blockIdx.z * g.c_split_stride;
-  float* C2 = g.C2 ? g.C2 + (size_t)blockIdx.z * g.c_split_stride : nullptr;
-  const int cstride = SWAP ? g.ldc : 1, mstride = SWAP ? g.ldm : 1;
-  const float bias_x = (!SWAP && g.bias && x_ok) ? __ldg(g.bias + x) : 0.f;
-  const bool relu = g.relu != 0;
-  for (int c0 = cgp * 16; c0 < un; c0 += 64) {
-    float v[16];
-    if (nk > 0) umma::tmem_ld16(tw + c0, v);
-    const int yb = y0 + c0;
-    const int ny = min(16, y_total - yb);  // valid elements of the group (<= 0: padding columns only)
-    float* cp = C + (SWAP ? (size_t)yb * g.ldc + x : (size_t)x * g.ldc + yb);
-    const float* mp = g.mask ? g.mask + (SWAP ? (size_t)yb * g.ldm + x : (size_t)x * g.ldm + yb) : nullptr;
-    // warp-uniform choice: tcgen05.wait::ld below is .sync.aligned, the whole warp must reach the same one
-    if (__all_sync(0xffffffffu, x_ok) && ny == 16 && !C2) {  // interior group, no redirected column: straight-line
-      // every global read of the group is issued before the first use and before the TMEM wait (the mask and the
-      // accumulate target may alias C for all the compiler knows: interleaved with the stores they would be 16
-      // dependent round trips to HBM)
-      float bv[16], mk[16], old[16];
-      const float* bp = (SWAP && g.bias) ? g.bias + yb : nullptr;
-#pragma unroll
-      for (int t = 0; t < 16; ++t) bv[t] = bp ? __ldg(bp + t) : bias_x;
-      if (mp) {
-#pragma unroll
-        for (int t = 0; t < 16; ++t) mk[t] = __ldg(mp + t * mstride);
-      }
-      if (g.accumulate) {
-#pragma unroll
-        for (int t = 0; t < 16; ++t) old[t] = cp[t * cstride];
-      }
-      if (nk > 0) {
-        umma::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int t = 0; t < 16; ++t) v[t] = 0.f;
-      }
-#pragma unroll
-      for (int t = 0; t < 16; ++t) {
-        const float r = v[t] + bv[t];
-        v[t] = relu ? fmaxf(r, 0.f) : r;
-      }
-      if (mp) {
-#pragma unroll
-        for (int t = 0; t < 16; ++t) v[t] = mk[t] > 0.f ? v[t] : 0.f;
-      }
-      if (g.accumulate) {
-#pragma unroll
-        for (int t = 0; t < 16; ++t) v[t] += old[t];
-      }
-#pragma unroll
-      for (int t = 0; t < 16; ++t) cp[t * cstride] = v[t];
-    } else {
-      if (nk > 0) {
-        umma::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int t = 0; t < 16; ++t) v[t] = 0.f;
-      }
-      if (x_ok) {
-#pragma unroll 1
-        for (int t = 0; t < ny; ++t) {
-          const int i = SWAP ? yb + t : x, j = SWAP ? x : yb + t;
-          float* dst = (C2 && j == g.n_main) ? (C2 + i) : (cp + (size_t)t * cstride);
-          float r = v[0] + (g.bias ? __ldg(g.bias + i) : 0.f);
-          if (relu) r = fmaxf(r, 0.f);
-          if (mp) r = __ldg(mp + (size_t)t * mstride) > 0.f ? r : 0.f;
-          if (g.accumulate) r += *dst;
-          *dst = r;
-#pragma unroll
-          for (int e = 0; e < 15; ++e) v[e] = v[e + 1];  // rotate: keeps v[] in registers under the rolled loop
-        }
-      }
+    if (++kc == nk) {
+      kc = 0;
+      ++t_cur;
     }
   }
-  if (g.ones_row && blockIdx.z == 0 && (SWAP ? blockIdx.y == 0 : blockIdx.x == 0)) {
-    // C[M][j] = 1 for the j of this CTA's tile
-    const int jn = SWAP ? UM : y_cnt, jb = SWAP ? x0 : y0;
-    for (int t = tid; t < jn; t += THREADS)
-      if (jb + t < g.N) g.C[(size_t)g.M * g.ldc + jb + t] = 1.0f;
+  cp_async_wait<0>();
+  if (total > 0) {  // the last commit covers every earlier MMA
+    umma::mbar_wait(bar + ((total - 1) & 1), phase[(total - 1) & 1]);
+    umma::tc_fence_after();
   }
+  while (epi < my_tiles) epilogue(epi++);
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tb, 512);
@@ -398,8 +430,16 @@ int launch(const GemmArgs& g, int splits, cudaStream_t s) {
   const float* xb = SWAP ? g.B : g.A;
   const float* yb = SWAP ? g.A : g.B;
   const int xl = SWAP ? g.ldb : g.lda, yl = SWAP ? g.lda : g.ldb;
-  dim3 grid((x_total + UM - 1) / UM, (y_total + UN_MAX - 1) / UN_MAX, splits);
-  tc_gemm_kernel<SWAP, X_MN, Y_MN><<<grid, THREADS, SMEM_BYTES, s>>>(g, aligned16(xb, xl), aligned16(yb, yl));
+  const int x_tiles = (x_total + UM - 1) / UM, y_tiles = (y_total + UN_MAX - 1) / UN_MAX;
+  // one column tile of <= 256 columns: both halves of TMEM hold an accumulator and the CTAs stream over the lane tiles
+  const int persistent = (y_tiles == 1 && y_total <= 256 && x_tiles > 1) ? 1 : 0;
+  int gx = x_tiles;
+  if (persistent) {
+    const int slots = lrx_sm_count() / (splits > 0 ? splits : 1);
+    gx = x_tiles < slots ? x_tiles : (slots > 0 ? slots : 1);
+  }
+  dim3 grid(gx, y_tiles, splits);
+  tc_gemm_kernel<SWAP, X_MN, Y_MN><<<grid, THREADS, SMEM_BYTES, s>>>(g, aligned16(xb, xl), aligned16(yb, yl), persistent);
   return LRX_OK;
 }
 

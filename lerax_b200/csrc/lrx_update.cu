@@ -131,6 +131,21 @@ int lrx_launch_gemm_fma(const GemmArgs& g, bool at, bool bt, int splits, cudaStr
   return LRX_OK;
 }
 
+// The layer-by-layer update's GEMM by itself (tools/gemm_time.py, tests): C[M x N] (+)= op(A) op(B) with the epilogue
+// options of GemmArgs; use_tc = 0 forces the FMA kernel.
+extern "C" int lrx_debug_gemm(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, int32_t M,
+                              int32_t N, int32_t K, int32_t at, int32_t bt, const float* bias, int32_t relu, const float* mask,
+                              int32_t ldm, int32_t accumulate, int32_t splits, int32_t k_chunk, int64_t c_split_stride,
+                              int32_t use_tc, lrx_stream_t stream) {
+  LRX_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && splits >= 1, LRX_ERR_INVALID_ARG, "lrx_debug_gemm: bad argument");
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.relu = relu; g.mask = mask; g.ldm = ldm; g.accumulate = accumulate;
+  g.k_chunk = k_chunk > 0 ? k_chunk : K; g.c_split_stride = c_split_stride; g.n_main = -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  return use_tc ? launch_gemm(g, at != 0, bt != 0, splits, s) : lrx_launch_gemm_fma(g, at != 0, bt != 0, splits, s);
+}
+
 // ============================================================================= gather
 // Rows idx[m] (reference order i = n*T + t) -> feature-major obsT [(d+1)][rows] with a ones
 // row, plus the per-row scalars.  buffer/base_buffer.py:90-103 (gather).
@@ -660,11 +675,13 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static Workspace carve(const LrxPolicyDesc& pol, int64_t B, void* base) {
   Workspace w{};
-  int64_t rows = B < LRX_CHUNK_ROWS ? B : LRX_CHUNK_ROWS;
+  static const int64_t chunk_rows = [] { const char* e = getenv("LRX_CHUNK_ROWS"); return e ? atoll(e) : LRX_CHUNK_ROWS; }();
+  static const int64_t split_rows = [] { const char* e = getenv("LRX_SPLIT_ROWS"); return e ? atoll(e) : 1024LL; }();
+  int64_t rows = B < chunk_rows ? B : chunk_rows;
   rows = (rows + 3) / 4 * 4;
   if (rows < 4) rows = 4;
   w.rows = rows;
-  int sp = (int)((rows + 1023) / 1024);
+  int sp = (int)((rows + split_rows - 1) / split_rows);
   w.splits = sp < 1 ? 1 : (sp > LRX_MAX_SPLIT ? LRX_MAX_SPLIT : sp);
   w.loss_blocks = (int)((rows + LRX_LOSS_THREADS - 1) / LRX_LOSS_THREADS);
   int np = 0;
