@@ -177,6 +177,109 @@ gae_tn_kernel(const float* __restrict__ rew, const float* __restrict__ val, cons
   }
 }
 
+// Streaming variant for wide buffers (N >= a few thousand env strips): ONE WARP PER ENV STRIP walks all T steps of its
+// 32 * EPL envs from t = T-1 down to 0 with the recurrence carried in registers -- the reference's own order of
+// operations (gae.py:47-66), no chunk summaries, no shared memory, no block barrier.  The loads are software pipelined
+// in groups of G steps: group k+1's rew / val / done rows are requested before group k is scanned, so a warp keeps
+// 2 * G * EPL * 9 bytes per lane in flight and ~7 warps per SM cover the HBM latency.  ncu on the chunked kernel at
+// config 2 (profiles/r2_gae.md): 66 thread instructions per element, issue slots 60 % busy at 39 % occupancy -- that
+// kernel is instruction bound below ~10^7 elements; this one executes ~14 per element.
+template <int EPL, int G, bool CS>
+__global__ void __launch_bounds__(256)
+gae_stream_kernel(const float* __restrict__ rew, const float* __restrict__ val, const uint8_t* __restrict__ done,
+                  const float* __restrict__ last_val, float* __restrict__ adv, float* __restrict__ ret, int N, int T,
+                  float gamma, float lam, double* ev_sums) {
+  using F = typename GaeVec<EPL>::F;
+  using U = typename GaeVec<EPL>::U;
+  __shared__ double sEv[16][4];
+  const int lane = threadIdx.x, w = threadIdx.y, W = blockDim.y;
+  const float gl = gamma * lam;
+  const int n_strips = (N + 32 * EPL - 1) / (32 * EPL);
+  const int ng = (T + G - 1) / G;
+  double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+  struct Group { F r[G], v[G]; U d[G]; };
+
+  for (int strip = blockIdx.x * W + w; strip < n_strips; strip += gridDim.x * W) {  // warp-uniform
+    const int n = (strip * 32 + lane) * EPL;
+    const bool live = n < N;
+    const int nl = live ? n : N - EPL;
+    auto load = [&](Group& gq, int k) {  // group k covers t in [T - (k+1) G, T - k G); rows below t = 0 re-read row 0
+      const int base = T - (k + 1) * G;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int t = base + i;
+        const size_t off = (size_t)(t > 0 ? t : 0) * N + nl;
+        if (CS) {
+          gq.r[i] = __ldcs(reinterpret_cast<const F*>(rew + off));
+          gq.v[i] = __ldcs(reinterpret_cast<const F*>(val + off));
+          gq.d[i] = __ldcs(reinterpret_cast<const U*>(done + off));
+        } else {
+          gq.r[i] = *reinterpret_cast<const F*>(rew + off);
+          gq.v[i] = *reinterpret_cast<const F*>(val + off);
+          gq.d[i] = *reinterpret_cast<const U*>(done + off);
+        }
+      }
+    };
+    float vn[EPL], A[EPL];  // value of step t + 1 (the bootstrap value past the end) and advantage of step t + 1
+    {
+      const F x = *reinterpret_cast<const F*>(last_val + nl);
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { vn[e] = reinterpret_cast<const float*>(&x)[e]; A[e] = 0.f; }
+    }
+    auto scan = [&](const Group& gq, int k) {
+      const int base = T - (k + 1) * G;
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;  // <= G * EPL terms in fp32, then fp64
+#pragma unroll
+      for (int i = G - 1; i >= 0; --i) {
+        const int t = base + i;
+        if (t >= 0) {  // warp-uniform
+          F Ao, Ro;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            const float r = reinterpret_cast<const float*>(&gq.r[i])[e], v = reinterpret_cast<const float*>(&gq.v[i])[e];
+            const float nd = 1.0f - (float)reinterpret_cast<const uint8_t*>(&gq.d[i])[e];
+            const float delta = r + gamma * vn[e] * nd - v;
+            A[e] = delta + gl * nd * A[e];
+            vn[e] = v;
+            const float Ri = A[e] + v;
+            reinterpret_cast<float*>(&Ao)[e] = A[e];
+            reinterpret_cast<float*>(&Ro)[e] = Ri;
+            f0 += Ri; f1 = fmaf(Ri, Ri, f1); f2 += A[e]; f3 = fmaf(A[e], A[e], f3);
+          }
+          if (live) {
+            const size_t off = (size_t)t * N + n;
+            if (CS) {
+              __stcs(reinterpret_cast<F*>(adv + off), Ao);
+              __stcs(reinterpret_cast<F*>(ret + off), Ro);
+            } else {
+              *reinterpret_cast<F*>(adv + off) = Ao;
+              *reinterpret_cast<F*>(ret + off) = Ro;
+            }
+          }
+        }
+      }
+      if (live) { e0 += f0; e1 += f1; e2 += f2; e3 += f3; }
+    };
+    Group ga, gb;
+    load(ga, 0);
+    for (int k = 0; k < ng; k += 2) {
+      if (k + 1 < ng) load(gb, k + 1);
+      scan(ga, k);
+      if (k + 1 < ng) {
+        if (k + 2 < ng) load(ga, k + 2);
+        scan(gb, k + 1);
+      }
+    }
+  }
+
+  if (ev_sums) {
+    e0 = warp_sum(e0); e1 = warp_sum(e1); e2 = warp_sum(e2); e3 = warp_sum(e3);
+    if (lane == 0) { sEv[w][0] = e0; sEv[w][1] = e1; sEv[w][2] = e2; sEv[w][3] = e3; }
+    __syncthreads();
+    ev_block_finish(ev_sums, sEv, W, threadIdx.y * 32 + threadIdx.x);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 gae_nt_kernel(const float* __restrict__ rew, const float* __restrict__ val,
               const uint8_t* __restrict__ done, const float* __restrict__ last_val,
@@ -267,6 +370,42 @@ extern "C" int lrx_gae(const float* rew, const float* val, const uint8_t* done,
     }
     if (N < 64 * epl) epl = 1;
     while (epl > 1 && !aligned(epl)) epl >>= 1;
+    // Streaming kernel (one warp per strip, the whole horizon through a register pipeline): chosen when the strips alone
+    // fill the GPU with several warps per SM; knob < 0 forces it: -(CS * 1000000 + W * 10000 + EPL * 100 + G), CS = 1:
+    // plain instead of evict-first loads / stores.
+    {
+      // tools/gae_time.py on B200 (profiles/r2_gae.md): plain loads / stores beat the evict-first hints by 4 - 10 %; two envs
+      // per lane and 16-step groups up to ~3 x 10^5 envs, four envs per lane and 8-step groups beyond
+      int sw = 4, se = 2, sg = 16, plain = 1;
+      bool want = g_gae_knob == 0 && epl >= 2 && (N + 63) / 64 >= 4 * lrx_sm_count();
+      if (want && aligned(4) && (N + 127) / 128 >= 16 * lrx_sm_count()) { se = 4; sg = 8; }
+      if (g_gae_knob < 0) {
+        const int k = -g_gae_knob;
+        plain = k / 1000000; sw = (k / 10000) % 100; se = (k / 100) % 100; sg = k % 100;
+        want = se >= 1 && se <= 4 && aligned(se) && N >= 32 * se;
+        if (!want) { minb = 0; epl = 2; L = 4; C = 4; if (N < 64 * epl) epl = 1; while (epl > 1 && !aligned(epl)) epl >>= 1; }
+      }
+      if (want) {
+        const int n_strips = (N + 32 * se - 1) / (32 * se);
+        const int blocks = (n_strips + sw - 1) / sw;
+        int per_sm = 1;
+        bool ok = true;
+#define LRX_GAE_STREAM(EE, GG, CC)                                                                                     \
+  if (se == EE && sg == GG && plain == (CC ? 0 : 1)) {                                                                \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gae_stream_kernel<EE, GG, CC>, 32 * sw, 0);                \
+    int grid = blocks < per_sm * lrx_sm_count() ? blocks : per_sm * lrx_sm_count();                                   \
+    if (grid > LRX_GAE_EV_BLOCKS) grid = LRX_GAE_EV_BLOCKS;                                                           \
+    gae_stream_kernel<EE, GG, CC><<<grid, dim3(32, sw), 0, s>>>(rew, val, done, last_value, adv, ret, N, T, gamma,    \
+                                                                lam, ev_sums);                                         \
+  } else
+        LRX_GAE_STREAM(2, 16, true) LRX_GAE_STREAM(2, 8, true) LRX_GAE_STREAM(1, 16, true) LRX_GAE_STREAM(4, 8, true)
+        LRX_GAE_STREAM(2, 16, false) LRX_GAE_STREAM(4, 8, false) LRX_GAE_STREAM(2, 12, true) { ok = false; }
+#undef LRX_GAE_STREAM
+        LRX_REQUIRE(ok && sw >= 1 && sw <= 8, LRX_ERR_INVALID_ARG, "lrx_gae: unsupported streaming shape W=%d EPL=%d G=%d", sw, se, sg);
+        LRX_LAUNCH_CHECK();
+        return LRX_OK;
+      }
+    }
     if (C > 16) C = 16;
     while (C > 1 && (C - 1) * L >= T) --C;  // no warp without a step
     const int n_strips = (N + 32 * epl - 1) / (32 * epl);

@@ -251,6 +251,36 @@ def test_gae_matches_oracle(T, N, layout):
     np.testing.assert_allclose(ev, want_ev, rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("T,N", [(1, 32), (3, 70), (16, 33), (63, 96), (128, 258), (300, 64), (2048, 36)])
+@pytest.mark.parametrize("knob", [-40216, -10116, -20208, -30408])
+def test_gae_streaming_kernel_matches_oracle(T, N, knob):
+    """The one-warp-per-strip streaming kernel (the default for wide buffers such as config 2) forced at small and
+    ragged shapes: W warps per block, EPL envs per lane, G steps per load group; horizon not a multiple of G, env count not a
+    multiple of the strip, more strips than warps."""
+    epl = (-knob // 100) % 100
+    if N % epl:
+        N += epl - N % epl
+    rng = np.random.default_rng(T * 1000 + N)
+    r = rng.standard_normal((T, N)).astype(np.float32)
+    v = rng.standard_normal((T, N)).astype(np.float32)
+    d = rng.random((T, N)) < 0.05
+    last = rng.standard_normal(N).astype(np.float32)
+    adv, ret = OG.gae(r, v, d, last, 0.99, 0.95)
+    from lerax_b200 import _lib as L
+
+    dbg = L.debug_lib()
+    dbg.lrx_debug_set_gae_chunk(knob)
+    try:
+        ga, gr, ev = H.run_gae(r, v, d, last, 0.99, 0.95, "TN", want_ev=True)
+    finally:
+        dbg.lrx_debug_set_gae_chunk(0)
+    H.assert_close(ga, adv, RTOL, 1e-5, "adv")
+    H.assert_close(gr, ret, RTOL, 1e-5, "ret")
+    want_ev = [ret.astype(np.float64).sum(), (ret.astype(np.float64) ** 2).sum(), adv.astype(np.float64).sum(),
+               (adv.astype(np.float64) ** 2).sum()]
+    np.testing.assert_allclose(ev, want_ev, rtol=1e-5, atol=1e-4)
+
+
 # ------------------------------------------------------------------------- update
 def synthetic_buffer(kind, T, N, seed=0, **pkw):
     oenv, spec, params, env, pol, rng, y0 = setup(kind, seed=seed, N=N, **pkw)
