@@ -27,6 +27,8 @@ void lrx_debug_set_gae_chunk(int knob);
 /* Cycle profile of ppo_grad_tc128_kernel: with a device buffer of 64 int64 set, CTA 0 accumulates the cycles between
  * consecutive step marks of row-owner thread 0 (slots 1..16) and of the issuer warp (slots 33..48); NULL switches it off. */
 void lrx_debug_set_tc128_prof(long long* device_buffer_64);
+/* ppo_grad_pp64_kernel: raw clock64 stamps of CTA 0 / half 0, 8 per issue step, first `records` steps of a launch. */
+void lrx_debug_set_pp64_prof(long long* device_buffer, int records);
 /* device-to-device copy of n floats to a raw device address (an exchange slot of lrx_p2p_*). */
 /* The generic-width update's GEMM by itself: C[M x N] (+)= op(A)[M x K] op(B)[K x N] (+ bias[i], ReLU, ReLU mask,
  * split-K over gridDim.z into C + z * c_split_stride); use_tc = 0 forces the fp32 FMA kernel. */

@@ -128,6 +128,7 @@ DEBUG_HOOKS = {
                                  C.c_int32, _vp]),
     "lrx_debug_set_gae_chunk": (None, [C.c_int]),
     "lrx_debug_set_tc128_prof": (None, [_vp]),
+    "lrx_debug_set_pp64_prof": (None, [_vp, C.c_int]),
 }
 # ... and the tensor-core self-tests of the separate liblerax_b200_test.so
 DEBUG_TESTS = {

@@ -34,11 +34,11 @@ int lrx_fused_enabled() {
   if (g_fused < 0) {
     const char* d = getenv("LRX_DISABLE_FUSED");
     const char* e = getenv("LRX_FUSED");
-    g_fused = (d && d[0] == '1') ? 0 : (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+    g_fused = (d && d[0] == '1') ? 0 : (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;
   }
   return g_fused;
 }
-extern "C" void lrx_debug_set_fused(int level) { g_fused = level < 0 ? 0 : level > 2 ? 2 : level; }
+extern "C" void lrx_debug_set_fused(int level) { g_fused = level < 0 ? 0 : level > 3 ? 3 : level; }
 
 int lrx_sm_count() {
   int dev = 0, n = 0;

@@ -803,14 +803,21 @@ int lrx_ppo_grad_tc128(const LrxPolicyDesc* pol, const float* params, const LrxB
                        int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, float* gradbuf,
                        void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled,
                        const LrxApplyArgs* apply);
-// Default-width policies: second-generation tensor-core kernel (lrx_update_tc128.cu), else the first-generation one
+int lrx_ppo_grad_pp64(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,
+                      int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, float* gradbuf,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled,
+                      const LrxApplyArgs* apply);
+// Default-width policies: third-generation (two half tiles in flight, lrx_update_pp64.cu), second-generation tensor-core kernel (lrx_update_tc128.cu), else the first-generation one
 // (lrx_update_fused.cu); `handled` stays false for other widths (or with the kernels switched off).
 static int lrx_ppo_grad_tensor(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,
                                int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, float* gradbuf,
                                void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled,
                                const LrxApplyArgs* apply) {
-  int rc = lrx_ppo_grad_tc128(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, stream,
-                              handled, apply);
+  int rc = lrx_ppo_grad_pp64(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, stream,
+                             handled, apply);
+  if (rc || *handled) return rc;
+  rc = lrx_ppo_grad_tc128(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, stream,
+                          handled, apply);
   if (rc || *handled) return rc;
   return lrx_ppo_grad_fused(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, stream,
                             handled, apply);
