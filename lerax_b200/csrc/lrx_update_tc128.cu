@@ -761,13 +761,26 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
   }
 
   mark(15);
+  long long tf0 = 0, tf1 = 0, tf2 = 0, tf3 = 0;  // flush time stamps, kept in registers (a global read-modify-write per mark would stall the path it measures)
+  if (prof_on) tf0 = clock64();
   // ------------------------------------------------------------------ flush the gradient partial
+  // Every epilogue is done and every GEMM waited for: the activation buffers are free.  The dW^T accumulators (TMEM lane =
+  // output unit, columns = inputs) are transposed through shared memory so that the partial is written with coalesced
+  // stores: written straight from the TMEM fragments, every lane stored into a different 128-byte line -- ~13 k L1
+  // store transactions per CTA, 13 k of the 15 k cycles this flush took (tools/tc128_prof.py), and the stores queued in
+  // the LSU held up everything behind them.
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
   float* part = a.partial + (size_t)blockIdx.x * a.partial_stride;
   const tc::LayerOffsets& lo = a.lo;
   const bool low = lane < 16;          // M = 64 accumulators: output / input unit mo at lanes 0-15 of the quadrant
   const int mo = q * 16 + (lane & 15);
-  // dW^T accumulators: TMEM row = output unit, columns = inputs, then the bias gradient at column bias_col
-  auto flush_T = [&](uint32_t col, int in_real, int in_pad, int bias_col, int layer) {
+  float* stg = reinterpret_cast<float*>(smem + OFF_XH1);  // XH1 | XH2: 66 KB, staging [64 outputs][in + 1] (odd pitch)
+  constexpr int S_ENC1 = 0, S_V1 = 64 * 65, S_V0 = 2 * 64 * 65, S_A0 = S_V0 + 64 * 17, S_ENC0 = S_A0 + 64 * 17;
+  static_assert((S_ENC0 + 64 * 9) * 4 <= 33 * CG, "flush staging exceeds the XH1 | XH2 region");
+  // dW^T accumulators -> staging; the bias gradient (column bias_col) goes straight out (lanes = consecutive outputs)
+  auto stage_T = [&](uint32_t col, int in_real, int in_pad, int bias_col, int layer, int soff, int pitch) {
     for (int c0 = 0; c0 < in_pad; c0 += 8) {
       float v[8];
       umma::tmem_ld8(tw + col + c0, v);
@@ -775,7 +788,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
       if (low) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (c0 + j < in_real) part[lo.w[layer] + mo * in_real + c0 + j] = v[j];
+          if (c0 + j < in_real) stg[soff + mo * pitch + c0 + j] = v[j];
       }
     }
     float v[8];
@@ -783,7 +796,8 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
     umma::tmem_ld_wait();
     if (low) part[lo.b[layer] + mo] = v[0];
   };
-  // dW accumulators: TMEM row = input unit, columns = outputs (their biases come from registers)
+  // dW accumulators: TMEM row = input unit, columns = outputs (their biases come from registers): lanes = consecutive
+  // inputs of one output -> already coalesced
   auto flush_N = [&](uint32_t col, int in_real, int out_real, int out_pad, int layer) {
     for (int c0 = 0; c0 < out_pad; c0 += 8) {
       float v[8];
@@ -796,50 +810,71 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
       }
     }
   };
-  umma::tc_fence_after();
-  if (worker && g == 0) { flush_T(C_G0, a.obs_dim, 8, 8, tc::L_ENC0); flush_N(C_G2, 64, 16, 16, tc::L_ENC2); }
-  if (worker && g == 1) flush_T(C_G1, 64, 64, 64, tc::L_ENC1);
-  if (worker && g == 2) { flush_T(C_GV1, 64, 64, 64, tc::L_V1); flush_T(C_GV0, 16, 16, 16, tc::L_V0); }
-  if (worker && g == 3) { flush_T(C_GA0, 16, 16, 16, tc::L_A0); flush_N(C_GA1, 64, 16, 16, tc::L_A1); }
+  if (worker && g == 0) { stage_T(C_G0, a.obs_dim, 8, 8, tc::L_ENC0, S_ENC0, 9); flush_N(C_G2, 64, 16, 16, tc::L_ENC2); }
+  if (worker && g == 1) stage_T(C_G1, 64, 64, 64, tc::L_ENC1, S_ENC1, 65);
+  if (worker && g == 2) { stage_T(C_GV1, 64, 64, 64, tc::L_V1, S_V1, 65); stage_T(C_GV0, 16, 16, 16, tc::L_V0, S_V0, 17); }
+  if (worker && g == 3) { stage_T(C_GA0, 16, 16, 16, tc::L_A0, S_A0, 17); flush_N(C_GA1, 64, 16, 16, tc::L_A1); }
 
-  // ------------------------------------------------------------------ register-held gradients (fixed order)
-  __syncthreads();  // every GEMM is done and waited for: the activation buffers are free
-  {
-    float* sh = reinterpret_cast<float*>(smem + OFF_XH1);
-    float* s_wv2 = sh;                 // [4 quadrants][64 columns]
-    float* s_bv2 = s_wv2 + 256;        // [4 quadrants]
-    float* s_e2 = s_bv2 + 4;           // [4 quadrants][16 columns]
-    float* s_mw = s_e2 + 64;           // [16 warps][NO][16]
-    float* s_mb = s_mw + 16 * LRX_MAX_NOUT * 16;  // [16 warps][NO]
-    if (worker) {
-      if ((lane & 1) == 0) s_wv2[q * 64 + cg + (lane >> 1)] = gw_v2;
+  // ------------------------------------------------------------------ register-held gradients and loss statistics
+  float* sh = reinterpret_cast<float*>(smem + OFF_XB1);
+  float* s_wv2 = sh;                 // [4 quadrants][64 columns]
+  float* s_bv2 = s_wv2 + 256;        // [4 quadrants]
+  float* s_e2 = s_bv2 + 4;           // [4 quadrants][16 columns]
+  float* s_mw = s_e2 + 64;           // [16 warps][NO][16]
+  float* s_mb = s_mw + 16 * LRX_MAX_NOUT * 16;  // [16 warps][NO]
+  double* shd = reinterpret_cast<double*>(smem + OFF_DY64);  // [6][16 warps]
+  if (worker) {
+    if ((lane & 1) == 0) s_wv2[q * 64 + cg + (lane >> 1)] = gw_v2;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = warp_sum(bs_e2[j]);
-        if (lane == 0) s_e2[q * 16 + 4 * g + j] = x;
-      }
-      if (g0) {
-        const float x = warp_sum(gb_v2);
-        if (lane == 0) s_bv2[q] = x;
-      }
-      // mapping layer: reduce over the warp's eight row slots (lanes with equal lane % 4), one slot per warp
+    for (int j = 0; j < 4; ++j) {
+      const float x = warp_sum(bs_e2[j]);
+      if (lane == 0) s_e2[q * 16 + 4 * g + j] = x;
+    }
+    if (g0) {
+      const float x = warp_sum(gb_v2);
+      if (lane == 0) s_bv2[q] = x;
+    }
+    // mapping layer: reduce over the warp's eight row slots (lanes with equal lane % 4), one slot per warp
 #pragma unroll
-      for (int o2 = 0; o2 < NO; ++o2) {
-        if (o2 < n_out) {
+    for (int o2 = 0; o2 < NO; ++o2) {
+      if (o2 < n_out) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float x = gm_w[o2][c];
-            x += __shfl_xor_sync(0xffffffffu, x, 4);
-            x += __shfl_xor_sync(0xffffffffu, x, 8);
-            x += __shfl_xor_sync(0xffffffffu, x, 16);
-            if (lane < 4) s_mw[(warp * LRX_MAX_NOUT + o2) * 16 + 4 * lane + c] = x;
-          }
-          const float xb = warp_sum(gm_b[o2]);
-          if (lane == 0) s_mb[warp * LRX_MAX_NOUT + o2] = xb;
+        for (int c = 0; c < 4; ++c) {
+          float x = gm_w[o2][c];
+          x += __shfl_xor_sync(0xffffffffu, x, 4);
+          x += __shfl_xor_sync(0xffffffffu, x, 8);
+          x += __shfl_xor_sync(0xffffffffu, x, 16);
+          if (lane < 4) s_mw[(warp * LRX_MAX_NOUT + o2) * 16 + 4 * lane + c] = x;
         }
+        const float xb = warp_sum(gm_b[o2]);
+        if (lane == 0) s_mb[warp * LRX_MAX_NOUT + o2] = xb;
       }
     }
-    __syncthreads();
+    double v6[6] = {(double)s_kl, (double)s_pol, (double)s_val, (double)s_ent, (double)s_dls, (double)s_bad};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      v6[k] = warp_sum(v6[k]);
+      if (lane == 0) shd[k * 16 + warp] = v6[k];
+    }
+  }
+  if (prof_on) tf1 = clock64();
+  __syncthreads();
+  if (prof_on) tf2 = clock64();
+  // ------------------------------------------------------------------ staging -> partial, coalesced; fixed-order sums
+  {
+    // 64 x 64 layers: shifts instead of a division by a run-time width; consecutive threads = consecutive addresses
+    for (int e = tid; e < 2 * 4096; e += THREADS) {
+      const int l2 = e >> 12, r = e & 4095, o = r >> 6, i = r & 63;
+      part[lo.w[l2 ? tc::L_V1 : tc::L_ENC1] + r] = stg[(l2 ? S_V1 : S_ENC1) + o * 65 + i];
+    }
+    for (int e = tid; e < 2 * 1024; e += THREADS) {
+      const int l2 = e >> 10, r = e & 1023, o = r >> 4, i = r & 15;
+      part[lo.w[l2 ? tc::L_A0 : tc::L_V0] + r] = stg[(l2 ? S_A0 : S_V0) + o * 17 + i];
+    }
+    for (int e = tid; e < 64 * a.obs_dim; e += THREADS) {
+      const int o = e / a.obs_dim, i = e - o * a.obs_dim;
+      part[lo.w[tc::L_ENC0] + e] = stg[S_ENC0 + o * 9 + i];
+    }
     auto sum4 = [](const float* p, int stride) { return ((p[0] + p[stride]) + p[2 * stride]) + p[3 * stride]; };
     auto sum16 = [](const float* p, int stride) {
       float t = 0.f;
@@ -861,24 +896,17 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128_kernel(const __grid
       for (int o2 = 0; o2 < n_out; ++o2) sacc = fmaf(sum16(s_mb + o2, LRX_MAX_NOUT), fp[tc::F_WMAP + o2 * 16 + i2], sacc);
       part[lo.b[tc::L_A1] + i2] = sacc;
     }
-  }
-
-  // ------------------------------------------------------------------ loss statistics (fixed order)
-  __syncthreads();
-  double* shd = reinterpret_cast<double*>(smem + OFF_DY64);  // [6][16 warps]
-  double v6[6] = {(double)s_kl, (double)s_pol, (double)s_val, (double)s_ent, (double)s_dls, (double)s_bad};
-  if (worker) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      v6[k] = warp_sum(v6[k]);
-      if (lane == 0) shd[k * 16 + warp] = v6[k];
+    if (tid >= 320 && tid < 326) {
+      const int k = tid - 320;
+      double s2 = 0;
+      for (int w = 0; w < 16; ++w) s2 += shd[k * 16 + w];
+      a.loss_partial[(size_t)blockIdx.x * 8 + k] = s2;
     }
   }
-  __syncthreads();
-  if (tid < 6) {
-    double s = 0;
-    for (int w = 0; w < 16; ++w) s += shd[tid * 16 + w];
-    a.loss_partial[(size_t)blockIdx.x * 8 + tid] = s;
+  if (prof_on) {
+    tf3 = clock64();
+    const int o = tid == 0 ? 64 : 96;
+    a.prof[o + 0] += tf1 - tf0; a.prof[o + 1] += tf2 - tf1; a.prof[o + 2] += tf3 - tf2;
   }
   mark(16);
   umma::tc_fence_before();

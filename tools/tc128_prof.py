@@ -19,7 +19,7 @@ cb = algo.consolidate_callbacks(None)
 st = algo.reset(env, pol, key=jr.key(1), callback=cb)
 st = algo.iteration(st, key=jr.key(2), callback=cb)
 torch.cuda.synchronize()
-prof = torch.zeros(64, dtype=torch.int64, device="cuda")
+prof = torch.zeros(160, dtype=torch.int64, device="cuda")
 L.debug_lib().lrx_debug_set_tc128_prof(prof.data_ptr())
 algo.train(st.policy, st.opt_state, st.last_buffer, key=jr.key(3))
 torch.cuda.synchronize()
@@ -40,3 +40,5 @@ for k in range(1, 12):
     per = launches * tiles_cta0
     print(f"  step {k:2d}: {p[16 + k] / per:7.0f} | {p[48 + k] / per:7.0f}")
 print(f"tile total {tot / (launches * tiles_cta0):.0f} cycles")
+print("flush per launch (thread 0): barrier + TMEM -> staging + register sums %d | barrier %d | staging -> global + final sums %d" % (
+    p[64] / launches, p[65] / launches, p[66] / launches))
