@@ -361,14 +361,15 @@ extern "C" int lrx_debug_umma_time_bf16(const float* A, const float* B, float* d
 // 256 back-to-back tcgen05.mma with CONSTANT descriptors (no per-instruction arithmetic) rotating
 // over DS independent accumulators: the tensor pipe's own cost per instruction for small shapes.
 template <int DS>
-__global__ void __launch_bounds__(128) umma_rate_kernel(int M, int N, int a_mn, int b_mn, long long* cycles_out) {
+__global__ void __launch_bounds__(128) umma_rate_kernel(int M, int N, int a_mn, int b_mn, long long* cycles_out, int a_tmem = 0,
+                                                        int issuers = 1) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar[4];
   __shared__ uint32_t tmem_slot;
   const int warp = umma::warp_idx_sync();
   for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3F803F80u;
   if (threadIdx.x == 0) {
-    umma::mbar_init(&bar, 1);
+    for (int i = 0; i < 4; ++i) umma::mbar_init(&bar[i], 1);
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int M, int N, int a_mn, 
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tbase = tmem_slot;
-  if (warp == 0) {
+  if (warp < issuers) {  // `issuers` warps issue concurrently, each into its own accumulators and its own barrier
     const bool leader = umma::elect_one();
     // K-major view: LBO = rows * 16, SBO = 128; MN-major view of the same canonical bytes: LBO = 128, SBO = rows * 16
     const uint32_t idesc = umma::idesc_bf16(M, N, a_mn, b_mn);
@@ -385,19 +386,29 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int M, int N, int a_mn, 
                              : umma::smem_desc(umma::smem_u32(smem), (uint32_t)M * 16u, 128u);
     const uint64_t bd = b_mn ? umma::smem_desc(umma::smem_u32(smem) + 8192u, 128u, (uint32_t)N * 16u)
                              : umma::smem_desc(umma::smem_u32(smem) + 8192u, (uint32_t)N * 16u, 128u);
+    const uint32_t dbase = tbase + (uint32_t)warp * 64u * (uint32_t)DS;
     const long long t0 = clock64();
+    if (a_tmem) {  // TS form: the A operand (bf16 pairs in 32-bit columns) from TMEM columns 448.., B from shared memory
 #pragma unroll 1
-    for (int rep = 0; rep < 16; ++rep) {
+      for (int rep = 0; rep < 16; ++rep) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (leader) umma::mma_f16(tbase + (uint32_t)((i % DS) * 64), ad, bd, idesc, 1u);
+        for (int i = 0; i < 16; ++i)
+          if (leader) umma::mma_f16_ts(dbase + (uint32_t)((i % DS) * 64), tbase + 448u, bd, idesc, 1u);
+      }
+    } else {
+#pragma unroll 1
+      for (int rep = 0; rep < 16; ++rep) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (leader) umma::mma_f16(dbase + (uint32_t)((i % DS) * 64), ad, bd, idesc, 1u);
+      }
     }
     const long long t1 = clock64();
-    if (leader) umma::mma_commit(&bar);
+    if (leader) umma::mma_commit(&bar[warp]);
     __syncwarp();
-    umma::mbar_wait(&bar, 0);
+    umma::mbar_wait(&bar[warp], 0);
     const long long t2 = clock64();
-    if (leader) { cycles_out[0] = t1 - t0; cycles_out[1] = t2 - t0; }
+    if (leader) { cycles_out[2 * warp] = t1 - t0; cycles_out[2 * warp + 1] = t2 - t0; }
   }
   umma::tc_fence_before();
   __syncthreads();
@@ -410,11 +421,13 @@ extern "C" int lrx_debug_umma_rate(int32_t M, int32_t N, int32_t dsplit, long lo
   const size_t smem = 16384;
   cudaStream_t s = (cudaStream_t)stream;
   const int a_mn = (dsplit >> 8) & 1, b_mn = (dsplit >> 9) & 1;  // operand majorness rides in the upper bits
+  const int a_tmem = (dsplit >> 10) & 1;
+  const int issuers = 1 + ((dsplit >> 11) & 3);  // `cycles` must hold 2 * issuers values
   dsplit &= 0xff;
-  if (dsplit == 1) umma_rate_kernel<1><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles);
-  else if (dsplit == 2) umma_rate_kernel<2><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles);
-  else if (dsplit == 4) umma_rate_kernel<4><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles);
-  else umma_rate_kernel<8><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles);
+  if (dsplit == 1) umma_rate_kernel<1><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles, a_tmem, issuers);
+  else if (dsplit == 2) umma_rate_kernel<2><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles, a_tmem, issuers);
+  else if (dsplit == 4) umma_rate_kernel<4><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles, a_tmem, issuers);
+  else umma_rate_kernel<8><<<1, 128, smem, s>>>(M, N, a_mn, b_mn, cycles, a_tmem, issuers);
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }
