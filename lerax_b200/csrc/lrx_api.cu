@@ -28,17 +28,17 @@ extern "C" int64_t lrx_launch_count(int reset) {
 
 // Kernel selection for default-width policies (include/lerax_b200_debug.h): 2 = newest tensor-core kernels (default),
 // 1 = first-generation tensor-core update kernel, 0 = generic-width kernels everywhere.  Initial value from the
-// environment (LRX_FUSED=0/1/2, LRX_DISABLE_FUSED=1).  A test hook: the tests run the implementations against each other.
+// environment (LRX_FUSED=0..4, LRX_DISABLE_FUSED=1).  A test hook: the tests run the implementations against each other.
 static int g_fused = -1;
 int lrx_fused_enabled() {
   if (g_fused < 0) {
     const char* d = getenv("LRX_DISABLE_FUSED");
     const char* e = getenv("LRX_FUSED");
-    g_fused = (d && d[0] == '1') ? 0 : (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;
+    g_fused = (d && d[0] == '1') ? 0 : (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 4;
   }
   return g_fused;
 }
-extern "C" void lrx_debug_set_fused(int level) { g_fused = level < 0 ? 0 : level > 3 ? 3 : level; }
+extern "C" void lrx_debug_set_fused(int level) { g_fused = level < 0 ? 0 : level > 4 ? 4 : level; }
 
 int lrx_sm_count() {
   int dev = 0, n = 0;

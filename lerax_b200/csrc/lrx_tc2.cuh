@@ -26,7 +26,10 @@ struct Mat {
   uint8_t* ptr;     // hi piece
   uint32_t R;       // rows
   uint32_t lo_off;  // byte distance hi -> lo piece
+  uint32_t cgs = 0; // byte distance between c-groups when it is not R * 16 (0 = contiguous): a two-c-group matrix may keep
+                    // its second c-group anywhere, e.g. share another matrix's constant ones column
 };
+__device__ __forceinline__ uint32_t cg_stride(const Mat& m) { return m.cgs ? m.cgs : m.R * 16u; }
 
 // two adjacent columns (c even at the lower address) -> hi word, lo word
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -58,15 +61,15 @@ __device__ __forceinline__ void store4(const Mat& m, int c0, int r, const float*
 
 template <bool MN>
 __device__ __forceinline__ uint32_t desc_hi(const Mat& m) {
-  return ((MN ? m.R * 16u : 128u) >> 4) | (1u << 14);  // SBO | version
+  return ((MN ? cg_stride(m) : 128u) >> 4) | (1u << 14);  // SBO | version
 }
 template <bool MN>
 __device__ __forceinline__ uint32_t desc_lo(const Mat& m) {
-  return ((umma::smem_u32(m.ptr) >> 4) & 0x3FFFu) | (((MN ? 128u : m.R * 16u) >> 4) << 16);  // addr | LBO
+  return ((umma::smem_u32(m.ptr) >> 4) & 0x3FFFu) | (((MN ? 128u : cg_stride(m)) >> 4) << 16);  // addr | LBO
 }
 template <bool MN>
 __device__ __forceinline__ uint32_t desc_kstep(const Mat& m) {
-  return (MN ? 256u : 2u * m.R * 16u) >> 4;
+  return (MN ? 256u : 2u * cg_stride(m)) >> 4;
 }
 
 // D[tmem] (+)= A * B^T over `ksteps` slices of K = 16, three products per slice, smallest first:

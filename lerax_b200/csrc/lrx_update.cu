@@ -807,14 +807,23 @@ int lrx_ppo_grad_pp64(const LrxPolicyDesc* pol, const float* params, const LrxBa
                       int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, float* gradbuf,
                       void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled,
                       const LrxApplyArgs* apply);
+int lrx_ppo_grad_tc128c(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,
+                        int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, float* gradbuf,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled,
+                        const LrxApplyArgs* apply);
+// Default-width policies, by lrx_fused_enabled(): 4 = 128-row kernel with composite weights (lrx_update_tc128c.cu, the default),
+// 3 = two half tiles in flight (lrx_update_pp64.cu), 2 = 128-row kernel (lrx_update_tc128.cu), 1 = first generation.
 // Default-width policies: third-generation (two half tiles in flight, lrx_update_pp64.cu), second-generation tensor-core kernel (lrx_update_tc128.cu), else the first-generation one
 // (lrx_update_fused.cu); `handled` stays false for other widths (or with the kernels switched off).
 static int lrx_ppo_grad_tensor(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,
                                int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, float* gradbuf,
                                void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled,
                                const LrxApplyArgs* apply) {
-  int rc = lrx_ppo_grad_pp64(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, stream,
-                             handled, apply);
+  int rc = lrx_ppo_grad_tc128c(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, stream,
+                               handled, apply);
+  if (rc || *handled) return rc;
+  rc = lrx_ppo_grad_pp64(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, stream,
+                         handled, apply);
   if (rc || *handled) return rc;
   rc = lrx_ppo_grad_tc128(pol, params, buf, idx, B, B_global, adv_sums, h, gradbuf, workspace, workspace_bytes, stream,
                           handled, apply);

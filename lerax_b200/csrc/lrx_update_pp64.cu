@@ -1004,7 +1004,7 @@ int lrx_ppo_grad_pp64(const LrxPolicyDesc* pol, const float* params, const LrxBa
                       void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled,
                       const LrxApplyArgs* apply) {
   *handled = false;
-  if (!tc::is_default_policy(*pol) || lrx_fused_enabled() < 3) return LRX_OK;
+  if (!tc::is_default_policy(*pol) || lrx_fused_enabled() != 3) return LRX_OK;
   FusedWorkspace w = carve_fused(*pol, workspace);
   LRX_REQUIRE(workspace_bytes >= w.total, LRX_ERR_INVALID_ARG, "lrx_ppo_grad: workspace too small for the fused path");
   Pp64Args a{};

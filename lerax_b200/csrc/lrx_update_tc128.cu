@@ -943,6 +943,7 @@ int lrx_launch_reduce_partials(const float* partial, int splits, long long strid
 
 static long long* g_tc128_prof = nullptr;  // test hook, include/lerax_b200_debug.h
 extern "C" void lrx_debug_set_tc128_prof(long long* device_buffer_64) { g_tc128_prof = device_buffer_64; }
+long long* lrx_tc128_prof_ptr() { return g_tc128_prof; }
 
 // Same workspace layout as the first-generation kernel (lrx_fused_workspace_bytes covers both).
 int lrx_ppo_grad_tc128(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,

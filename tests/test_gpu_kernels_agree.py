@@ -19,8 +19,8 @@ KINDS = ["cartpole", "pendulum", "acrobot", "mountain_car", "continuous_mountain
 def fused_toggle():
     from lerax_b200 import _lib as L
 
-    yield L.debug_lib().lrx_debug_set_fused  # 3: two half tiles in flight, 2: 128-row tensor-core kernels, 1: first-generation update kernel, 0: generic
-    L.debug_lib().lrx_debug_set_fused(2)
+    yield L.debug_lib().lrx_debug_set_fused  # 4: 128-row kernel with composite weights (default), 3: two half tiles in flight, 2: 128-row tensor-core kernels, 1: first-generation update kernel, 0: generic
+    L.debug_lib().lrx_debug_set_fused(4)
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -47,7 +47,7 @@ def test_rollout_tensor_core_vs_generic(kind, mes, fused_toggle):
         H.assert_close(a[name], b[name], 1e-4, drift, name)
 
 
-@pytest.mark.parametrize("level", [3, 2, 1])
+@pytest.mark.parametrize("level", [4, 3, 2, 1])
 @pytest.mark.parametrize("kind", KINDS)
 def test_gradient_tensor_core_vs_generic(kind, level, fused_toggle):
     T, N, B = 40, 33, 1000  # 7 full 128-row tiles (15 of 64 rows for the first-generation kernel) + a ragged one
@@ -107,7 +107,7 @@ def test_full_size_properties():
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("level", [3, 2, 1])
+@pytest.mark.parametrize("level", [4, 3, 2, 1])
 @pytest.mark.parametrize("kind", ["cartpole", "pendulum", "mountain_car"])
 def test_gradient_many_tiles_per_cta_vs_generic(kind, level, fused_toggle):
     """Every CTA of the fused kernel walks two or three tiles (row staging reuse, buffer reuse across tiles, a ragged

@@ -28,9 +28,15 @@ p = prof.cpu().tolist()
 launches = 32
 tiles = (N * T // 32 + 127) // 128
 tiles_cta0 = (tiles + 147) // 148
+level = int(os.environ.get("LRX_FUSED", "4"))
+names4 = ["", "top: wait rows, enc0 FMA + XH1", "enc1 (MMA + epi)", "heads layer 0 (composite)", "v1 + value dot", "value loss + dY",
+          "v1 bwd + a0 fwd epi", "logits + policy loss", "a1 bwd", "h2 bwd (composite)", "enc1 bwd", "g0 only step", "-", "-",
+          "(loop overhead)", "tail wait", "flush"]
 names = ["", "top: enc0 FMA + XH1", "enc1 (MMA + epi)", "enc2", "v0 (+a0 bg)", "v1 + value dot", "value loss + dY", "v1 bwd + a0 fwd epi",
          "a1 + policy loss", "a1 bwd", "a0 bwd -> dfeat", "enc2 bwd", "enc1 bwd", "g0 only step", "(loop overhead)", "tail wait", "flush"]
-tot = sum(p[1:14])
+if level >= 4:
+    names = names4
+tot = sum(p[1:15])
 print(f"{tiles_cta0} tiles per CTA, {launches} launches; cycles per tile (row-owner thread 0 | issuer lane 0)")
 for k in range(1, 17):
     per = launches * tiles_cta0 if k <= 14 else launches
@@ -38,7 +44,8 @@ for k in range(1, 17):
 print("barrier wait per step (thread 0 | issuer):")
 for k in range(1, 12):
     per = launches * tiles_cta0
-    print(f"  step {k:2d}: {p[16 + k] / per:7.0f} | {p[48 + k] / per:7.0f}")
+    if level < 4:
+        print(f"  step {k:2d}: {p[16 + k] / per:7.0f} | {p[48 + k] / per:7.0f}")
 print(f"tile total {tot / (launches * tiles_cta0):.0f} cycles")
 print("flush per launch (thread 0): barrier + TMEM -> staging + register sums %d | barrier %d | staging -> global + final sums %d" % (
     p[64] / launches, p[65] / launches, p[66] / launches))
