@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 
 METRIC = "env-steps/sec (rollout+GAE+PPO update)"
 UNIT = "env-steps/s"
-UPDATE_KERNEL = "ppo_grad_tc128_kernel"  # the tensor-core gradient kernel default-width policies run (profiles/kernels.json key)
+UPDATE_KERNEL = "ppo_grad_tc128c_kernel"  # the tensor-core gradient kernel default-width policies run (profiles/kernels.json key)
 
 WIDE = dict(feature_width=256, value_width=256, action_width=256)
 # name -> env, envs (per GPU for weak scaling, TOTAL for strong), horizon, epochs, minibatches, policy kwargs, scaling

@@ -858,6 +858,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128c_kernel(const __gri
       const float g1 = G[64];
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 8
       for (int i = 0; i < 64; ++i) {
         const float gi = G[i];
         const float4 w0 = *reinterpret_cast<const float4*>(stg + S_W2T + i * 16 + kh * 8);
@@ -873,6 +874,7 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128c_kernel(const __gri
       // dW2 [16][64] = Wv0^T Gv_h + Wa0^T Ga_h: thread = (input i, 4 of the 16 k)
       const int t = tid - 256, i = t & 63, kg = t >> 6;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
       for (int o = 0; o < 64; ++o) {
         const float gv = stg[S_GV + o * 65 + i], ga = stg[S_GA + o * 65 + i];
         const float4 wv = *reinterpret_cast<const float4*>(stg + S_WV0 + o * 16 + kg * 4);

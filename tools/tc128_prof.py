@@ -29,8 +29,8 @@ launches = 32
 tiles = (N * T // 32 + 127) // 128
 tiles_cta0 = (tiles + 147) // 148
 level = int(os.environ.get("LRX_FUSED", "4"))
-names4 = ["", "top: wait rows, enc0 FMA + XH1", "enc1 (MMA + epi)", "heads layer 0 (composite)", "v1 + value dot", "value loss + dY",
-          "v1 bwd + a0 fwd epi", "logits + policy loss", "a1 bwd", "h2 bwd (composite)", "enc1 bwd", "g0 only step", "-", "-",
+names4 = ["", "enc0 (MMA + epi)", "enc1 (MMA + epi)", "heads layer 0 (composite)", "v1 + value dot", "value loss + dY",
+          "v1 bwd + a0 fwd epi", "logits + policy loss", "a1 bwd", "h2 bwd (composite)", "enc1 bwd", "g0 only step", "top: wait rows + XOBS", "-",
           "(loop overhead)", "tail wait", "flush"]
 names = ["", "top: enc0 FMA + XH1", "enc1 (MMA + epi)", "enc2", "v0 (+a0 bg)", "v1 + value dot", "value loss + dY", "v1 bwd + a0 fwd epi",
          "a1 + policy loss", "a1 bwd", "a0 bwd -> dfeat", "enc2 bwd", "enc1 bwd", "g0 only step", "(loop overhead)", "tail wait", "flush"]
@@ -49,3 +49,4 @@ for k in range(1, 12):
 print(f"tile total {tot / (launches * tiles_cta0):.0f} cycles")
 print("flush per launch (thread 0): barrier + TMEM -> staging + register sums %d | barrier %d | staging -> global + final sums %d" % (
     p[64] / launches, p[65] / launches, p[66] / launches))
+print("flush phases (thread 0 | issuer):", [round(p[64 + k] / launches) for k in range(7)], [round(p[96 + k] / launches) for k in range(7)])
