@@ -31,14 +31,22 @@ struct Mat {
 };
 __device__ __forceinline__ uint32_t cg_stride(const Mat& m) { return m.cgs ? m.cgs : m.R * 16u; }
 
-// two adjacent columns (c even at the lower address) -> hi word, lo word
+// two adjacent columns (c even at the lower address) -> hi word, lo word.
+// The lo piece is stored NEGATED (lo' = bf16(hi - x)): the mixed-precision subtract of sm_100 (sub.f32.bf16, SASS FHADD.BF16
+// with a half selector) takes the packed hi word as it is, so the split is four instructions per pair instead of six, and
+// the two cross products of gemm() put the sign back with the instruction descriptor's negate bits.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  const float ra = a - __low2float(h), rb = b - __high2float(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  uint32_t h, l;
+  float da, db;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+  asm("{\n\t.reg .b16 l16, u16;\n\tmov.b32 {l16, u16}, %2;\n\tsub.rn.f32.bf16 %0, l16, %3;\n\tsub.rn.f32.bf16 %1, u16, %4;\n\t}"
+      : "=f"(da), "=f"(db)
+      : "r"(h), "f"(a), "f"(b));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(db), "f"(da));
+  hi = h;
+  lo = l;
 }
+constexpr uint32_t NEG_A = 1u << 13, NEG_B = 1u << 14;  // instruction descriptor: negate the A / B operand
 
 // 8 consecutive columns (one 16-byte chunk) of row r
 __device__ __forceinline__ void store8(const Mat& m, int chunk, int r, const float* v) {
@@ -91,8 +99,8 @@ __device__ __forceinline__ void gemm(bool leader, uint32_t d_tmem, const Mat& A,
 #pragma unroll 1
   for (int ks = 0; ks < ksteps; ++ks) {
     if (leader) {
-      umma::mma_f16(d_tmem, ah, bl, idesc_lo, acc);
-      umma::mma_f16(d_tmem, al, bh, idesc, N_lo == N ? 1u : acc);
+      umma::mma_f16(d_tmem, ah, bl, idesc_lo | NEG_B, acc);
+      umma::mma_f16(d_tmem, al, bh, idesc | NEG_A, N_lo == N ? 1u : acc);
       umma::mma_f16(d_tmem, ah, bh, idesc, 1u);
     }
     acc = 1u;
