@@ -47,6 +47,23 @@ class GradientExchange:
                                         L.ptr(self._scratch), self._scratch.numel(), L.stream_ptr()),
                 "lrx_ppo_apply_p2p")
 
+    def grad_apply(self, pol_desc, policy, opt_state, view, idx_row, B_local, B_global, adv_sums, hyper, stats_out,
+                   nonfinite, workspace) -> bool:
+        """One minibatch in two launches (lrx_ppo_grad_apply_p2p): gradient kernel, then reduce + block-wise exchange +
+        clip + Adam.  Returns False (nothing enqueued, seq untouched) for policies the fused gradient kernels do not cover."""
+        self.seq += 1
+        handled = C.c_int32(0)
+        L.check(L.lib.lrx_ppo_grad_apply_p2p(pol_desc, L.ptr(policy.params), L.ptr(opt_state.mu), L.ptr(opt_state.nu),
+                                             L.ptr(opt_state.count), view, L.ptr(idx_row), B_local, B_global,
+                                             L.ptr(adv_sums), hyper, L.ptr(self.addresses), self._own, self.rank,
+                                             self.world, self._seq32(), L.ptr(stats_out), L.ptr(nonfinite),
+                                             L.ptr(self.error), L.ptr(workspace), workspace.numel(), L.stream_ptr(),
+                                             C.byref(handled)), "lrx_ppo_grad_apply_p2p")
+        if not handled.value:
+            self.seq -= 1
+            return False
+        return True
+
     def check(self) -> None:
         if int(self.error.item()) != 0:
             raise RuntimeError("lrx_p2p_allreduce: a peer rank did not publish its gradient within 10 s")

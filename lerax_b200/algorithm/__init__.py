@@ -11,6 +11,7 @@ with more than one rank).  Host code only sequences launches; nothing is compute
 from __future__ import annotations
 
 import copy
+import os
 
 from dataclasses import dataclass
 from typing import Any, Callable, Sequence
@@ -281,8 +282,18 @@ class PPO(AbstractAlgorithm):
             if dist is not None:
                 dist.all_reduce(b["adv_sums"])  # one collective for the whole epoch
             ex = self._exchange(policy, dist)
+            # LRX_P2P_FUSED=1: the two-launch variant (lrx_ppo_grad_apply_p2p); measured 5 us per minibatch SLOWER than the
+            # three calls below at 2 GPUs (407 blocks each fencing and polling at system scope), so it is opt-in
+            fused_p2p = ex is not None and os.environ.get("LRX_P2P_FUSED", "0") == "1"
             for i in range(nb):
                 h = self._hyper(self._lr_at(count))
+                if fused_p2p:
+                    # two launches per minibatch: gradient kernel, then reduce + block-wise NVLink exchange + clip + Adam
+                    if ex.grad_apply(pol_d, policy, opt_state, view, idx[i], B_local, B_global, b["adv_sums"][i], h,
+                                     stats[e, i], b["nonfinite"], b["workspace"]):
+                        count += 1
+                        continue
+                    fused_p2p = False  # a policy the fused gradient kernels do not cover: three calls per minibatch
                 # the local gradient goes straight into this rank's exchange slot when peers read it over NVLink
                 grad_dst = ex.next_slot() if ex is not None else L.ptr(b["gradbuf"])
                 L.check(L.lib.lrx_ppo_grad(pol_d, L.ptr(policy.params), view, L.ptr(idx[i]), B_local, B_global,

@@ -6,7 +6,15 @@
 
 namespace p2p {
 
-constexpr size_t HEADER = 128;  // flag (uint32 at offset 0), padded to a line
+// Buffer = [global flag (uint32 at offset 0), padded to a line | per-block flags of slot 0 | of slot 1 | slot 0 | slot 1].
+// The global flag serves lrx_p2p_allreduce / lrx_ppo_apply_p2p (whole-slot publish); the per-block flags serve the fused
+// reduce + exchange + apply kernel of lrx_ppo_grad_apply_p2p, where block b of a rank only depends on block b of its peers.
+constexpr int MAX_BLOCK_FLAGS = 1024;
+constexpr size_t GLOBAL_FLAG_BYTES = 128;
+constexpr size_t HEADER = GLOBAL_FLAG_BYTES + 2 * (size_t)MAX_BLOCK_FLAGS * 4;  // 8320 = 65 lines
+__host__ __device__ inline uint32_t* block_flag(char* buffer, uint32_t seq, int block) {
+  return reinterpret_cast<uint32_t*>(buffer + GLOBAL_FLAG_BYTES) + (size_t)(seq & 1u) * MAX_BLOCK_FLAGS + block;
+}
 
 __host__ __device__ inline size_t slot_bytes(int n_floats) { return ((size_t)n_floats * 4 + 127) / 128 * 128; }
 

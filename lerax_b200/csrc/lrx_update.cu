@@ -368,6 +368,14 @@ __global__ void __launch_bounds__(LRX_LOSS_THREADS) loss_kernel(const LossArgs a
 struct LrxApplyArgs {
   float* params; float* m; float* v; int32_t* count; LrxPpoHyper h; float* stats_out; int32_t* nonfinite_flag;
   double* blk_ss;        // [gridDim.x]
+  // multi-GPU (lrx_ppo_grad_apply_p2p): `gradbuf` is this rank's exchange slot; after the local reduction every block
+  // publishes ITS 32 entries (per-block flag), waits for the same block of every peer and sums the G slots in rank order
+  char* const* peers;    // device array of the G exchange buffers; nullptr = single GPU
+  int rank, world;
+  size_t slot_b;
+  uint32_t seq;
+  int* error_flag;
+  float* gsum;           // [P + LRX_PPO_NSTATS]: the summed statistics and log_std entry (block 0 -> everyone, after the grid barrier)
 };
 
 __global__ void __launch_bounds__(256)
@@ -408,19 +416,62 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
   if (blockIdx.x == 0 && threadIdx.x == 255) { gradbuf[P + 4] = 0.f; gradbuf[P + 5] = 0.f; gradbuf[P + 7] = 0.f; }
   if (!ap.params) return;
 
+  // ---- multi-GPU: the exchange, block by block.  Block b's 32 entries of the own slot are complete -> release its flag;
+  // wait for block b of every peer (they run the same grid); sum the G slots in rank order (bit-identical on every rank).
+  // No grid-wide barrier and no second launch between the local reduction and the exchange; two slots suffice because a
+  // rank reaches seq + 2 only after its block b saw every peer's block b at seq + 1, i.e. after they finished kernel seq.
+  const bool p2p_on = ap.peers != nullptr;
+  bool peer_lost = false;
+  double lsg_ss = 0;  // p2p: the summed log_std entry's contribution to the norm (block 0, warp 1, lane 8)
+  if (p2p_on) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      p2p::st_release_sys(p2p::block_flag(ap.peers[ap.rank], ap.seq, blockIdx.x), ap.seq);
+    }
+    int timed_out = 0;
+    if ((int)threadIdx.x < ap.world) {
+      const uint32_t* flag = p2p::block_flag(ap.peers[threadIdx.x], ap.seq, blockIdx.x);
+      const long long t0 = clock64();
+      while ((int32_t)(p2p::ld_acquire_sys(flag) - ap.seq) < 0) {
+        if (clock64() - t0 > 20000000000LL) {  // a peer is gone -- report instead of hanging the GPU
+          *ap.error_flag = 1;
+          timed_out = 1;
+          break;
+        }
+        __nanosleep(200);
+      }
+    }
+    peer_lost = __syncthreads_or(timed_out) != 0;
+    if (!peer_lost) {
+      if (rg == 0 && p < P && p != log_std_off) t = p2p::peer_sum(ap.peers, ap.world, ap.slot_b, ap.seq, p);
+      if (blockIdx.x == 0 && rg == 1) {  // the statistics and the log_std entry: written by block 0 on every rank
+        if (pl < LRX_PPO_NSTATS) {
+          ap.gsum[P + pl] = p2p::peer_sum(ap.peers, ap.world, ap.slot_b, ap.seq, P + pl);
+        } else if (pl == LRX_PPO_NSTATS && log_std_off >= 0) {
+          const float gs = p2p::peer_sum(ap.peers, ap.world, ap.slot_b, ap.seq, log_std_off);
+          ap.gsum[log_std_off] = gs;
+          const float gl = gs + (-ap.h.entropy_loss_coefficient);
+          lsg_ss = (double)gl * gl;
+        }
+      }
+    }
+  }
+
   // ---- fused apply (cooperative launch): per-block sum of squares (the log_std entry, owned by
   // block 0, carries the -c_H entropy term exactly as lrx_ppo_apply adds it), grid barrier, every
   // block rebuilds the same global norm in block order and updates ITS 32 parameters.
   double ss = 0;
   if (rg == 0) ss = (double)t * t;
-  if (blockIdx.x == 0 && rg == 4 && pl == 0 && log_std_off >= 0) {
+  if (!p2p_on && blockIdx.x == 0 && rg == 4 && pl == 0 && log_std_off >= 0) {
     const float gl = (float)lsg + (-ap.h.entropy_loss_coefficient);
     ss = (double)gl * gl;
   }
+  if (p2p_on && rg == 1) ss = lsg_ss;
   ss = warp_sum(ss);
   if (pl == 0) red[rg] = ss;
   __syncthreads();
-  if (threadIdx.x == 0) ap.blk_ss[blockIdx.x] = red[0] + red[4];
+  if (threadIdx.x == 0) ap.blk_ss[blockIdx.x] = p2p_on ? red[0] + red[1] : red[0] + red[4];
   const int cnt = *ap.count + 1;  // read before the barrier; block 0 stores it after
   cooperative_groups::this_grid().sync();
   double acc = 0;
@@ -434,13 +485,16 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
   for (int i = 0; i < 8; ++i) tt += red[i];
   const float norm = (float)sqrt(tt);
   const LrxPpoHyper& h = ap.h;
-  const float nbad = __ldcg(gradbuf + P + 6);
-  const bool bad = nbad > 0.f || !isfinite(norm);
+  // a peer that timed out in ANY block (the flag is sticky) voids the exchange for every block alike
+  if (p2p_on) peer_lost = *reinterpret_cast<volatile int*>(ap.error_flag) != 0;
+  const float* gsrc = p2p_on ? ap.gsum : gradbuf;  // where the (summed) statistics and log_std entry are
+  const float nbad = peer_lost ? 0.f : __ldcg(gsrc + P + 6);
+  const bool bad = peer_lost || nbad > 0.f || !isfinite(norm);
   if (!bad && rg == 0 && p < P) {
     const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
     const float bc1 = 1.0f - powf(h.adam_b1, (float)cnt);
     const float bc2 = 1.0f - powf(h.adam_b2, (float)cnt);
-    float gp = __ldcg(gradbuf + p) + (p == log_std_off ? ls_extra : 0.f);
+    float gp = (p2p_on && p != log_std_off) ? t : __ldcg(gsrc + p) + (p == log_std_off ? ls_extra : 0.f);
     if (!(norm < h.max_grad_norm)) gp = (gp / norm) * h.max_grad_norm;
     const float mn = h.adam_b1 * ap.m[p] + (1.0f - h.adam_b1) * gp;
     const float vn = h.adam_b2 * ap.v[p] + (1.0f - h.adam_b2) * (gp * gp);
@@ -451,12 +505,12 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (!bad) *ap.count = cnt;
-    else if (ap.nonfinite_flag) atomicOr(ap.nonfinite_flag, 1);
-    if (ap.stats_out) {
-      const float kl = __ldcg(gradbuf + P + 0) - 1.0f;
-      const float plo = -__ldcg(gradbuf + P + 1);
-      const float vl = __ldcg(gradbuf + P + 2) / 2.0f;
-      const float el = -__ldcg(gradbuf + P + 3);
+    else if (ap.nonfinite_flag && !peer_lost) atomicOr(ap.nonfinite_flag, 1);
+    if (ap.stats_out && !peer_lost) {
+      const float kl = __ldcg(gsrc + P + 0) - 1.0f;
+      const float plo = -__ldcg(gsrc + P + 1);
+      const float vl = __ldcg(gsrc + P + 2) / 2.0f;
+      const float el = -__ldcg(gsrc + P + 3);
       ap.stats_out[0] = kl;
       ap.stats_out[1] = plo + vl * h.value_loss_coefficient + el * h.entropy_loss_coefficient;
       ap.stats_out[2] = plo;
@@ -1001,6 +1055,47 @@ extern "C" int lrx_ppo_apply_p2p(const LrxPolicyDesc* pol, float* params, float*
   LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)apply_p2p_kernel, dim3(want < cap ? want : cap), dim3(256), args, 0,
                                              (cudaStream_t)stream));
   LRX_LAUNCH_CHECK();
+  return LRX_OK;
+}
+
+// Multi-GPU minibatch in TWO launches: the gradient kernel, then one cooperative kernel that reduces the per-CTA partials
+// into this rank's exchange slot, exchanges block by block over NVLink peer memory and applies clip + Adam.
+// *handled = 0 (nothing launched) for policies the fused gradient kernels do not cover: the caller then runs
+// lrx_ppo_grad -> lrx_ppo_apply_p2p.
+extern "C" int lrx_ppo_grad_apply_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
+                                      int32_t* adam_count, const LrxBatchView* buf, const int32_t* idx, int64_t B,
+                                      int64_t B_global, const double* adv_sums, const LrxPpoHyper* h,
+                                      void* const* peer_buffers, void* own_buffer, int32_t rank, int32_t world,
+                                      uint32_t seq, float* stats_out, int32_t* nonfinite_flag, int32_t* error_flag,
+                                      void* workspace, size_t workspace_bytes, lrx_stream_t stream, int32_t* handled) {
+  LRX_REQUIRE(handled, LRX_ERR_INVALID_ARG, "lrx_ppo_grad_apply_p2p: NULL handled");
+  *handled = 0;
+  int rc = validate_update_args(pol, buf, h);
+  if (rc) return rc;
+  LRX_REQUIRE(params && adam_m && adam_v && adam_count && idx && peer_buffers && own_buffer && error_flag && workspace &&
+                  B > 0 && B_global >= B,
+              LRX_ERR_INVALID_ARG, "lrx_ppo_grad_apply_p2p: bad argument");
+  LRX_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && seq != 0, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_grad_apply_p2p: bad rank / world / seq");
+  LRX_REQUIRE(workspace_bytes >= lrx_ppo_workspace_bytes(pol, B), LRX_ERR_INVALID_ARG,
+              "lrx_ppo_grad_apply_p2p: workspace too small");
+  const int grid = (pol->n_params + 31) / 32;
+  if (grid > p2p::MAX_BLOCK_FLAGS || grid > 4 * lrx_sm_count()) return LRX_OK;  // not one resident cooperative wave
+  const WorkspaceTail tail = workspace_tail(pol, B);
+  const int n = pol->n_params + LRX_PPO_NSTATS;
+  LrxApplyArgs ap{};
+  ap.params = params; ap.m = adam_m; ap.v = adam_v; ap.count = adam_count; ap.h = *h;
+  ap.stats_out = stats_out; ap.nonfinite_flag = nonfinite_flag;
+  ap.blk_ss = (double*)((char*)workspace + tail.scratch_off);
+  ap.peers = reinterpret_cast<char* const*>(peer_buffers);
+  ap.rank = rank; ap.world = world; ap.slot_b = p2p::slot_bytes(n); ap.seq = seq; ap.error_flag = error_flag;
+  ap.gsum = (float*)((char*)workspace + tail.gradbuf_off);
+  float* slot = reinterpret_cast<float*>(static_cast<char*>(own_buffer) + p2p::HEADER + (size_t)(seq & 1u) * ap.slot_b);
+  bool done = false;
+  rc = lrx_ppo_grad_tensor(pol, params, buf, idx, B, B_global, adv_sums, h, slot, workspace, tail.adv_sums_off,
+                           (cudaStream_t)stream, &done, &ap);
+  if (rc) return rc;
+  *handled = done ? 1 : 0;
   return LRX_OK;
 }
 
