@@ -320,6 +320,12 @@ int lrx_ppo_apply_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, fl
                       float* stats_out, int32_t* nonfinite_flag, int32_t* error_flag, void* scratch,
                       size_t scratch_bytes, lrx_stream_t stream);
 
+/* lrx_ppo_grad into slot `seq & 1` of this rank's exchange buffer (lrx_p2p_alloc), with the slot published (flag = seq) by
+ * the last block of the partial reduction: the flag reaches the peers while lrx_ppo_apply_p2p is being launched. */
+int lrx_ppo_grad_p2p(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx, int64_t B,
+                     int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, void* own_buffer, uint32_t seq,
+                     void* workspace, size_t workspace_bytes, lrx_stream_t stream);
+
 /* One minibatch of the multi-GPU update in two launches (default-width policies): lrx_ppo_grad's gradient kernel, then ONE
  * cooperative kernel that reduces the per-CTA partials into this rank's exchange slot `seq & 1`, publishes and awaits the
  * peers block by block (per-block flags in the exchange buffer's header), sums the slots in rank order and applies

@@ -30,6 +30,13 @@ class GradientExchange:
         self.seq += 1
         return int(L.lib.lrx_p2p_slot(self._own, self.n, self._seq32()))
 
+    def grad(self, pol_desc, policy, view, idx_row, B_local, B_global, adv_sums, hyper, workspace) -> None:
+        """lrx_ppo_grad_p2p: the next minibatch's gradient into this rank's slot, published by the reduction's last block."""
+        self.seq += 1
+        L.check(L.lib.lrx_ppo_grad_p2p(pol_desc, L.ptr(policy.params), view, L.ptr(idx_row), B_local, B_global,
+                                       L.ptr(adv_sums), hyper, self._own, self._seq32(), L.ptr(workspace),
+                                       workspace.numel(), L.stream_ptr()), "lrx_ppo_grad_p2p")
+
     def allreduce(self, out) -> None:
         """Sum of the slots published for the current seq, in rank order, into `out` (float32 [n])."""
         L.check(L.lib.lrx_p2p_allreduce(L.ptr(self.addresses), self.rank, self.world, self.n, L.ptr(out), self._seq32(),

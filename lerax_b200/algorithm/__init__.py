@@ -294,11 +294,13 @@ class PPO(AbstractAlgorithm):
                         count += 1
                         continue
                     fused_p2p = False  # a policy the fused gradient kernels do not cover: three calls per minibatch
-                # the local gradient goes straight into this rank's exchange slot when peers read it over NVLink
-                grad_dst = ex.next_slot() if ex is not None else L.ptr(b["gradbuf"])
-                L.check(L.lib.lrx_ppo_grad(pol_d, L.ptr(policy.params), view, L.ptr(idx[i]), B_local, B_global,
-                                           L.ptr(b["adv_sums"][i]), h, grad_dst, ws, ws_bytes,
-                                           L.stream_ptr()), "lrx_ppo_grad")
+                if ex is not None:
+                    # the local gradient goes straight into this rank's exchange slot, published as soon as it is complete
+                    ex.grad(pol_d, policy, view, idx[i], B_local, B_global, b["adv_sums"][i], h, b["workspace"])
+                else:
+                    L.check(L.lib.lrx_ppo_grad(pol_d, L.ptr(policy.params), view, L.ptr(idx[i]), B_local, B_global,
+                                               L.ptr(b["adv_sums"][i]), h, L.ptr(b["gradbuf"]), ws, ws_bytes,
+                                               L.stream_ptr()), "lrx_ppo_grad")
                 if ex is not None:
                     # SUM over the ranks' exchange slots (NVLink peer memory, rank order) + clip + Adam: one launch
                     ex.apply(pol_d, policy, opt_state, h, stats[e, i], b["nonfinite"])

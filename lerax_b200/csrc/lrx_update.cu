@@ -376,6 +376,11 @@ struct LrxApplyArgs {
   uint32_t seq;
   int* error_flag;
   float* gsum;           // [P + LRX_PPO_NSTATS]: the summed statistics and log_std entry (block 0 -> everyone, after the grid barrier)
+  // multi-GPU, three-call path (lrx_ppo_grad_p2p; params == nullptr): the LAST block to finish the reduction publishes the
+  // slot (own global flag = publish_seq), so the flag travels to the peers while lrx_ppo_apply_p2p is still being launched
+  uint32_t* publish_flag;
+  uint32_t publish_seq;
+  unsigned* ticket;      // zero between launches (the last block resets it)
 };
 
 __global__ void __launch_bounds__(256)
@@ -414,6 +419,15 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 255) { gradbuf[P + 4] = 0.f; gradbuf[P + 5] = 0.f; gradbuf[P + 7] = 0.f; }
+  if (ap.publish_flag) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(ap.ticket, 1u) == gridDim.x - 1) {
+      *ap.ticket = 0u;
+      __threadfence_system();  // every block's stores to the slot (observed through the ticket) before the flag
+      p2p::st_release_sys(ap.publish_flag, ap.publish_seq);
+    }
+  }
   if (!ap.params) return;
 
   // ---- multi-GPU: the exchange, block by block.  Block b's 32 entries of the own slot are complete -> release its flag;
@@ -796,6 +810,10 @@ int lrx_launch_reduce_partials(const float* partial, int splits, long long strid
                                const LrxApplyArgs* apply, cudaStream_t s) {
   LrxApplyArgs ap{};
   const int grid = (P + 31) / 32;
+  if (apply && !apply->params) {  // no update, only the early publish of the slot
+    ap = *apply;
+    apply = nullptr;
+  }
   if (apply && grid <= 4 * lrx_sm_count()) {
     // fused reduce + clip + Adam: needs every block resident at once (grid barrier) -> cooperative launch
     ap = *apply;
@@ -1056,6 +1074,32 @@ extern "C" int lrx_ppo_apply_p2p(const LrxPolicyDesc* pol, float* params, float*
                                              (cudaStream_t)stream));
   LRX_LAUNCH_CHECK();
   return LRX_OK;
+}
+
+// lrx_ppo_grad for the NVLink exchange: the gradient goes into slot `seq & 1` of this rank's exchange buffer and the reduction
+// kernel's last block publishes `seq` in the buffer's flag, so the peers can read the slot while this rank's
+// lrx_ppo_apply_p2p (which publishes the same value again: harmless) is still being launched.
+extern "C" int lrx_ppo_grad_p2p(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,
+                                int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, void* own_buffer,
+                                uint32_t seq, void* workspace, size_t workspace_bytes, lrx_stream_t stream) {
+  int rc = validate_update_args(pol, buf, h);
+  if (rc) return rc;
+  LRX_REQUIRE(params && idx && own_buffer && workspace && B > 0 && B_global >= B && seq != 0, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_grad_p2p: bad argument");
+  LRX_REQUIRE(workspace_bytes >= workspace_tail(pol, B).adv_sums_off, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_grad_p2p: workspace too small");
+  const int n = pol->n_params + LRX_PPO_NSTATS;
+  char* own = static_cast<char*>(own_buffer);
+  float* slot = reinterpret_cast<float*>(own + p2p::HEADER + (size_t)(seq & 1u) * p2p::slot_bytes(n));
+  LrxApplyArgs ap{};
+  ap.publish_flag = reinterpret_cast<uint32_t*>(own);
+  ap.publish_seq = seq;
+  ap.ticket = reinterpret_cast<unsigned*>(own + 64);  // inside the global flag's line; zeroed by lrx_p2p_alloc, self-resetting
+  bool handled = false;
+  rc = lrx_ppo_grad_tensor(pol, params, buf, idx, B, B_global, adv_sums, h, slot, workspace, workspace_bytes,
+                           (cudaStream_t)stream, &handled, &ap);
+  if (rc || handled) return rc;
+  return lrx_ppo_grad(pol, params, buf, idx, B, B_global, adv_sums, h, slot, workspace, workspace_bytes, stream);
 }
 
 // Multi-GPU minibatch in TWO launches: the gradient kernel, then one cooperative kernel that reduces the per-CTA partials
