@@ -326,6 +326,17 @@ int lrx_ppo_grad_p2p(const LrxPolicyDesc* pol, const float* params, const LrxBat
                      int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, void* own_buffer, uint32_t seq,
                      void* workspace, size_t workspace_bytes, lrx_stream_t stream);
 
+/* One epoch of the data-parallel update in ONE call: for each of the num_batches rows of idx, lrx_ppo_grad_p2p and
+ * lrx_ppo_apply_p2p with sequence numbers derived from seq64 + 1 .. seq64 + num_batches (train_epoch, ppo.py:494-521, with the
+ * gradient SUM over the ranks inside).  adv_sums [num_batches][2]: the all-reduced advantage sums of the epoch;
+ * learning_rates_host: optional per-minibatch rates (a schedule), else h->learning_rate. */
+int lrx_ppo_update_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v, int32_t* adam_count,
+                       const LrxBatchView* buf, const int32_t* idx, int32_t num_batches, int64_t B, int64_t B_global,
+                       const double* adv_sums, const LrxPpoHyper* h, const float* learning_rates_host,
+                       void* const* peer_buffers, void* own_buffer, int32_t rank, int32_t world, uint64_t seq64,
+                       float* stats_out, int32_t* nonfinite_flag, int32_t* error_flag, void* scratch, size_t scratch_bytes,
+                       void* workspace, size_t workspace_bytes, lrx_stream_t stream);
+
 /* One minibatch of the multi-GPU update in two launches (default-width policies): lrx_ppo_grad's gradient kernel, then ONE
  * cooperative kernel that reduces the per-CTA partials into this rank's exchange slot `seq & 1`, publishes and awaits the
  * peers block by block (per-block flags in the exchange buffer's header), sums the slots in rank order and applies

@@ -101,6 +101,9 @@ PROTOTYPES = {
     "lrx_p2p_allreduce": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_uint32, _vp, _vp]),
     "lrx_ppo_grad_p2p": (C.c_int, [_P(LrxPolicyDesc), _vp, _P(LrxBatchView), _vp, C.c_int64, C.c_int64, _vp, _P(LrxPpoHyper), _vp,
                                     C.c_uint32, _vp, C.c_size_t, _vp]),
+    "lrx_ppo_update_p2p": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _P(LrxBatchView), _vp, C.c_int32, C.c_int64, C.c_int64,
+                                      _vp, _P(LrxPpoHyper), _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_uint64, _vp, _vp, _vp, _vp,
+                                      C.c_size_t, _vp, C.c_size_t, _vp]),
     "lrx_ppo_grad_apply_p2p": (C.c_int, [_P(LrxPolicyDesc), _vp, _vp, _vp, _vp, _P(LrxBatchView), _vp, C.c_int64, C.c_int64, _vp,
                                           _P(LrxPpoHyper), _vp, _vp, C.c_int32, C.c_int32, C.c_uint32, _vp, _vp, _vp, _vp,
                                           C.c_size_t, _vp, _P(C.c_int32)]),

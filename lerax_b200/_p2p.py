@@ -71,6 +71,22 @@ class GradientExchange:
             return False
         return True
 
+    def update_epoch(self, pol_desc, policy, opt_state, view, idx, B_local, B_global, adv_sums, hyper, lrs, stats_out,
+                     nonfinite, workspace) -> None:
+        """lrx_ppo_update_p2p: every minibatch of an epoch (gradient -> NVLink exchange -> clip + Adam) in one C call."""
+        torch = L.require_cuda()
+        if getattr(self, "_scratch", None) is None:
+            nbytes = int(L.lib.lrx_ppo_apply_p2p_scratch_bytes(pol_desc))
+            self._scratch = torch.empty((nbytes,), dtype=torch.uint8, device=self.error.device)
+        nb = int(idx.shape[0])
+        L.check(L.lib.lrx_ppo_update_p2p(pol_desc, L.ptr(policy.params), L.ptr(opt_state.mu), L.ptr(opt_state.nu),
+                                         L.ptr(opt_state.count), view, L.ptr(idx), nb, B_local, B_global, L.ptr(adv_sums),
+                                         hyper, lrs, L.ptr(self.addresses), self._own, self.rank, self.world, self.seq,
+                                         L.ptr(stats_out), L.ptr(nonfinite), L.ptr(self.error), L.ptr(self._scratch),
+                                         self._scratch.numel(), L.ptr(workspace), workspace.numel(), L.stream_ptr()),
+                "lrx_ppo_update_p2p")
+        self.seq += nb
+
     def check(self) -> None:
         if int(self.error.item()) != 0:
             raise RuntimeError("lrx_p2p_allreduce: a peer rank did not publish its gradient within 10 s")

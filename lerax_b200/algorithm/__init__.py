@@ -285,6 +285,18 @@ class PPO(AbstractAlgorithm):
             # LRX_P2P_FUSED=1: the two-launch variant (lrx_ppo_grad_apply_p2p); measured 5 us per minibatch SLOWER than the
             # three calls below at 2 GPUs (407 blocks each fencing and polling at system scope), so it is opt-in
             fused_p2p = ex is not None and os.environ.get("LRX_P2P_FUSED", "0") == "1"
+            if ex is not None and not fused_p2p and idx.is_contiguous():
+                # the whole epoch in one C call (gradient -> NVLink exchange -> clip + Adam per minibatch): the per-minibatch
+                # interpreter round trips cost more than the exchange
+                lrs = None
+                if callable(self.learning_rate):
+                    import ctypes
+
+                    lrs = (ctypes.c_float * nb)(*[self._lr_at(count + i) for i in range(nb)])
+                ex.update_epoch(pol_d, policy, opt_state, view, idx, B_local, B_global, b["adv_sums"],
+                                self._hyper(self._lr_at(count)), lrs, stats[e], b["nonfinite"], b["workspace"])
+                count += nb
+                continue
             for i in range(nb):
                 h = self._hyper(self._lr_at(count))
                 if fused_p2p:

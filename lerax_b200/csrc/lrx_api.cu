@@ -38,6 +38,15 @@ int lrx_fused_enabled() {
   }
   return g_fused;
 }
+// Programmatic dependent launch between the update's kernels (LRX_PDL=0 switches it off: an A/B knob)
+int lrx_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LRX_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
 extern "C" void lrx_debug_set_fused(int level) { g_fused = level < 0 ? 0 : level > 4 ? 4 : level; }
 
 int lrx_sm_count() {

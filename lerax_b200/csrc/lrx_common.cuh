@@ -75,6 +75,7 @@ __host__ __device__ inline int lrx_policy_layers(const LrxPolicyDesc& p, LrxLaye
 }
 
 int lrx_fused_enabled();
+int lrx_pdl_enabled();
 int lrx_validate_policy(const LrxPolicyDesc* pol);
 int lrx_validate_env(const LrxEnvDesc* env);
 int lrx_env_state_dim(int kind);

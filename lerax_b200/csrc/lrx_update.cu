@@ -389,6 +389,9 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
                        float ent_coef, double B_global, float* gradbuf, const LrxApplyArgs ap) {
   __shared__ float sub[8][33];
   __shared__ double red[8];
+  // programmatic dependent launch (see ppo_grad_tc128c_kernel): the partials are the previous kernel's output
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int pl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + pl;
   float s = 0.f;
@@ -636,6 +639,8 @@ apply_p2p_kernel(float* __restrict__ params, float* __restrict__ m, float* __res
                  float* stats_out, int32_t* nonfinite_flag) {
   __shared__ double red[8];
   __shared__ float norm_s;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch: the own slot is the previous kernel's output
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tid = threadIdx.x;
   const bool arrived = p2p::publish_and_wait(peers, rank, world, seq, blockIdx.x == 0, error_flag);
   const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
@@ -817,15 +822,34 @@ int lrx_launch_reduce_partials(const float* partial, int splits, long long strid
   if (apply && grid <= 4 * lrx_sm_count()) {
     // fused reduce + clip + Adam: needs every block resident at once (grid barrier) -> cooperative launch
     ap = *apply;
-    void* args[] = {(void*)&partial, (void*)&splits, (void*)&stride, (void*)&P, (void*)&loss_partial,
-                    (void*)&loss_blocks, (void*)&log_std_off, (void*)&ent_coef, (void*)&B_global, (void*)&gradbuf,
-                    (void*)&ap};
-    LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)reduce_partials_kernel, dim3(grid), dim3(256), args, 0, s));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = lrx_pdl_enabled() ? 2 : 1;
+    LRX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, partial, splits, stride, P, loss_partial, loss_blocks,
+                                      log_std_off, ent_coef, B_global, gradbuf, ap));
     return LRX_OK;
   }
-  reduce_partials_kernel<<<grid, 256, 0, s>>>(partial, splits, stride, P, loss_partial, loss_blocks, log_std_off,
-                                              ent_coef, B_global, gradbuf, ap);
-  LRX_CUDA_CHECK(cudaGetLastError());
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = lrx_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LRX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, partial, splits, stride, P, loss_partial, loss_blocks,
+                                      log_std_off, ent_coef, B_global, gradbuf, ap));
+  }
   if (apply)  // too many blocks for one resident wave of the fused kernel: separate apply launch
     return launch_apply(apply->params, apply->m, apply->v, apply->count, gradbuf, P, log_std_off, apply->h, apply->stats_out,
                         apply->nonfinite_flag, s, apply->blk_ss);
@@ -1070,8 +1094,18 @@ extern "C" int lrx_ppo_apply_p2p(const LrxPolicyDesc* pol, float* params, float*
                   (void*)&wd, (void*)&slot_b, (void*)&sq, (void*)&error_flag, (void*)&gsum, (void*)&blk_ss, (void*)&P,
                   (void*)&log_std_off, (void*)&hh, (void*)&stats_out, (void*)&nonfinite_flag};
   const int cap = 4 * lrx_sm_count(), want = (n + 255) / 256;
-  LRX_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)apply_p2p_kernel, dim3(want < cap ? want : cap), dim3(256), args, 0,
-                                             (cudaStream_t)stream));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(want < cap ? want : cap));
+  cfg.blockDim = dim3(256);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lrx_pdl_enabled() ? 2 : 1;
+  LRX_CUDA_CHECK(cudaLaunchKernelExC(&cfg, (const void*)apply_p2p_kernel, args));
   LRX_LAUNCH_CHECK();
   return LRX_OK;
 }
@@ -1100,6 +1134,34 @@ extern "C" int lrx_ppo_grad_p2p(const LrxPolicyDesc* pol, const float* params, c
                            (cudaStream_t)stream, &handled, &ap);
   if (rc || handled) return rc;
   return lrx_ppo_grad(pol, params, buf, idx, B, B_global, adv_sums, h, slot, workspace, workspace_bytes, stream);
+}
+
+// One epoch of the multi-GPU update driven from C: per minibatch lrx_ppo_grad_p2p + lrx_ppo_apply_p2p with the sequence
+// numbers seq64 + 1 .. seq64 + num_batches (folded into 1 .. 2^32 - 2 with an even period, so consecutive exchanges
+// always alternate between the two slots).  `adv_sums` [num_batches][2] are the (already all-reduced) advantage sums.
+// Per-minibatch host work is what bounds a data-parallel run once the kernels are fast: 2 x 320 interpreter round trips
+// per iteration cost more than the exchange itself.
+extern "C" int lrx_ppo_update_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v, int32_t* adam_count,
+                                  const LrxBatchView* buf, const int32_t* idx, int32_t num_batches, int64_t B,
+                                  int64_t B_global, const double* adv_sums, const LrxPpoHyper* h,
+                                  const float* learning_rates_host, void* const* peer_buffers, void* own_buffer,
+                                  int32_t rank, int32_t world, uint64_t seq64, float* stats_out, int32_t* nonfinite_flag,
+                                  int32_t* error_flag, void* scratch, size_t scratch_bytes, void* workspace,
+                                  size_t workspace_bytes, lrx_stream_t stream) {
+  LRX_REQUIRE(num_batches >= 0 && num_batches <= LRX_MAX_BATCHES && idx && stats_out && h, LRX_ERR_INVALID_ARG,
+              "lrx_ppo_update_p2p: bad argument");
+  LrxPpoHyper hh = *h;
+  for (int b = 0; b < num_batches; ++b) {
+    const uint32_t seq = (uint32_t)((seq64 + (uint64_t)b) % 0xFFFFFFFEull) + 1u;  // = ((seq64 + b + 1) - 1) % (2^32 - 2) + 1
+    if (learning_rates_host) hh.learning_rate = learning_rates_host[b];
+    int rc = lrx_ppo_grad_p2p(pol, params, buf, idx + (size_t)b * B, B, B_global, adv_sums ? adv_sums + 2 * b : nullptr, &hh,
+                              own_buffer, seq, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    rc = lrx_ppo_apply_p2p(pol, params, adam_m, adam_v, adam_count, peer_buffers, rank, world, seq, &hh,
+                           stats_out + (size_t)b * LRX_PPO_NSTATS, nonfinite_flag, error_flag, scratch, scratch_bytes, stream);
+    if (rc) return rc;
+  }
+  return LRX_OK;
 }
 
 // Multi-GPU minibatch in TWO launches: the gradient kernel, then one cooperative kernel that reduces the per-CTA partials

@@ -137,6 +137,11 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128c_kernel(const __gri
   constexpr int NO = NOUT ? NOUT : LRX_MAX_NOUT;
   const int n_out = NOUT ? NOUT : a.n_out;
   extern __shared__ __align__(1024) uint8_t smem[];
+  // Programmatic dependent launch: this grid may be scheduled while the previous kernel of the stream (the reduce / clip /
+  // Adam kernel that writes the parameters) is still draining; nothing of its output is touched before the wait, and the
+  // next kernel (the reduction of this grid's partials) may be set up as early as it likes -- it waits the same way.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
   const bool worker = warp < WORKERS / 32;  // warp-uniform
   const int q = warp & 3, g = worker ? (warp >> 2) : 0;
@@ -981,11 +986,21 @@ int lrx_ppo_grad_tc128c(const LrxPolicyDesc* pol, const float* params, const Lrx
   LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_tc128c_kernel<1>, (int)SMEM_BYTES, set1));
   LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_tc128c_kernel<2>, (int)SMEM_BYTES, set2));
   LRX_CUDA_CHECK(lrx_set_max_smem(ppo_grad_tc128c_kernel<3>, (int)SMEM_BYTES, set3));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = lrx_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   switch (pol->n_out) {
-    case 1: ppo_grad_tc128c_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
-    case 2: ppo_grad_tc128c_kernel<2><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
-    case 3: ppo_grad_tc128c_kernel<3><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
-    default: ppo_grad_tc128c_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(a); break;
+    case 1: LRX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ppo_grad_tc128c_kernel<1>, a)); break;
+    case 2: LRX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ppo_grad_tc128c_kernel<2>, a)); break;
+    case 3: LRX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ppo_grad_tc128c_kernel<3>, a)); break;
+    default: LRX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ppo_grad_tc128c_kernel<0>, a)); break;
   }
   LRX_LAUNCH_CHECK();
   const int rc = lrx_launch_reduce_partials(w.partial, grid, (long long)w.P_pad, pol->n_params, w.loss_partial, grid,

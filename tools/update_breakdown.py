@@ -20,7 +20,7 @@ b = algo._bufs
 from lerax_b200.buffer import RolloutBuffer
 buf = RolloutBuffer(b["obs"], b["act"], b["rew"], b["done"], b["logp"], b["val"])
 buf = buf.compute_returns_and_advantages(b["last_value"], algo.gae_lambda, algo.gamma, ev_sums=b["ev_sums"])
-view = buf.view()
+view = buf.view(packed=b.get("packed"))
 B = algo.batch_size
 idx = buf.batch_indices(B, key=jr.key(3))[:32]
 nb = idx.shape[0]
@@ -58,9 +58,23 @@ def epoch_grad_apply():
         L.check(L.lib.lrx_ppo_apply(d, L.ptr(pol.params), L.ptr(opt.mu), L.ptr(opt.nu), L.ptr(opt.count),
                                     L.ptr(b["gradbuf"]), h, L.ptr(stats[0, i]), L.ptr(b["nonfinite"]), L.stream_ptr()), "apply")
 
+# the data-parallel path with a one-rank exchange (every NVLink access is local): what the p2p kernels cost by themselves
+import ctypes as C
+from lerax_b200._p2p import GradientExchange
+own = C.c_void_p()
+hbuf = (C.c_ubyte * L.LRX_P2P_HANDLE_BYTES)()
+L.check(L.lib.lrx_p2p_alloc(pol.n_params + L.LRX_PPO_NSTATS, C.byref(own), hbuf), "alloc")
+ex = GradientExchange(pol.n_params + L.LRX_PPO_NSTATS, 0, 1, own.value, [], torch.tensor([own.value], dtype=torch.int64, device="cuda"),
+                      torch.zeros((), dtype=torch.int32, device="cuda"))
+
+def epoch_p2p_self():
+    ex.update_epoch(d, pol, opt, view, idx, B, B, b["adv_sums"], h, None, stats[0], b["nonfinite"], b["workspace"])
+
 L.check(L.lib.lrx_ppo_adv_sums(view.adv, view.N, view.T, L.ptr(idx), nb, B, L.ptr(b["adv_sums"]), L.stream_ptr()), "sums")
 t_u = timed(epoch_update)
 t_g = timed(epoch_grad_only)
 t_ga = timed(epoch_grad_apply)
+t_p = timed(epoch_p2p_self)
 print(f"per minibatch (B={B}): lrx_ppo_update {1e3 * t_u / nb:.1f} us | lrx_ppo_grad only {1e3 * t_g / nb:.1f} us | "
-      f"grad + apply (multi-GPU path) {1e3 * t_ga / nb:.1f} us")
+      f"grad + apply (NCCL path without the all-reduce) {1e3 * t_ga / nb:.1f} us | "
+      f"lrx_ppo_update_p2p with a one-rank exchange {1e3 * t_p / nb:.1f} us")
