@@ -25,7 +25,7 @@ __global__ void p2p_allreduce_kernel(char* const* __restrict__ peers, int rank, 
 
 extern "C" size_t lrx_p2p_buffer_bytes(int32_t n_floats) {
   const size_t slot = p2p::slot_bytes(n_floats);
-  return p2p::HEADER + 2 * slot;
+  return p2p::HEADER + 2 * slot + 2 * (size_t)p2p::PUSH_MAX_RANKS * slot;  // pull slots, then the push receive areas
 }
 
 extern "C" int lrx_p2p_alloc(int32_t n_floats, void** buffer, unsigned char* ipc_handle) {

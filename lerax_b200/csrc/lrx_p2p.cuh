@@ -11,7 +11,20 @@ namespace p2p {
 // reduce + exchange + apply kernel of lrx_ppo_grad_apply_p2p, where block b of a rank only depends on block b of its peers.
 constexpr int MAX_BLOCK_FLAGS = 1024;
 constexpr size_t GLOBAL_FLAG_BYTES = 128;
-constexpr size_t HEADER = GLOBAL_FLAG_BYTES + 2 * (size_t)MAX_BLOCK_FLAGS * 4;  // 8320 = 65 lines
+// PUSH exchange (the default of lrx_ppo_update_p2p for up to PUSH_MAX_RANKS ranks): a rank WRITES its reduced gradient
+// into every peer's receive area recv[slot][source rank] and then the source's arrival flag, so the receiver polls and
+// sums LOCAL memory only: one one-way NVLink trip per minibatch instead of the pull protocol's flag round trips plus a
+// remote-load round trip.
+constexpr int PUSH_MAX_RANKS = 8;
+constexpr size_t PUSH_FLAG_BYTES = 256;  // arrival flag of source rank r: uint32 at GLOBAL_FLAG_BYTES + 2 * MAX_BLOCK_FLAGS * 4 + 4 r
+constexpr size_t HEADER = GLOBAL_FLAG_BYTES + 2 * (size_t)MAX_BLOCK_FLAGS * 4 + PUSH_FLAG_BYTES;  // 8576 = 67 lines
+__host__ __device__ inline uint32_t* push_flag(char* buffer, int source_rank) {
+  return reinterpret_cast<uint32_t*>(buffer + GLOBAL_FLAG_BYTES + 2 * (size_t)MAX_BLOCK_FLAGS * 4) + source_rank;
+}
+// receive area of `source_rank` for slot `seq & 1`: behind the two pull slots
+__host__ __device__ inline float* push_recv(char* buffer, size_t slot_b, uint32_t seq, int source_rank) {
+  return reinterpret_cast<float*>(buffer + HEADER + 2 * slot_b + ((size_t)(seq & 1u) * PUSH_MAX_RANKS + source_rank) * slot_b);
+}
 __host__ __device__ inline uint32_t* block_flag(char* buffer, uint32_t seq, int block) {
   return reinterpret_cast<uint32_t*>(buffer + GLOBAL_FLAG_BYTES) + (size_t)(seq & 1u) * MAX_BLOCK_FLAGS + block;
 }

@@ -381,6 +381,9 @@ struct LrxApplyArgs {
   uint32_t* publish_flag;
   uint32_t publish_seq;
   unsigned* ticket;      // zero between launches (the last block resets it)
+  // ... or PUSHES it (push != 0; peers / rank / world / slot_b above): every entry is also written into each rank's receive
+  // area of this rank, and the last block sets this rank's arrival flag in every buffer
+  int push;
 };
 
 __global__ void __launch_bounds__(256)
@@ -423,12 +426,34 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
   }
   if (blockIdx.x == 0 && threadIdx.x == 255) { gradbuf[P + 4] = 0.f; gradbuf[P + 5] = 0.f; gradbuf[P + 7] = 0.f; }
   if (ap.publish_flag) {
-    __threadfence();
+    if (ap.push) {
+      __syncthreads();  // block 0: the statistics and the log_std entry written above
+      // this block's entries of the own slot -> receive area [slot][this rank] of EVERY rank (its own included)
+      const int n_mine = blockIdx.x == 0 ? 32 + LRX_PPO_NSTATS + 1 : 32;
+      if ((int)threadIdx.x < n_mine) {
+        int e = -1;
+        if (threadIdx.x < 32) e = (p < P) ? p : -1;
+        else if (threadIdx.x < 32 + LRX_PPO_NSTATS) e = P + ((int)threadIdx.x - 32);
+        else e = log_std_off;  // -1 for Discrete policies
+        if (e >= 0) {
+          const float val = (threadIdx.x < 32 && p != log_std_off) ? t : gradbuf[e];
+          if (threadIdx.x >= 32 || p != log_std_off)
+            for (int r = 0; r < ap.world; ++r) p2p::push_recv(ap.peers[r], ap.slot_b, ap.publish_seq, ap.rank)[e] = val;
+        }
+      }
+      __threadfence_system();
+    } else {
+      __threadfence();
+    }
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(ap.ticket, 1u) == gridDim.x - 1) {
       *ap.ticket = 0u;
-      __threadfence_system();  // every block's stores to the slot (observed through the ticket) before the flag
-      p2p::st_release_sys(ap.publish_flag, ap.publish_seq);
+      __threadfence_system();  // every block's stores (observed through the ticket) before the flag(s)
+      if (ap.push) {
+        for (int r = 0; r < ap.world; ++r) p2p::st_release_sys(p2p::push_flag(ap.peers[r], ap.rank), ap.publish_seq);
+      } else {
+        p2p::st_release_sys(ap.publish_flag, ap.publish_seq);
+      }
     }
   }
   if (!ap.params) return;
@@ -636,13 +661,30 @@ __global__ void __launch_bounds__(256)
 apply_p2p_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v, int32_t* count,
                  char* const* __restrict__ peers, int rank, int world, size_t slot_b, uint32_t seq, int* error_flag,
                  float* __restrict__ gsum, double* __restrict__ blk_ss, int P, int log_std_off, LrxPpoHyper h,
-                 float* stats_out, int32_t* nonfinite_flag) {
+                 float* stats_out, int32_t* nonfinite_flag, int push) {
   __shared__ double red[8];
   __shared__ float norm_s;
   asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch: the own slot is the previous kernel's output
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tid = threadIdx.x;
-  const bool arrived = p2p::publish_and_wait(peers, rank, world, seq, blockIdx.x == 0, error_flag);
+  bool arrived;
+  if (push) {  // the peers wrote their gradients and arrival flags into THIS rank's buffer: local polling, local loads
+    int timed_out = 0;
+    if (tid < world) {
+      const uint32_t* flag = p2p::push_flag(peers[rank], tid);
+      const long long t0 = clock64();
+      while ((int32_t)(p2p::ld_acquire_sys(flag) - seq) < 0) {
+        if (clock64() - t0 > 20000000000LL) {
+          *error_flag = 1;
+          timed_out = 1;
+          break;
+        }
+      }
+    }
+    arrived = __syncthreads_or(timed_out) == 0;
+  } else {
+    arrived = p2p::publish_and_wait(peers, rank, world, seq, blockIdx.x == 0, error_flag);
+  }
   const float ls_extra = (log_std_off >= 0) ? -h.entropy_loss_coefficient : 0.f;
   const int cnt = *count + 1;
   // pass 1 (grid stride; the grid is capped at what a cooperative launch keeps resident): rank-ordered sum of every
@@ -650,7 +692,13 @@ apply_p2p_kernel(float* __restrict__ params, float* __restrict__ m, float* __res
   double ss = 0;
   if (arrived) {  // a lost peer's slot may be stale or half written: never summed
     for (int p = blockIdx.x * blockDim.x + tid; p < P + LRX_PPO_NSTATS; p += gridDim.x * blockDim.x) {
-      const float sum = p2p::peer_sum(peers, world, slot_b, seq, p);
+      float sum;
+      if (push) {
+        sum = 0.f;
+        for (int r = 0; r < world; ++r) sum += p2p::ld_volatile_f32(p2p::push_recv(peers[rank], slot_b, seq, r) + p);  // rank order
+      } else {
+        sum = p2p::peer_sum(peers, world, slot_b, seq, p);
+      }
       gsum[p] = sum;
       if (p < P) {
         const float gp = sum + (p == log_std_off ? ls_extra : 0.f);
@@ -1069,10 +1117,21 @@ extern "C" size_t lrx_ppo_apply_p2p_scratch_bytes(const LrxPolicyDesc* pol) {
   return align_up(n * 4, 256) + ((n + 255) / 256) * sizeof(double);
 }
 
+static int apply_p2p_impl(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v, int32_t* adam_count,
+                          void* const* peer_buffers, int32_t rank, int32_t world, uint32_t seq, const LrxPpoHyper* h,
+                          float* stats_out, int32_t* nonfinite_flag, int32_t* error_flag, void* scratch, size_t scratch_bytes,
+                          lrx_stream_t stream, int push);
 extern "C" int lrx_ppo_apply_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
                                  int32_t* adam_count, void* const* peer_buffers, int32_t rank, int32_t world,
                                  uint32_t seq, const LrxPpoHyper* h, float* stats_out, int32_t* nonfinite_flag,
                                  int32_t* error_flag, void* scratch, size_t scratch_bytes, lrx_stream_t stream) {
+  return apply_p2p_impl(pol, params, adam_m, adam_v, adam_count, peer_buffers, rank, world, seq, h, stats_out, nonfinite_flag,
+                        error_flag, scratch, scratch_bytes, stream, 0);
+}
+static int apply_p2p_impl(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v, int32_t* adam_count,
+                          void* const* peer_buffers, int32_t rank, int32_t world, uint32_t seq, const LrxPpoHyper* h,
+                          float* stats_out, int32_t* nonfinite_flag, int32_t* error_flag, void* scratch, size_t scratch_bytes,
+                          lrx_stream_t stream, int push) {
   int rc = lrx_validate_policy(pol);
   if (rc) return rc;
   LRX_REQUIRE(params && adam_m && adam_v && adam_count && peer_buffers && h && error_flag && scratch,
@@ -1092,7 +1151,7 @@ extern "C" int lrx_ppo_apply_p2p(const LrxPolicyDesc* pol, float* params, float*
   uint32_t sq = seq;
   void* args[] = {(void*)&params, (void*)&adam_m, (void*)&adam_v, (void*)&adam_count, (void*)&peers, (void*)&rk,
                   (void*)&wd, (void*)&slot_b, (void*)&sq, (void*)&error_flag, (void*)&gsum, (void*)&blk_ss, (void*)&P,
-                  (void*)&log_std_off, (void*)&hh, (void*)&stats_out, (void*)&nonfinite_flag};
+                  (void*)&log_std_off, (void*)&hh, (void*)&stats_out, (void*)&nonfinite_flag, (void*)&push};
   const int cap = 4 * lrx_sm_count(), want = (n + 255) / 256;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(want < cap ? want : cap));
@@ -1113,9 +1172,24 @@ extern "C" int lrx_ppo_apply_p2p(const LrxPolicyDesc* pol, float* params, float*
 // lrx_ppo_grad for the NVLink exchange: the gradient goes into slot `seq & 1` of this rank's exchange buffer and the reduction
 // kernel's last block publishes `seq` in the buffer's flag, so the peers can read the slot while this rank's
 // lrx_ppo_apply_p2p (which publishes the same value again: harmless) is still being launched.
+static int grad_p2p_impl(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx, int64_t B,
+                         int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, void* own_buffer, uint32_t seq,
+                         void* workspace, size_t workspace_bytes, lrx_stream_t stream, void* const* push_peers, int rank,
+                         int world, bool* pushed);
 extern "C" int lrx_ppo_grad_p2p(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx,
                                 int64_t B, int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, void* own_buffer,
                                 uint32_t seq, void* workspace, size_t workspace_bytes, lrx_stream_t stream) {
+  bool pushed = false;
+  return grad_p2p_impl(pol, params, buf, idx, B, B_global, adv_sums, h, own_buffer, seq, workspace, workspace_bytes, stream,
+                       nullptr, 0, 1, &pushed);
+}
+// push_peers != nullptr: the reduction also writes the gradient into every rank's receive area and sets the arrival flags
+// (*pushed = true); policies the fused gradient kernels do not cover fall back to the plain slot (*pushed = false).
+static int grad_p2p_impl(const LrxPolicyDesc* pol, const float* params, const LrxBatchView* buf, const int32_t* idx, int64_t B,
+                         int64_t B_global, const double* adv_sums, const LrxPpoHyper* h, void* own_buffer, uint32_t seq,
+                         void* workspace, size_t workspace_bytes, lrx_stream_t stream, void* const* push_peers, int rank,
+                         int world, bool* pushed) {
+  *pushed = false;
   int rc = validate_update_args(pol, buf, h);
   if (rc) return rc;
   LRX_REQUIRE(params && idx && own_buffer && workspace && B > 0 && B_global >= B && seq != 0, LRX_ERR_INVALID_ARG,
@@ -1129,10 +1203,21 @@ extern "C" int lrx_ppo_grad_p2p(const LrxPolicyDesc* pol, const float* params, c
   ap.publish_flag = reinterpret_cast<uint32_t*>(own);
   ap.publish_seq = seq;
   ap.ticket = reinterpret_cast<unsigned*>(own + 64);  // inside the global flag's line; zeroed by lrx_p2p_alloc, self-resetting
+  if (push_peers) {
+    ap.push = 1;
+    ap.peers = reinterpret_cast<char* const*>(push_peers);
+    ap.rank = rank;
+    ap.world = world;
+    ap.slot_b = p2p::slot_bytes(n);
+  }
   bool handled = false;
   rc = lrx_ppo_grad_tensor(pol, params, buf, idx, B, B_global, adv_sums, h, slot, workspace, workspace_bytes,
                            (cudaStream_t)stream, &handled, &ap);
-  if (rc || handled) return rc;
+  if (rc) return rc;
+  if (handled) {
+    *pushed = push_peers != nullptr;
+    return LRX_OK;
+  }
   return lrx_ppo_grad(pol, params, buf, idx, B, B_global, adv_sums, h, slot, workspace, workspace_bytes, stream);
 }
 
@@ -1151,14 +1236,25 @@ extern "C" int lrx_ppo_update_p2p(const LrxPolicyDesc* pol, float* params, float
   LRX_REQUIRE(num_batches >= 0 && num_batches <= LRX_MAX_BATCHES && idx && stats_out && h, LRX_ERR_INVALID_ARG,
               "lrx_ppo_update_p2p: bad argument");
   LrxPpoHyper hh = *h;
+  // LRX_P2P_PUSH=1: push exchange (p2p::PUSH_MAX_RANKS receive areas per slot).  Measured equal to the pull protocol at 2
+  // GPUs (197.7 vs 197.3 - 200 us per minibatch), so the simpler pull protocol stays the default.
+  static int push_env = -1;
+  if (push_env < 0) {
+    const char* e = getenv("LRX_P2P_PUSH");
+    push_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  const bool use_push = push_env && world <= p2p::PUSH_MAX_RANKS;
   for (int b = 0; b < num_batches; ++b) {
     const uint32_t seq = (uint32_t)((seq64 + (uint64_t)b) % 0xFFFFFFFEull) + 1u;  // = ((seq64 + b + 1) - 1) % (2^32 - 2) + 1
     if (learning_rates_host) hh.learning_rate = learning_rates_host[b];
-    int rc = lrx_ppo_grad_p2p(pol, params, buf, idx + (size_t)b * B, B, B_global, adv_sums ? adv_sums + 2 * b : nullptr, &hh,
-                              own_buffer, seq, workspace, workspace_bytes, stream);
+    bool pushed = false;
+    int rc = grad_p2p_impl(pol, params, buf, idx + (size_t)b * B, B, B_global, adv_sums ? adv_sums + 2 * b : nullptr, &hh,
+                           own_buffer, seq, workspace, workspace_bytes, stream, use_push ? peer_buffers : nullptr, rank, world,
+                           &pushed);
     if (rc) return rc;
-    rc = lrx_ppo_apply_p2p(pol, params, adam_m, adam_v, adam_count, peer_buffers, rank, world, seq, &hh,
-                           stats_out + (size_t)b * LRX_PPO_NSTATS, nonfinite_flag, error_flag, scratch, scratch_bytes, stream);
+    rc = apply_p2p_impl(pol, params, adam_m, adam_v, adam_count, peer_buffers, rank, world, seq, &hh,
+                        stats_out + (size_t)b * LRX_PPO_NSTATS, nonfinite_flag, error_flag, scratch, scratch_bytes, stream,
+                        pushed ? 1 : 0);
     if (rc) return rc;
   }
   return LRX_OK;
