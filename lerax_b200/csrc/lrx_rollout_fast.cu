@@ -27,18 +27,22 @@ constexpr uint32_t LRX_STREAM_INIT_ = 2;
 
 constexpr uint32_t PW16 = 64 * 16 * 2, PW64 = 64 * 64 * 2;          // weight pieces ([64][16], [64][64] / [16][64] = PW16)
 constexpr uint32_t PX16 = ENVS * 16 * 2, PX64 = ENVS * 64 * 2;      // activation pieces
+// Composite weights across the policy's two linear-linear seams (the same identity as lrx_update_tc128c.cu): the encoder's
+// 16-wide output has no activation, so both heads' first layers read h2 through Wcv = Wv0 W2 / Wca = Wa0 W2 (64 x 64), and
+// action_dist.mapping follows the action head's linear output layer, so the logits are (Wmap Wa1) xa + (Wmap ba1 + bmap).
+// Four MMA round trips per env-step instead of five, no 16 -> n_out mapping on the FMA pipe.  The composites are formed
+// once per launch in fp32 (one rounding of a 16-term dot product per weight, ~1e-7 relative: the rollout's contract is
+// 1e-5) and then split exactly into three pieces like every other operand.
 constexpr uint32_t OFF_W0 = 0;
 constexpr uint32_t OFF_W1 = OFF_W0 + 3 * PW16;
-constexpr uint32_t OFF_W2 = OFF_W1 + 3 * PW64;
-constexpr uint32_t OFF_WV0 = OFF_W2 + 3 * PW16;
-constexpr uint32_t OFF_WV1 = OFF_WV0 + 3 * PW16;
-constexpr uint32_t OFF_WA0 = OFF_WV1 + 3 * PW64;
-constexpr uint32_t OFF_WA1 = OFF_WA0 + 3 * PW16;
-constexpr uint32_t OFF_XOBS = OFF_WA1 + 3 * PW16;
-constexpr uint32_t OFF_XH1 = OFF_XOBS + 3 * PX16;   // encoder layer 1, then value head layer 1
-constexpr uint32_t OFF_XH2 = OFF_XH1 + 3 * PX64;    // encoder layer 2, then action head layer 1
-constexpr uint32_t OFF_XF = OFF_XH2 + 3 * PX64;
-constexpr uint32_t OFF_F32 = OFF_XF + 3 * PX16;
+constexpr uint32_t OFF_WCV = OFF_W1 + 3 * PW64;
+constexpr uint32_t OFF_WCA = OFF_WCV + 3 * PW64;
+constexpr uint32_t OFF_WV1 = OFF_WCA + 3 * PW64;
+constexpr uint32_t OFF_WCM = OFF_WV1 + 3 * PW64;    // [16][64]: rows >= n_out zero
+constexpr uint32_t OFF_XOBS = OFF_WCM + 3 * PW16;
+constexpr uint32_t OFF_XH1 = OFF_XOBS + 3 * PX16;   // encoder layer 1, then value head layer 0
+constexpr uint32_t OFF_XH2 = OFF_XH1 + 3 * PX64;    // encoder layer 2 (h2), then action head layer 0
+constexpr uint32_t OFF_F32 = OFF_XH2 + 3 * PX64;
 constexpr uint32_t OFF_VPART = OFF_F32 + tc::F_RESERVE * 4;   // [4][128] partial value dot products
 constexpr uint32_t OFF_MISC = OFF_VPART + 4 * ENVS * 4;
 constexpr uint32_t SMEM_BYTES = OFF_MISC + 64;
@@ -74,20 +78,63 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_tc_kernel(const __grid_con
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_MISC);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 8);
 
-  const tc::Mat W0{smem + OFF_W0, 64, PW16}, W1{smem + OFF_W1, 64, PW64}, W2{smem + OFF_W2, 16, PW16};
-  const tc::Mat WV0{smem + OFF_WV0, 64, PW16}, WV1{smem + OFF_WV1, 64, PW64};
-  const tc::Mat WA0{smem + OFF_WA0, 64, PW16}, WA1{smem + OFF_WA1, 16, PW16};
+  const tc::Mat W0{smem + OFF_W0, 64, PW16}, W1{smem + OFF_W1, 64, PW64}, WV1{smem + OFF_WV1, 64, PW64};
+  const tc::Mat WCV{smem + OFF_WCV, 64, PW64}, WCA{smem + OFF_WCA, 64, PW64}, WCM{smem + OFF_WCM, 16, PW16};
   const tc::Mat XOBS{smem + OFF_XOBS, ENVS, PX16}, XH1{smem + OFF_XH1, ENVS, PX64}, XH2{smem + OFF_XH2, ENVS, PX64};
-  const tc::Mat XF{smem + OFF_XF, ENVS, PX16};
 
   tc::stage_weight(a.params + a.lo.w[tc::L_ENC0], 64, OD, 16, W0, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_ENC1], 64, 64, 64, W1, tid, THREADS);
-  tc::stage_weight(a.params + a.lo.w[tc::L_ENC2], 16, 64, 64, W2, tid, THREADS);
-  tc::stage_weight(a.params + a.lo.w[tc::L_V0], 64, 16, 16, WV0, tid, THREADS);
   tc::stage_weight(a.params + a.lo.w[tc::L_V1], 64, 64, 64, WV1, tid, THREADS);
-  tc::stage_weight(a.params + a.lo.w[tc::L_A0], 64, 16, 16, WA0, tid, THREADS);
-  tc::stage_weight(a.params + a.lo.w[tc::L_A1], 16, 64, 64, WA1, tid, THREADS);
   tc::stage_f32(a.params, a.lo, a.n_out, OD, fp, tid, THREADS);
+  {
+    // fp32 sources of the composites in the (still unused) XH1 region:
+    //   W2 [16][64] | Wv0 [64][16] | Wa0 [64][16] | Wa1 [16][64] | Wmap [8][16] (rows >= n_out zero)
+    float* cs = reinterpret_cast<float*>(smem + OFF_XH1);
+    constexpr int CS_W2 = 0, CS_WV0 = 1024, CS_WA0 = 2048, CS_WA1 = 3072, CS_WMAP = 4096, CS_N = 4224;
+    for (int i = tid; i < CS_N; i += THREADS) {
+      float x;
+      if (i < CS_WV0) x = __ldg(a.params + a.lo.w[tc::L_ENC2] + i);
+      else if (i < CS_WA0) x = __ldg(a.params + a.lo.w[tc::L_V0] + (i - CS_WV0));
+      else if (i < CS_WA1) x = __ldg(a.params + a.lo.w[tc::L_A0] + (i - CS_WA0));
+      else if (i < CS_WMAP) x = __ldg(a.params + a.lo.w[tc::L_A1] + (i - CS_WA1));
+      else x = (i - CS_WMAP) < a.n_out * 16 ? __ldg(a.params + a.lo.w[tc::L_MAP] + (i - CS_WMAP)) : 0.f;
+      cs[i] = x;
+    }
+    __syncthreads();  // cs, and the biases stage_f32 wrote
+    // chunk e = 8 consecutive inputs i of one output o:  Wc[o][i] = sum_k L[o][k] R[k][i]  (k = 0..15 in order)
+    for (int e = tid; e < 512 + 512 + 128; e += THREADS) {
+      const int mat = e < 512 ? 0 : (e < 1024 ? 1 : 2);
+      const int el = e - (mat == 2 ? 1024 : mat * 512);
+      const int o = mat == 2 ? (el & 15) : (el & 63), ch = mat == 2 ? (el >> 4) : (el >> 6);
+      const float* Lrow = cs + (mat == 0 ? CS_WV0 : (mat == 1 ? CS_WA0 : CS_WMAP)) + o * 16;
+      const float* R = cs + (mat == 2 ? CS_WA1 : CS_W2) + ch * 8;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (mat != 2 || o < LRX_MAX_NOUT) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float l = Lrow[k];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(l, R[k * 64 + j], acc[j]);
+        }
+      }
+      tc::store8(mat == 0 ? WCV : (mat == 1 ? WCA : WCM), ch, o, acc);
+    }
+    // composite biases, computed into registers first (they replace entries other threads still read)
+    float cb = 0.f;
+    int cb_slot = -1;
+    if (tid < 64 + 64 + LRX_MAX_NOUT) {
+      const int mat = tid < 64 ? 0 : (tid < 128 ? 1 : 2), o = tid - (mat == 2 ? 128 : mat * 64);
+      const float* Lrow = cs + (mat == 0 ? CS_WV0 : (mat == 1 ? CS_WA0 : CS_WMAP)) + o * 16;
+      const float* bb = fp + (mat == 2 ? tc::F_BA1 : tc::F_B2);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) cb = fmaf(Lrow[k], bb[k], cb);
+      cb += fp[(mat == 0 ? tc::F_BV0 : (mat == 1 ? tc::F_BA0 : tc::F_BMAP)) + o];  // F_BMAP entries >= n_out are zero
+      if (mat == 2 && o >= a.n_out) cb = 0.f;
+      cb_slot = (mat == 0 ? tc::F_BV0 : (mat == 1 ? tc::F_BA0 : tc::F_BMAP)) + o;
+    }
+    __syncthreads();  // every read of cs and of the plain biases
+    if (cb_slot >= 0) fp[cb_slot] = cb;  // F_BV0 / F_BA0 / F_BMAP now hold the composite biases
+  }
   if (tid == 0) {
     umma::mbar_init(bar, ISSUERS);
     umma::fence_mbar_init();
@@ -152,19 +199,16 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_tc_kernel(const __grid_con
       if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH1, W1, 128, 64, 4, 0u);
     });
     epilogue(C_D0, cg, fp + tc::F_B1, true, XH2, nop);
+    // both heads' layer 0 straight from h2 (composites)
     sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH2, W2, 128, 16, 4, 0u);
-    });
-    if (g0) epilogue(C_D0, 0, fp + tc::F_B2, false, XF, nop);
-    sync_issue([&](bool ld, int p) {
-      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XF, WV0, 128, 64, 1, 0u);
-      if (p == 1 && want_head) tc::gemm<false, false>(ld, tb + C_D1, XF, WA0, 128, 64, 1, 0u);
+      if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH2, WCV, 128, 64, 4, 0u);
+      if (p == 1 && want_head) tc::gemm<false, false>(ld, tb + C_D1, XH2, WCA, 128, 64, 4, 0u);
     });
     epilogue(C_D0, cg, fp + tc::F_BV0, true, XH1, nop);
-    if (want_head) epilogue(C_D1, cg, fp + tc::F_BA0, true, XH2, nop);
+    if (want_head) epilogue(C_D1, cg, fp + tc::F_BA0, true, XH2, nop);  // h2 is dead: both GEMMs above are complete
     sync_issue([&](bool ld, int p) {
       if (p == 0) tc::gemm<false, false>(ld, tb + C_D0, XH1, WV1, 128, 64, 4, 0u);
-      if (p == 1 && want_head) tc::gemm<false, false>(ld, tb + C_D1, XH2, WA1, 128, 16, 4, 0u);
+      if (p == 1 && want_head) tc::gemm<false, false>(ld, tb + C_D1, XH2, WCM, 128, 16, 4, 0u);  // logits / loc
     });
     {
       float v[16];
@@ -176,21 +220,11 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_tc_kernel(const __grid_con
       vpart[g * ENVS + m] = part;
     }
     if (want_head && g0) {
-      float a2[16];
-      umma::tmem_ld16(tw + C_D1, a2);
+      float lg[8];
+      umma::tmem_ld8(tw + C_D1, lg);
       umma::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) a2[j] += fp[tc::F_BA1 + j];
-      // action_dist.mapping (Linear 16 -> n_out, policy/actor.py:248-261)
-#pragma unroll
-      for (int o2 = 0; o2 < LRX_MAX_NOUT; ++o2) {
-        float s = fp[tc::F_BMAP + o2];
-        if (o2 < EnvDims<KIND>::NA) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) s = fmaf(fp[tc::F_WMAP + o2 * 16 + i], a2[i], s);
-        }
-        head[o2] = s;
-      }
+      for (int o2 = 0; o2 < LRX_MAX_NOUT; ++o2) head[o2] = lg[o2] + fp[tc::F_BMAP + o2];
     }
     umma::tc_fence_before();
     __syncthreads();
