@@ -282,12 +282,9 @@ class PPO(AbstractAlgorithm):
             if dist is not None:
                 dist.all_reduce(b["adv_sums"])  # one collective for the whole epoch
             ex = self._exchange(policy, dist)
-            # LRX_P2P_FUSED=1: the two-launch variant (lrx_ppo_grad_apply_p2p); measured 5 us per minibatch SLOWER than the
-            # three calls below at 2 GPUs (407 blocks each fencing and polling at system scope), so it is opt-in
-            fused_p2p = ex is not None and os.environ.get("LRX_P2P_FUSED", "0") == "1"
-            if ex is not None and not fused_p2p and idx.is_contiguous():
-                # the whole epoch in one C call (gradient -> NVLink exchange -> clip + Adam per minibatch): the per-minibatch
-                # interpreter round trips cost more than the exchange
+            if ex is not None and idx.is_contiguous():
+                # the whole epoch in one C call (lrx_ppo_update_p2p): per minibatch the gradient kernel and ONE cooperative
+                # kernel for reduce + NVLink exchange + clip + Adam
                 lrs = None
                 if callable(self.learning_rate):
                     import ctypes
@@ -299,13 +296,6 @@ class PPO(AbstractAlgorithm):
                 continue
             for i in range(nb):
                 h = self._hyper(self._lr_at(count))
-                if fused_p2p:
-                    # two launches per minibatch: gradient kernel, then reduce + block-wise NVLink exchange + clip + Adam
-                    if ex.grad_apply(pol_d, policy, opt_state, view, idx[i], B_local, B_global, b["adv_sums"][i], h,
-                                     stats[e, i], b["nonfinite"], b["workspace"]):
-                        count += 1
-                        continue
-                    fused_p2p = False  # a policy the fused gradient kernels do not cover: three calls per minibatch
                 if ex is not None:
                     # the local gradient goes straight into this rank's exchange slot, published as soon as it is complete
                     ex.grad(pol_d, policy, view, idx[i], B_local, B_global, b["adv_sums"][i], h, b["workspace"])

@@ -466,14 +466,27 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
   bool peer_lost = false;
   double lsg_ss = 0;  // p2p: the summed log_std entry's contribution to the norm (block 0, warp 1, lane 8)
   if (p2p_on) {
+    // LRX_P2P_FUSED=2 (ap.push == 2 here): ONE flag per rank, published by the last block to finish the reduction (ticket),
+    // instead of one per block: a single system-scope fence and flag store per rank and minibatch
+    const bool one_flag = ap.push == 2;
+    if (one_flag) __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence_system();
-      p2p::st_release_sys(p2p::block_flag(ap.peers[ap.rank], ap.seq, blockIdx.x), ap.seq);
+      if (one_flag) {
+        if (atomicAdd(ap.ticket, 1u) == gridDim.x - 1) {
+          *ap.ticket = 0u;
+          __threadfence_system();
+          p2p::st_release_sys(reinterpret_cast<uint32_t*>(ap.peers[ap.rank]), ap.seq);
+        }
+      } else {
+        __threadfence_system();
+        p2p::st_release_sys(p2p::block_flag(ap.peers[ap.rank], ap.seq, blockIdx.x), ap.seq);
+      }
     }
     int timed_out = 0;
     if ((int)threadIdx.x < ap.world) {
-      const uint32_t* flag = p2p::block_flag(ap.peers[threadIdx.x], ap.seq, blockIdx.x);
+      const uint32_t* flag = one_flag ? reinterpret_cast<const uint32_t*>(ap.peers[threadIdx.x])
+                                      : p2p::block_flag(ap.peers[threadIdx.x], ap.seq, blockIdx.x);
       const long long t0 = clock64();
       while ((int32_t)(p2p::ld_acquire_sys(flag) - ap.seq) < 0) {
         if (clock64() - t0 > 20000000000LL) {  // a peer is gone -- report instead of hanging the GPU
@@ -1226,6 +1239,12 @@ static int grad_p2p_impl(const LrxPolicyDesc* pol, const float* params, const Lr
 // always alternate between the two slots).  `adv_sums` [num_batches][2] are the (already all-reduced) advantage sums.
 // Per-minibatch host work is what bounds a data-parallel run once the kernels are fast: 2 x 320 interpreter round trips
 // per iteration cost more than the exchange itself.
+extern "C" int lrx_ppo_grad_apply_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v,
+                                      int32_t* adam_count, const LrxBatchView* buf, const int32_t* idx, int64_t B,
+                                      int64_t B_global, const double* adv_sums, const LrxPpoHyper* h,
+                                      void* const* peer_buffers, void* own_buffer, int32_t rank, int32_t world,
+                                      uint32_t seq, float* stats_out, int32_t* nonfinite_flag, int32_t* error_flag,
+                                      void* workspace, size_t workspace_bytes, lrx_stream_t stream, int32_t* handled);
 extern "C" int lrx_ppo_update_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v, int32_t* adam_count,
                                   const LrxBatchView* buf, const int32_t* idx, int32_t num_batches, int64_t B,
                                   int64_t B_global, const double* adv_sums, const LrxPpoHyper* h,
@@ -1244,9 +1263,26 @@ extern "C" int lrx_ppo_update_p2p(const LrxPolicyDesc* pol, float* params, float
     push_env = (e && e[0] == '1') ? 1 : 0;
   }
   const bool use_push = push_env && world <= p2p::PUSH_MAX_RANKS;
+  // default: TWO launches per minibatch (lrx_ppo_grad_apply_p2p; 191 us against 193 us for the three calls below at 2 GPUs);
+  // LRX_P2P_FUSED=0 or a policy the fused gradient kernels do not cover: three
+  bool fused = !use_push;
+  {
+    const char* e = getenv("LRX_P2P_FUSED");
+    if (e && e[0] == '0') fused = false;
+  }
   for (int b = 0; b < num_batches; ++b) {
     const uint32_t seq = (uint32_t)((seq64 + (uint64_t)b) % 0xFFFFFFFEull) + 1u;  // = ((seq64 + b + 1) - 1) % (2^32 - 2) + 1
     if (learning_rates_host) hh.learning_rate = learning_rates_host[b];
+    if (fused) {
+      int32_t handled = 0;
+      const int rc = lrx_ppo_grad_apply_p2p(pol, params, adam_m, adam_v, adam_count, buf, idx + (size_t)b * B, B, B_global,
+                                            adv_sums ? adv_sums + 2 * b : nullptr, &hh, peer_buffers, own_buffer, rank, world,
+                                            seq, stats_out + (size_t)b * LRX_PPO_NSTATS, nonfinite_flag, error_flag,
+                                            workspace, workspace_bytes, stream, &handled);
+      if (rc) return rc;
+      if (handled) continue;
+      fused = false;
+    }
     bool pushed = false;
     int rc = grad_p2p_impl(pol, params, buf, idx + (size_t)b * B, B, B_global, adv_sums ? adv_sums + 2 * b : nullptr, &hh,
                            own_buffer, seq, workspace, workspace_bytes, stream, use_push ? peer_buffers : nullptr, rank, world,
@@ -1292,6 +1328,14 @@ extern "C" int lrx_ppo_grad_apply_p2p(const LrxPolicyDesc* pol, float* params, f
   ap.peers = reinterpret_cast<char* const*>(peer_buffers);
   ap.rank = rank; ap.world = world; ap.slot_b = p2p::slot_bytes(n); ap.seq = seq; ap.error_flag = error_flag;
   ap.gsum = (float*)((char*)workspace + tail.gradbuf_off);
+  {
+    // one flag per rank, published by the last block of the reduction (default); LRX_P2P_FUSED=1: one flag per block
+    const char* e = getenv("LRX_P2P_FUSED");
+    if (!(e && e[0] == '1')) {
+      ap.push = 2;
+      ap.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(own_buffer) + 64);
+    }
+  }
   float* slot = reinterpret_cast<float*>(static_cast<char*>(own_buffer) + p2p::HEADER + (size_t)(seq & 1u) * ap.slot_b);
   bool done = false;
   rc = lrx_ppo_grad_tensor(pol, params, buf, idx, B, B_global, adv_sums, h, slot, workspace, tail.adv_sums_off,
