@@ -468,15 +468,38 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
   if (p2p_on) {
     // LRX_P2P_FUSED=2 (ap.push == 2 here): ONE flag per rank, published by the last block to finish the reduction (ticket),
     // instead of one per block: a single system-scope fence and flag store per rank and minibatch
-    const bool one_flag = ap.push == 2;
-    if (one_flag) __threadfence();
+    // LRX_P2P_FUSED=3 (ap.push == 3): as 2, but PUSH -- the entries also go into every rank's receive area of this rank and
+    // the last block sets this rank's arrival flag in every buffer; receivers poll and sum local memory only
+    const bool fpush = ap.push == 3;
+    const bool one_flag = ap.push == 2 || fpush;
+    if (fpush) {
+      __syncthreads();  // block 0: the statistics and the log_std entry written above
+      const int n_mine = blockIdx.x == 0 ? 32 + LRX_PPO_NSTATS + 1 : 32;
+      if ((int)threadIdx.x < n_mine) {
+        int e = -1;
+        if (threadIdx.x < 32) e = (p < P && p != log_std_off) ? p : -1;
+        else if (threadIdx.x < 32 + LRX_PPO_NSTATS) e = P + ((int)threadIdx.x - 32);
+        else e = log_std_off;  // -1 for Discrete policies
+        if (e >= 0) {
+          const float val = threadIdx.x < 32 ? t : gradbuf[e];
+          for (int r = 0; r < ap.world; ++r) p2p::push_recv(ap.peers[r], ap.slot_b, ap.seq, ap.rank)[e] = val;
+        }
+      }
+      __threadfence_system();
+    } else if (one_flag) {
+      __threadfence();
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       if (one_flag) {
         if (atomicAdd(ap.ticket, 1u) == gridDim.x - 1) {
           *ap.ticket = 0u;
           __threadfence_system();
-          p2p::st_release_sys(reinterpret_cast<uint32_t*>(ap.peers[ap.rank]), ap.seq);
+          if (fpush) {
+            for (int r = 0; r < ap.world; ++r) p2p::st_release_sys(p2p::push_flag(ap.peers[r], ap.rank), ap.seq);
+          } else {
+            p2p::st_release_sys(reinterpret_cast<uint32_t*>(ap.peers[ap.rank]), ap.seq);
+          }
         }
       } else {
         __threadfence_system();
@@ -484,9 +507,15 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
       }
     }
     int timed_out = 0;
-    if ((int)threadIdx.x < ap.world) {
-      const uint32_t* flag = one_flag ? reinterpret_cast<const uint32_t*>(ap.peers[threadIdx.x])
-                                      : p2p::block_flag(ap.peers[threadIdx.x], ap.seq, blockIdx.x);
+    // one_flag: only block 0 polls the peers' flags over NVLink (G threads per rank; every block polling them was 218 us
+    // per minibatch at 8 GPUs against 201 us for the three-call path) and relays "everyone has arrived" through a flag in
+    // LOCAL memory (own buffer, offset 72) that the other blocks poll
+    uint32_t* relay = reinterpret_cast<uint32_t*>(ap.peers[ap.rank] + 72);
+    const bool remote_poller = !one_flag || blockIdx.x == 0;
+    if (remote_poller && (int)threadIdx.x < ap.world) {
+      const uint32_t* flag = fpush      ? p2p::push_flag(ap.peers[ap.rank], (int)threadIdx.x)  // local
+                             : one_flag ? reinterpret_cast<const uint32_t*>(ap.peers[threadIdx.x])
+                                        : p2p::block_flag(ap.peers[threadIdx.x], ap.seq, blockIdx.x);
       const long long t0 = clock64();
       while ((int32_t)(p2p::ld_acquire_sys(flag) - ap.seq) < 0) {
         if (clock64() - t0 > 20000000000LL) {  // a peer is gone -- report instead of hanging the GPU
@@ -494,17 +523,39 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, long long 
           timed_out = 1;
           break;
         }
-        __nanosleep(200);
+        if (!fpush) __nanosleep(200);
+      }
+    }
+    if (one_flag) {
+      if (blockIdx.x == 0) {
+        const int lost = __syncthreads_or(timed_out);
+        if (threadIdx.x == 0) p2p::st_release_sys(relay, lost ? 0xFFFFFFFFu : ap.seq);  // all ones: a peer is gone
+        timed_out = lost;
+      } else if (threadIdx.x == 0) {
+        uint32_t v;
+        while ((int32_t)((v = p2p::ld_acquire_sys(relay)) - ap.seq) < 0 && v != 0xFFFFFFFFu) __nanosleep(100);
+        timed_out = (v == 0xFFFFFFFFu) ? 1 : 0;
       }
     }
     peer_lost = __syncthreads_or(timed_out) != 0;
     if (!peer_lost) {
-      if (rg == 0 && p < P && p != log_std_off) t = p2p::peer_sum(ap.peers, ap.world, ap.slot_b, ap.seq, p);
+      auto xsum = [&](int e) {  // element e summed over the ranks, in rank order
+        if (!fpush) return p2p::peer_sum(ap.peers, ap.world, ap.slot_b, ap.seq, e);
+        float v[p2p::PUSH_MAX_RANKS], acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < p2p::PUSH_MAX_RANKS; ++r)
+          v[r] = r < ap.world ? p2p::ld_volatile_f32(p2p::push_recv(ap.peers[ap.rank], ap.slot_b, ap.seq, r) + e) : 0.f;
+#pragma unroll
+        for (int r = 0; r < p2p::PUSH_MAX_RANKS; ++r)
+          if (r < ap.world) acc += v[r];
+        return acc;
+      };
+      if (rg == 0 && p < P && p != log_std_off) t = xsum(p);
       if (blockIdx.x == 0 && rg == 1) {  // the statistics and the log_std entry: written by block 0 on every rank
         if (pl < LRX_PPO_NSTATS) {
-          ap.gsum[P + pl] = p2p::peer_sum(ap.peers, ap.world, ap.slot_b, ap.seq, P + pl);
+          ap.gsum[P + pl] = xsum(P + pl);
         } else if (pl == LRX_PPO_NSTATS && log_std_off >= 0) {
-          const float gs = p2p::peer_sum(ap.peers, ap.world, ap.slot_b, ap.seq, log_std_off);
+          const float gs = xsum(log_std_off);
           ap.gsum[log_std_off] = gs;
           const float gl = gs + (-ap.h.entropy_loss_coefficient);
           lsg_ss = (double)gl * gl;
@@ -1332,7 +1383,7 @@ extern "C" int lrx_ppo_grad_apply_p2p(const LrxPolicyDesc* pol, float* params, f
     // one flag per rank, published by the last block of the reduction (default); LRX_P2P_FUSED=1: one flag per block
     const char* e = getenv("LRX_P2P_FUSED");
     if (!(e && e[0] == '1')) {
-      ap.push = 2;
+      ap.push = (e && e[0] == '3' && world <= p2p::PUSH_MAX_RANKS) ? 3 : 2;
       ap.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(own_buffer) + 64);
     }
   }

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Multi-GPU evidence (run with gpurun --gpus 8): c4 strong scaling at 2/4/8, c2 weak scaling at 8 (the 2-GPU p2p parity
-# test and c4 / c2 at N = 1 run in the single-GPU calls).  Outputs: gpurun_out/mg/*
+# Multi-GPU evidence (run with gpurun --gpus 8): c2 weak scaling and c4 strong scaling at 8 GPUs (smaller N: separate calls).
+# Outputs: gpurun_out/mg/*
 O=gpurun_out/mg; mkdir -p $O
 run() { # name gpus args...
   local name=$1 n=$2; shift 2
@@ -8,8 +8,5 @@ run() { # name gpus args...
     bench.py --gpus $n --steps 3 --warmup 3 --no-cpu-baseline "$@" > $O/$name.json 2> $O/$name.err
   echo "$name rc=$?"; tail -c 300 $O/$name.json
 }
-nvidia-smi -L | head -8
 run c2_n8 8 --config c2
-run c4_n8 8 --config c4
-run c4_n4 4 --config c4
-run c4_n2 2 --config c4
+
