@@ -8,5 +8,11 @@ run() { # name gpus args...
     bench.py --gpus $n --steps 3 --warmup 3 --no-cpu-baseline "$@" > $O/$name.json 2> $O/$name.err
   echo "$name rc=$?"; tail -c 300 $O/$name.json
 }
-run c2_n8 8 --config c2
-
+for c in "$@"; do
+  case $c in
+    c2_n8) run c2_n8 8 --config c2;;
+    c4_n8) run c4_n8 8 --config c4;;
+    c4_n4) run c4_n4 4 --config c4;;
+    c4_n2) run c4_n2 2 --config c4;;
+  esac
+done
