@@ -1308,9 +1308,9 @@ extern "C" int lrx_ppo_update_p2p(const LrxPolicyDesc* pol, float* params, float
   LrxPpoHyper hh = *h;
   // LRX_P2P_PUSH=1: push exchange (p2p::PUSH_MAX_RANKS receive areas per slot).  Measured equal to the pull protocol at 2
   // GPUs (197.7 vs 197.3 - 200 us per minibatch), so the simpler pull protocol stays the default.
-  static int push_env = -1;
-  if (push_env < 0) {
-    const char* e = getenv("LRX_P2P_PUSH");
+  int push_env = 0;
+  {
+    const char* e = getenv("LRX_P2P_PUSH");  // read per call (once per epoch): the tests switch variants within a process
     push_env = (e && e[0] == '1') ? 1 : 0;
   }
   const bool use_push = push_env && world <= p2p::PUSH_MAX_RANKS;
