@@ -338,11 +338,13 @@ int lrx_ppo_update_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, f
                        void* workspace, size_t workspace_bytes, lrx_stream_t stream);
 
 /* One minibatch of the multi-GPU update in two launches (default-width policies): lrx_ppo_grad's gradient kernel, then ONE
- * cooperative kernel that reduces the per-CTA partials into this rank's exchange slot `seq & 1`, publishes and awaits the
- * peers block by block (per-block flags in the exchange buffer's header), sums the slots in rank order and applies
- * clip + Adam (backward -> gradient SUM over the ranks -> train_batch, ppo.py:469-492).  `peer_buffers` is the DEVICE array
- * of the G exchange buffers (lrx_p2p_alloc / lrx_p2p_open), `own_buffer` this rank's.  *handled = 0 and nothing is enqueued
- * for policies the fused gradient kernels do not cover (run lrx_ppo_grad + lrx_ppo_apply_p2p instead). */
+ * cooperative kernel that reduces the per-CTA partials into this rank's exchange slot `seq & 1`, publishes ONE flag per rank
+ * (the last block to finish the reduction), waits for the peers (block 0 polls their flags over NVLink and relays the
+ * arrival through a flag in local memory), sums the slots in rank order and applies clip + Adam (backward -> gradient SUM
+ * over the ranks -> train_batch, ppo.py:469-492).  `peer_buffers` is the DEVICE array of the G exchange buffers
+ * (lrx_p2p_alloc / lrx_p2p_open), `own_buffer` this rank's.  *handled = 0 and nothing is enqueued for policies the fused
+ * gradient kernels do not cover (run lrx_ppo_grad_p2p + lrx_ppo_apply_p2p instead).  Environment: LRX_P2P_FUSED=1 one flag
+ * per block, =3 push variant (both measured slower, profiles/r2_configs.md). */
 int lrx_ppo_grad_apply_p2p(const LrxPolicyDesc* pol, float* params, float* adam_m, float* adam_v, int32_t* adam_count,
                            const LrxBatchView* buf, const int32_t* idx, int64_t B, int64_t B_global,
                            const double* adv_sums, const LrxPpoHyper* h, void* const* peer_buffers, void* own_buffer,

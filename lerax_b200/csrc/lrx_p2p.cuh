@@ -9,6 +9,8 @@ namespace p2p {
 // Buffer = [global flag (uint32 at offset 0), padded to a line | per-block flags of slot 0 | of slot 1 | slot 0 | slot 1].
 // The global flag serves lrx_p2p_allreduce / lrx_ppo_apply_p2p (whole-slot publish); the per-block flags serve the fused
 // reduce + exchange + apply kernel of lrx_ppo_grad_apply_p2p, where block b of a rank only depends on block b of its peers.
+// Inside the global flag's line: +64 the ticket of the reduction kernel (which block finishes last), +72 the relay flag
+// ("every peer has arrived", written by block 0, polled locally by the other blocks); both zeroed by lrx_p2p_alloc.
 constexpr int MAX_BLOCK_FLAGS = 1024;
 constexpr size_t GLOBAL_FLAG_BYTES = 128;
 // PUSH exchange (the default of lrx_ppo_update_p2p for up to PUSH_MAX_RANKS ranks): a rank WRITES its reduced gradient
