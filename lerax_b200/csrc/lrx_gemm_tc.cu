@@ -182,6 +182,10 @@ template <bool SWAP, bool X_MN, bool Y_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const GemmArgs g, const int x_al16, const int y_al16, const int persistent) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  // programmatic dependent launch: a layer-by-layer update is 30 dependent launches per minibatch; this grid may be set up
+  // while the previous GEMM drains (nothing of its output is read before the wait)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_MISC);  // [2]: the MMAs that read operand stage s are done
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 16);
@@ -438,8 +442,17 @@ int launch(const GemmArgs& g, int splits, cudaStream_t s) {
     const int slots = lrx_sm_count() / (splits > 0 ? splits : 1);
     gx = x_tiles < slots ? x_tiles : (slots > 0 ? slots : 1);
   }
-  dim3 grid(gx, y_tiles, splits);
-  tc_gemm_kernel<SWAP, X_MN, Y_MN><<<grid, THREADS, SMEM_BYTES, s>>>(g, aligned16(xb, xl), aligned16(yb, yl), persistent);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, y_tiles, splits);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = lrx_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LRX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<SWAP, X_MN, Y_MN>, g, aligned16(xb, xl), aligned16(yb, yl), persistent));
   return LRX_OK;
 }
 
