@@ -195,34 +195,52 @@ __global__ void __launch_bounds__(THREADS, 1) ppo_grad_tc128c_kernel(const __gri
     //   W2 [16][64] | Wv0 [64][16] | Wa0 [64][16] | Wa1 [16][64] | Wmap [8][16] (rows >= n_out zero) | b2 [16] | ba1 [16]
     float* cs = reinterpret_cast<float*>(smem + OFF_DY64);
     constexpr int CS_W2 = 0, CS_WV0 = 1024, CS_WA0 = 2048, CS_WA1 = 3072, CS_WMAP = 4096, CS_B2 = 4224, CS_BA1 = 4240, CS_N = 4256;
-    for (int i = tid; i < CS_N; i += THREADS) {
-      float x;
-      if (i < CS_WV0) x = __ldg(a.params + a.lo.w[tc::L_ENC2] + i);
-      else if (i < CS_WA0) x = __ldg(a.params + a.lo.w[tc::L_V0] + (i - CS_WV0));
-      else if (i < CS_WA1) x = __ldg(a.params + a.lo.w[tc::L_A0] + (i - CS_WA0));
-      else if (i < CS_WMAP) x = __ldg(a.params + a.lo.w[tc::L_A1] + (i - CS_WA1));
-      else if (i < CS_B2) x = (i - CS_WMAP) < n_out * 16 ? __ldg(a.params + a.lo.w[tc::L_MAP] + (i - CS_WMAP)) : 0.f;
-      else if (i < CS_BA1) x = __ldg(a.params + a.lo.b[tc::L_ENC2] + (i - CS_B2));
-      else x = __ldg(a.params + a.lo.b[tc::L_A1] + (i - CS_BA1));
-      cs[i] = x;
+    // Source address by selection, every load of the thread issued before the first store: as a loop of load -> store
+    // with a branch per range (what the compiler makes of the obvious form) these were ten dependent L2 round trips per
+    // launch.  nullptr = the entry is a constant zero (skip = false) or is not written here (skip = true).
+    constexpr int CS_PER = (CS_N + THREADS - 1) / THREADS, FP_PER = (F_COUNT + THREADS - 1) / THREADS;
+    float xc[CS_PER], xf[FP_PER];
+    bool skip_f[FP_PER];
+#pragma unroll
+    for (int k = 0; k < CS_PER; ++k) {
+      const int i = tid + k * THREADS;
+      const float* src = nullptr;
+      if (i < CS_WV0) src = a.params + a.lo.w[tc::L_ENC2] + i;
+      else if (i < CS_WA0) src = a.params + a.lo.w[tc::L_V0] + (i - CS_WV0);
+      else if (i < CS_WA1) src = a.params + a.lo.w[tc::L_A0] + (i - CS_WA0);
+      else if (i < CS_WMAP) src = a.params + a.lo.w[tc::L_A1] + (i - CS_WA1);
+      else if (i < CS_B2) src = (i - CS_WMAP) < n_out * 16 ? a.params + a.lo.w[tc::L_MAP] + (i - CS_WMAP) : nullptr;
+      else if (i < CS_BA1) src = a.params + a.lo.b[tc::L_ENC2] + (i - CS_B2);
+      else if (i < CS_N) src = a.params + a.lo.b[tc::L_A1] + (i - CS_BA1);
+      xc[k] = src ? __ldg(src) : 0.f;
     }
     // fp32 parameter block, except the composite biases
-    for (int i = tid; i < F_COUNT; i += THREADS) {
-      float x = 0.f;
-      if (i < FB1) x = __ldg(a.params + a.lo.b[tc::L_ENC0] + i);
-      else if (i < FBCV) x = __ldg(a.params + a.lo.b[tc::L_ENC1] + (i - FB1));
-      else if (i < FBV1) continue;
-      else if (i < FBCA) x = __ldg(a.params + a.lo.b[tc::L_V1] + (i - FBV1));
-      else if (i < FBV2) continue;
-      else if (i < FBCM) x = (i == FBV2) ? __ldg(a.params + a.lo.b[tc::L_V2]) : 0.f;
-      else if (i < FWV2) continue;
-      else if (i < FW0) x = __ldg(a.params + a.lo.w[tc::L_V2] + (i - FWV2));
-      else {
-        const int o = (i - FW0) >> 3, k = (i - FW0) & 7;
-        x = k < a.obs_dim ? __ldg(a.params + a.lo.w[tc::L_ENC0] + o * a.obs_dim + k) : 0.f;
+#pragma unroll
+    for (int k = 0; k < FP_PER; ++k) {
+      const int i = tid + k * THREADS;
+      const float* src = nullptr;
+      bool skip = i >= F_COUNT;
+      if (i < FB1) src = a.params + a.lo.b[tc::L_ENC0] + i;
+      else if (i < FBCV) src = a.params + a.lo.b[tc::L_ENC1] + (i - FB1);
+      else if (i < FBV1) skip = true;
+      else if (i < FBCA) src = a.params + a.lo.b[tc::L_V1] + (i - FBV1);
+      else if (i < FBV2) skip = true;
+      else if (i < FBCM) src = (i == FBV2) ? a.params + a.lo.b[tc::L_V2] : nullptr;
+      else if (i < FWV2) skip = true;
+      else if (i < FW0) src = a.params + a.lo.w[tc::L_V2] + (i - FWV2);
+      else if (i < F_COUNT) {
+        const int o = (i - FW0) >> 3, kk = (i - FW0) & 7;
+        src = kk < a.obs_dim ? a.params + a.lo.w[tc::L_ENC0] + o * a.obs_dim + kk : nullptr;
       }
-      fp[i] = x;
+      xf[k] = (src && !skip) ? __ldg(src) : 0.f;
+      skip_f[k] = skip;
     }
+#pragma unroll
+    for (int k = 0; k < CS_PER; ++k)
+      if (tid + k * THREADS < CS_N) cs[tid + k * THREADS] = xc[k];
+#pragma unroll
+    for (int k = 0; k < FP_PER; ++k)
+      if (!skip_f[k]) fp[tid + k * THREADS] = xf[k];
 #pragma unroll
     for (int k = 0; k < PER; ++k)
       if (mi[k] >= 0) tc2::store8(mi[k] ? WV1 : W1, cc[k], oo[k], v[k]);
